@@ -1,0 +1,146 @@
+"""Pins the CPU oracle (oracle/stereo_oracle.c) -- no GPU needed.
+
+(1) against the reference's own goldens (test/UTest.cpp:247-256: left/right-0022_rect.png),
+(2) against committed cv2 vectors (tests/golden/cv2_golden.npz, made by make_golden.py),
+(3) against the live OpenCV build (cv2) on seeded inputs and a parameter sweep.
+Everything is bit-exact (integer / byte work); the float stages are compared bit-for-bit as well.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O, cv2_ref as CV, synth
+
+cv2 = pytest.importorskip("cv2")
+
+
+def test_rectify_matches_reference_goldens(fixtures, calib):
+    # RectifyMonoCpu (test/UTest.cpp:247-260): rectified raw == *_rect.png, bit-exact
+    for side in ("left", "right"):
+        out = O.rectify(fixtures[side + "_raw"], **calib[side])
+        assert np.array_equal(out, fixtures[side + "_rect"]), side
+
+
+@pytest.mark.parametrize("size", [(752, 480), (1242, 375), (1280, 720), (1920, 1080)])
+def test_rect_map_matches_cv2(size):
+    W, H = size
+    cal = synth.scaled_calibration(W, H)
+    for side in ("left", "right"):
+        c = cal[side]
+        mx, my = O.build_rect_map(c["K"], c["D"], c["R"], c["P"], W, H)
+        cx, cy = CV.rect_maps(c["K"], c["D"], c["R"], c["P"], W, H)
+        # the fixed-point coordinates (what remap consumes) must be identical; at most a couple of
+        # floats may differ in the last ulp
+        fx = lambda m: np.rint(m * np.float32(32)).astype(np.int64)
+        assert np.array_equal(fx(mx), fx(cx)) and np.array_equal(fx(my), fx(cy))
+        assert (mx != cx).sum() + (my != cy).sum() <= 4
+
+
+def test_remap_matches_cv2_random():
+    rng = np.random.default_rng(7)
+    src = rng.integers(0, 256, (300, 400), dtype=np.uint8)
+    mx = (rng.random((200, 320), dtype=np.float32) * 420 - 10).astype(np.float32)
+    my = (rng.random((200, 320), dtype=np.float32) * 320 - 10).astype(np.float32)
+    assert np.array_equal(O.remap_linear(src, mx, my), cv2.remap(src, mx, my, cv2.INTER_LINEAR))
+    src3 = rng.integers(0, 256, (300, 400, 3), dtype=np.uint8)
+    assert np.array_equal(O.remap_linear(src3, mx, my), cv2.remap(src3, mx, my, cv2.INTER_LINEAR))
+
+
+def test_prefilter_norm_fast_equals_definition():
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (61, 83), dtype=np.uint8)
+    for ps, cap in [(5, 31), (9, 31), (21, 63), (33, 10)]:
+        assert np.array_equal(O.prefilter_norm(img, ps, cap, fast=True), O.prefilter_norm(img, ps, cap, fast=False))
+
+
+def test_stereobm_matches_committed_cv2_vectors(fixtures, cv2_golden):
+    pairs = {"0022": (fixtures["left_rect"], fixtures["right_rect"]), "aloe": (fixtures["aloe_L"], fixtures["aloe_R"])}
+    for name, m in cv2_golden["meta"].items():
+        p = O.BMParams(**m["params"])
+        L, R = pairs[m["pair"]]
+        assert np.array_equal(O.stereobm_compute(L, R, p), cv2_golden["disp_" + name]), name
+
+
+SWEEP = [
+    dict(), dict(numDisparities=128, blockSize=15, speckleWindowSize=100, speckleRange=4),
+    dict(preFilterType=0, preFilterSize=9), dict(minDisparity=-16, numDisparities=64, blockSize=11),
+    dict(numDisparities=16, blockSize=5, minDisparity=-10, disp12MaxDiff=2),
+    dict(numDisparities=16, blockSize=21, minDisparity=-40, disp12MaxDiff=1),
+    dict(numDisparities=32, blockSize=9, minDisparity=-32, uniquenessRatio=0),
+    dict(numDisparities=64, blockSize=9, disp12MaxDiff=0, speckleWindowSize=50, speckleRange=2, minDisparity=-5),
+    dict(numDisparities=112, blockSize=7, uniquenessRatio=5, disp12MaxDiff=1, textureThreshold=0),
+    dict(numDisparities=32, blockSize=51, preFilterCap=63, uniquenessRatio=30),
+    dict(blockSize=25, preFilterType=0, preFilterSize=21), dict(numDisparities=48, blockSize=5, preFilterCap=1, textureThreshold=0),
+]
+
+
+@pytest.mark.parametrize("kw", SWEEP)
+def test_stereobm_matches_live_cv2_synthetic(kw):
+    p = O.BMParams(**kw)
+    L, R = synth.synth_pair(400, 211, max(p.numDisparities, 16), seed=11)  # odd height on purpose (x-Sobel quirk)
+    assert np.array_equal(O.stereobm_compute(L, R, p), CV.stereobm_compute(L, R, p))
+
+
+def test_stereobm_positive_mindisparity_parity_domain():
+    # upstream writes minD columns past the row end for minD > 0: parity on X >= minD only
+    p = O.BMParams(minDisparity=32, numDisparities=64, blockSize=15)
+    L, R = synth.synth_pair(500, 200, 96, seed=5)
+    a, b = O.stereobm_compute(L, R, p), CV.stereobm_compute(L, R, p)
+    assert np.array_equal(a[:, 32:], b[:, 32:])
+
+
+def test_stereobm_full_size_kitti_shape():
+    p = O.BMParams(numDisparities=128, blockSize=15, speckleWindowSize=100, speckleRange=4)
+    L, R = synth.synth_pair(1242, 375, 128, seed=2000)
+    assert np.array_equal(O.stereobm_compute(L, R, p), CV.stereobm_compute(L, R, p))
+
+
+def test_parameter_validation_mirrors_cv2():
+    L, R = synth.synth_pair(64, 48, 16, seed=1)
+    for kw in [dict(numDisparities=24), dict(blockSize=4), dict(blockSize=49), dict(preFilterCap=64), dict(preFilterCap=0),
+               dict(preFilterSize=4), dict(preFilterSize=257), dict(textureThreshold=-1), dict(uniquenessRatio=-1),
+               dict(preFilterType=2), dict(numDisparities=-16)]:
+        base = dict(numDisparities=16, blockSize=9)
+        base.update(kw)
+        p = O.BMParams(**base)
+        with pytest.raises(ValueError):
+            O.stereobm_compute(L, R, p)
+        with pytest.raises(cv2.error):
+            CV.stereobm_compute(L, R, p)
+
+
+def test_speckle_matches_cv2(cv2_golden):
+    src = cv2_golden["speckle_in"]
+    assert np.array_equal(O.filter_speckles(src, -16, 100, 4), cv2_golden["speckle_out_100_4"])
+    assert np.array_equal(O.filter_speckles(src, -16, 800, 80), cv2_golden["speckle_out_800_80"])
+    assert np.array_equal(O.filter_speckles(src, -16, 30, 0), CV.filter_speckles(src, -16, 30, 0))
+    u8flow = (np.maximum(src, 0) >> 4).astype(np.int16)  # reference GPU flow: integer disparities, newVal 0
+    assert np.array_equal(O.filter_speckles(u8flow, 0, 200, 5), CV.filter_speckles(u8flow, 0, 200, 5))
+
+
+def test_reproject_and_pack(fixtures, cv2_golden):
+    Q = O.stereo_Q(fixtures["left_P"], fixtures["right_P"])
+    assert np.array_equal(Q, cv2_golden["Q"])
+    d = cv2_golden["disp_nd128_b15_uniq_speckle"]
+    df = O.disparity_to_float(d, fixtures["left_P"][2] - fixtures["right_P"][2])
+    assert np.array_equal(df, cv2_golden["df_nd128"])
+    xyz = O.reproject(df, Q)
+    assert np.array_equal(xyz[::4, ::4].view(np.uint32), cv2_golden["xyz_nd128"].view(np.uint32))
+    assert np.array_equal(xyz.view(np.uint32), CV.reproject(df, Q).view(np.uint32))
+    # a Q with a principal-point offset between the cameras (cx != cx')
+    Q2 = Q.copy(); Q2[3, 3] = Q[3, 2] * -3.25
+    df2 = O.disparity_to_float(d, 3.25)
+    assert np.array_equal(O.reproject(df2, Q2).view(np.uint32), CV.reproject(df2, Q2).view(np.uint32))
+    pc = O.pack_pointcloud2(xyz, fixtures["left_rect"])
+    rec = pc.reshape(-1, 32)
+    f = rec[:, :12].copy().view(np.float32).reshape(-1, 3)
+    valid = (xyz[..., 2].ravel() != 10000.0) & ~np.isinf(xyz[..., 2].ravel())
+    assert np.array_equal(f[valid].view(np.uint32), xyz.reshape(-1, 3)[valid].view(np.uint32))
+    assert np.isnan(f[~valid]).all()
+    assert (rec[:, 12:16] == 0).all() and (rec[:, 19:] == 0).all()
+    g = fixtures["left_rect"].ravel()
+    assert (rec[:, 16] == g).all() and (rec[:, 17] == g).all() and (rec[:, 18] == g).all()
+
+
+def test_valid_window_formula():
+    # GpuSenderDisparity.cpp:30-39
+    assert O.valid_window(752, 480, 0, 64, 21) == dict(x_offset=73, y_offset=10, width=752 - 1 - 10 - 73, height=480 - 1 - 10 - 10)
