@@ -1,0 +1,71 @@
+// Internal launcher interface between the host pipeline (api.cu) and the sm_100a kernels.
+// Every function enqueues work on `st` and returns the number of kernels it launched (>= 0) or a
+// negative value when the launch configuration is impossible (caller maps it to B200S_E*).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200s {
+
+struct CamModel {          // one camera: K, D and ir = inv(P[:, :3] * R) (FP64, host-computed)
+    double fx, fy, cx, cy;
+    double k1, k2, p1, p2, k3, k4, k5, k6;
+    double ir[9];
+};
+
+struct BMConfig {          // cv::StereoBM state actually used by the matcher
+    int minD, nd, wsz, cap, textureThreshold, uniquenessRatio, disp12MaxDiff;
+};
+
+// ---- rectify.cu -------------------------------------------------------------------------------------
+// fixed-point map: map[y*W+x] = (sx, sy) = (rint(u*32), rint(v*32)) of cv::initUndistortRectifyMap
+int launch_build_map(const CamModel& cm, int W, int H, int2* map, cudaStream_t st);
+// cv::remap INTER_LINEAR / BORDER_CONSTANT(0); ch = 1 or 3 interleaved. map == nullptr -> evaluate the map on the fly.
+int launch_remap(const uint8_t* src, int sW, int sH, int ch, const int2* map, const CamModel& cm,
+                 uint8_t* dst, int W, int H, cudaStream_t st);
+// fused rectify (mono) + x-Sobel prefilter: writes the rectified plane and the prefiltered plane in one kernel
+int launch_rectify_xsobel(const uint8_t* src, int sW, int sH, const int2* map, const CamModel& cm,
+                          uint8_t* rect, uint8_t* pre, int W, int H, int cap, cudaStream_t st);
+int launch_remap_nearest(const uint8_t* src, int sW, int sH, int ch, const int2* map, const CamModel& cm,
+                         uint8_t* dst, int W, int H, cudaStream_t st);
+
+// ---- prefilter.cu -----------------------------------------------------------------------------------
+int launch_prefilter_xsobel(const uint8_t* src, uint8_t* dst, int W, int H, int cap, cudaStream_t st);
+// scratch: W*H int32
+int launch_prefilter_norm(const uint8_t* src, uint8_t* dst, int W, int H, int ps, int cap, int* scratch, cudaStream_t st);
+int launch_bgr_to_gray(const uint8_t* src, uint8_t* dst, int n, int rgb_order, cudaStream_t st);
+int launch_gray_to_bgr(const uint8_t* src, uint8_t* dst, int n, cudaStream_t st);
+int launch_swap_rb(const uint8_t* src, uint8_t* dst, int n, cudaStream_t st);
+
+// ---- bm_sad.cu --------------------------------------------------------------------------------------
+struct BMScratch {         // device scratch owned by the caller
+    int* vol;              // generic-path cost volume
+    size_t vol_bytes;
+};
+// Full matcher on prefiltered planes: fills disp (s16, every pixel) and, if cost != nullptr, the s16 cost plane.
+// When cfg.disp12MaxDiff < 0 the valid-ROI mask is applied directly (pixels outside are FILTERED);
+// otherwise all columns [lofs, lofs+width1) of the ROI rows are produced and the caller runs validate + mask.
+// evals (optional) receives the number of (pixel, disparity) evaluations inside the valid ROI.
+int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, int W, int H, const BMConfig& cfg,
+                       int16_t* disp, int16_t* cost, BMScratch* scratch, cudaStream_t st, double* evals);
+size_t bm_scratch_bytes(int W, int H, const BMConfig& cfg);
+
+// ---- post.cu ----------------------------------------------------------------------------------------
+int launch_validate_disp12(int16_t* disp, const int16_t* cost, int W, int H, const BMConfig& cfg, cudaStream_t st);
+int launch_roi_mask(int16_t* disp, int W, int H, const BMConfig& cfg, cudaStream_t st);
+// scratch: 2 * W*H int32 (labels, sizes)
+int launch_filter_speckles(int16_t* img, int W, int H, int newVal, int maxSize, int maxDiff, int* scratch, cudaStream_t st);
+
+// ---- reproject.cu -----------------------------------------------------------------------------------
+// d16 -> f32 (d/16 - cxd); also reduces min(d16) into *min_d16 (device int, must be preset to INT_MAX by this call)
+int launch_disparity_to_float(const int16_t* d16, float* df, int n, double cxd, int* min_d16, cudaStream_t st);
+// cv::reprojectImageTo3D(handleMissingValues=true) fused with PointCloud2 packing.
+// xyz (f32 x3, optional) and pc2 (32 B records, optional); color: ch = 1 (mono replicated) or 3 (BGR)
+int launch_reproject_pack(const int16_t* d16, int W, int H, double cxd, const double* Q, const int* min_d16,
+                          const uint8_t* color, int ch, float* xyz, uint8_t* pc2, cudaStream_t st);
+int launch_disparity_color(const int16_t* d16, uint8_t* bgra, int n, int nd, cudaStream_t st);
+
+// ---- intpeak.cu -------------------------------------------------------------------------------------
+int run_int_peak(int which, double* lane_ops_per_s, double* sm_mhz, cudaStream_t st);
+
+}  // namespace b200s

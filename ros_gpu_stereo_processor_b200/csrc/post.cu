@@ -1,0 +1,168 @@
+// Post-filters of cv::StereoBM::compute for sm_100a: L/R consistency (cv::validateDisparity), valid-ROI mask,
+// speckle filter (cv::filterSpeckles) as connected-component labelling.  SURVEY.md A.2.6, A.3, A.4.
+// Reference call sites: block_matcher_cpu_->setDisp12MaxDiff (src/GPUStereoProcessor.cpp:23),
+// filterSpeckles (src/GPUStereoProcessor.cpp:356-385, a host flood fill behind a stream sync in the reference).
+#include "kernels.h"
+
+#include <algorithm>
+
+namespace b200s {
+
+// ---- validateDisparity: one block per row ---------------------------------------------------------------
+// pass 1 is a scatter-min: the sequential rule "c2[x2] > c (strict), x ascending" keeps the smallest cost and,
+// among equal costs, the smallest x  ==  atomicMin over the key (cost + 32768) << 16 | x.
+__global__ void __launch_bounds__(256) validate_kernel(int16_t* __restrict__ disp, const int16_t* __restrict__ cost,
+                                                       int W, int minD, int nd, int maxdiff16, int ya)
+{
+    extern __shared__ uint32_t vsm[];
+    uint32_t* key = vsm;                 // [W]
+    int16_t* d2 = (int16_t*)(vsm + W);   // [W]
+    const int y = ya + blockIdx.x;
+    int16_t* dp = disp + (size_t)y * W;
+    const int16_t* cp = cost + (size_t)y * W;
+    const int INV = (minD - 1) * 16;
+    const int maxD = minD + nd;
+    const int minX1 = max(maxD, 0), maxX1 = W + min(minD, 0);
+    for (int x = threadIdx.x; x < W; x += blockDim.x) key[x] = 0xFFFFFFFFu;
+    __syncthreads();
+    for (int x = minX1 + threadIdx.x; x < maxX1; x += blockDim.x) {
+        int d = dp[x];
+        if (d == INV) continue;
+        int x2 = x - ((d + 8) >> 4);
+        if ((unsigned)x2 >= (unsigned)W) continue;
+        uint32_t k = ((uint32_t)((int)cp[x] + 32768) << 16) | (uint32_t)x;
+        atomicMin(&key[x2], k);
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        uint32_t k = key[x];
+        d2[x] = (k == 0xFFFFFFFFu) ? (int16_t)INV : dp[k & 0xFFFFu];
+    }
+    __syncthreads();
+    for (int x = minX1 + threadIdx.x; x < maxX1; x += blockDim.x) {
+        int d = dp[x];
+        if (d == INV) continue;
+        int d0 = d >> 4, d1 = (d + 15) >> 4;
+        int x0 = x - d0, x1 = x - d1;
+        bool b0 = (unsigned)x0 < (unsigned)W && d2[x0] > INV && abs((int)d2[x0] - d) > maxdiff16;
+        bool b1 = (unsigned)x1 < (unsigned)W && d2[x1] > INV && abs((int)d2[x1] - d) > maxdiff16;
+        if (b0 && b1) dp[x] = (int16_t)INV;
+    }
+}
+
+__global__ void __launch_bounds__(256) roi_mask_kernel(int16_t* __restrict__ disp, int W, int H, int x0, int x1, int y0,
+                                                       int y1, int16_t filtered)
+{
+    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    if (!(x >= x0 && x < x1 && y >= y0 && y < y1)) disp[(size_t)y * W + x] = filtered;
+}
+
+// ---- speckle filter: union-find connected components over the 4-neighbourhood ---------------------------
+// nodes: pixels != newVal; edge between 4-neighbours when |a - b| <= maxDiff.  A component of size <= maxSize is
+// set to newVal.  Component membership and sizes are order independent, so this equals OpenCV's flood fill.
+__device__ __forceinline__ int uf_find(int* L, int i)
+{
+    int p = L[i];
+    while (p != i) {
+        int gp = L[p];
+        if (gp != p) L[i] = gp;   // path halving (benign race: only ever shortens towards a root)
+        i = p;
+        p = gp;
+    }
+    return i;
+}
+
+__device__ __forceinline__ void uf_union(int* L, int a, int b)
+{
+    while (true) {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }   // a > b: hook the larger root under the smaller
+        int old = atomicCAS(&L[a], a, b);   // succeeds only while a is still a root
+        if (old == a) return;
+        a = old;   // somebody else hooked a first; retry from its new parent
+    }
+}
+
+__global__ void __launch_bounds__(256) ccl_init_kernel(const int16_t* __restrict__ img, int* __restrict__ L,
+                                                       int* __restrict__ sz, int n, int newVal)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    L[i] = (img[i] != newVal) ? i : -1;
+    sz[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) ccl_merge_kernel(const int16_t* __restrict__ img, int* __restrict__ L, int W,
+                                                        int H, int newVal, int maxDiff)
+{
+    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    int i = y * W + x;
+    int v = img[i];
+    if (v == newVal) return;
+    if (x + 1 < W) {
+        int u = img[i + 1];
+        if (u != newVal && abs(u - v) <= maxDiff) uf_union(L, i, i + 1);
+    }
+    if (y + 1 < H) {
+        int u = img[i + W];
+        if (u != newVal && abs(u - v) <= maxDiff) uf_union(L, i, i + W);
+    }
+}
+
+__global__ void __launch_bounds__(256) ccl_count_kernel(int* __restrict__ L, int* __restrict__ sz, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || L[i] < 0) return;
+    int root = uf_find(L, i);
+    L[i] = root;
+    atomicAdd(&sz[root], 1);
+}
+
+__global__ void __launch_bounds__(256) ccl_apply_kernel(int16_t* __restrict__ img, const int* __restrict__ L,
+                                                        const int* __restrict__ sz, int n, int newVal, int maxSize)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int root = L[i];
+    if (root >= 0 && sz[root] <= maxSize) img[i] = (int16_t)newVal;
+}
+
+static inline dim3 grid2d(int W, int H) { return dim3((W + 31) / 32, (H + 7) / 8); }
+
+int launch_validate_disp12(int16_t* disp, const int16_t* cost, int W, int H, const BMConfig& cfg, cudaStream_t st)
+{
+    int r = cfg.wsz / 2;
+    int y0 = r, y1 = H - r;
+    if (y1 <= y0 || W > 65535) return y1 <= y0 ? 0 : -1;
+    size_t smem = (size_t)W * 4 + (size_t)W * 2 + 16;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(validate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    validate_kernel<<<y1 - y0, 256, smem, st>>>(disp, cost, W, cfg.minD, cfg.nd, cfg.disp12MaxDiff * 16, y0);
+    return 1;
+}
+
+int launch_roi_mask(int16_t* disp, int W, int H, const BMConfig& cfg, cudaStream_t st)
+{
+    int r = cfg.wsz / 2;
+    int x0 = std::max(cfg.minD + cfg.nd - 1, 0) + r, x1 = W - r, y0 = r, y1 = H - r;
+    roi_mask_kernel<<<grid2d(W, H), 256, 0, st>>>(disp, W, H, x0, x1, y0, y1, (int16_t)((cfg.minD - 1) * 16));
+    return 1;
+}
+
+int launch_filter_speckles(int16_t* img, int W, int H, int newVal, int maxSize, int maxDiff, int* scratch, cudaStream_t st)
+{
+    int n = W * H;
+    int* L = scratch;
+    int* sz = scratch + n;
+    int nb = (n + 255) / 256;
+    ccl_init_kernel<<<nb, 256, 0, st>>>(img, L, sz, n, newVal);
+    ccl_merge_kernel<<<grid2d(W, H), 256, 0, st>>>(img, L, W, H, newVal, maxDiff);
+    ccl_count_kernel<<<nb, 256, 0, st>>>(L, sz, n);
+    ccl_apply_kernel<<<nb, 256, 0, st>>>(img, L, sz, n, newVal, maxSize);
+    return 4;
+}
+
+}  // namespace b200s

@@ -1,0 +1,180 @@
+// Rectification for sm_100a: cv::initUndistortRectifyMap-equivalent (FP64, no FMA contraction) and
+// cv::remap's 5-bit fixed-point bilinear interpolation, optionally fused with the x-Sobel prefilter.
+// Replaces PinholeCameraModel::rectifyImageGPU (reference call sites src/GPUStereoProcessor.cpp:244,248)
+// with the CPU semantics of rectifyImageLeft/Right (:252-262), which is what the reference's goldens pin
+// (test/UTest.cpp:247-256).  Algorithm: SURVEY.md A.1.
+#include "kernels.h"
+
+namespace b200s {
+
+// (sx, sy) = (rint(float(u)*32), rint(float(v)*32)); every double op is an explicit round-to-nearest
+// intrinsic so that ptxas can never contract a multiply-add (bit-exactness against the CPU evaluation).
+__device__ __forceinline__ void map_uv(const CamModel& c, int j, int i, float& uf, float& vf)
+{
+    const double dj = (double)j, di = (double)i;
+    double _x = __dadd_rn(__dmul_rn(dj, c.ir[0]), __dadd_rn(__dmul_rn(di, c.ir[1]), c.ir[2]));
+    double _y = __dadd_rn(__dmul_rn(dj, c.ir[3]), __dadd_rn(__dmul_rn(di, c.ir[4]), c.ir[5]));
+    double _w = __dadd_rn(__dmul_rn(dj, c.ir[6]), __dadd_rn(__dmul_rn(di, c.ir[7]), c.ir[8]));
+    double w = __ddiv_rn(1.0, _w);
+    double x = __dmul_rn(_x, w), y = __dmul_rn(_y, w);
+    double x2 = __dmul_rn(x, x), y2 = __dmul_rn(y, y);
+    double r2 = __dadd_rn(x2, y2);
+    double _2xy = __dmul_rn(__dmul_rn(2.0, x), y);
+    double num = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(c.k3, r2), c.k2), r2), c.k1), r2));
+    double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(c.k6, r2), c.k5), r2), c.k4), r2));
+    double kr = __ddiv_rn(num, den);
+    double xd = __dadd_rn(__dadd_rn(__dmul_rn(x, kr), __dmul_rn(c.p1, _2xy)),
+                          __dmul_rn(c.p2, __dadd_rn(r2, __dmul_rn(2.0, x2))));
+    double yd = __dadd_rn(__dadd_rn(__dmul_rn(y, kr), __dmul_rn(c.p1, __dadd_rn(r2, __dmul_rn(2.0, y2)))),
+                          __dmul_rn(c.p2, _2xy));
+    double u = __dadd_rn(__dmul_rn(c.fx, xd), c.cx);
+    double v = __dadd_rn(__dmul_rn(c.fy, yd), c.cy);
+    uf = __double2float_rn(u);
+    vf = __double2float_rn(v);
+}
+
+__device__ __forceinline__ int2 map_point(const CamModel& c, int j, int i)
+{
+    float uf, vf;
+    map_uv(c, j, i, uf, vf);
+    return make_int2(__float2int_rn(__fmul_rn(uf, 32.0f)), __float2int_rn(__fmul_rn(vf, 32.0f)));
+}
+
+__device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }
+
+__device__ __forceinline__ int fetch1(const uint8_t* __restrict__ s, int sW, int sH, int x, int y, int ch, int c)
+{
+    return ((unsigned)x < (unsigned)sW && (unsigned)y < (unsigned)sH) ? (int)__ldg(s + ((size_t)y * sW + x) * ch + c) : 0;
+}
+
+// one bilinear sample; weights (32-a)(32-b) etc. are the 15-bit table of cv::remap divided by 32
+__device__ __forceinline__ int sample_linear(const uint8_t* __restrict__ s, int sW, int sH, int ch, int c, int2 m)
+{
+    int a = m.x & 31, b = m.y & 31;
+    int X0 = sat16(m.x >> 5), Y0 = sat16(m.y >> 5);
+    int s00 = fetch1(s, sW, sH, X0, Y0, ch, c), s01 = fetch1(s, sW, sH, X0 + 1, Y0, ch, c);
+    int s10 = fetch1(s, sW, sH, X0, Y0 + 1, ch, c), s11 = fetch1(s, sW, sH, X0 + 1, Y0 + 1, ch, c);
+    int acc = (32 - a) * (32 - b) * s00 + a * (32 - b) * s01 + (32 - a) * b * s10 + a * b * s11;
+    return (acc + 512) >> 10;
+}
+
+__global__ void __launch_bounds__(256) build_map_kernel(CamModel cm, int W, int H, int2* __restrict__ map)
+{
+    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x < W && y < H) map[(size_t)y * W + x] = map_point(cm, x, y);
+}
+
+template <bool FLY, int CH>
+__global__ void __launch_bounds__(256) remap_kernel(const uint8_t* __restrict__ src, int sW, int sH,
+                                                    const int2* __restrict__ map, CamModel cm,
+                                                    uint8_t* __restrict__ dst, int W, int H)
+{
+    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    int2 m = FLY ? map_point(cm, x, y) : __ldg(map + (size_t)y * W + x);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) dst[((size_t)y * W + x) * CH + c] = (uint8_t)sample_linear(src, sW, sH, CH, c, m);
+}
+
+// cv::remap INTER_NEAREST on float maps: source pixel (cvRound(u), cvRound(v)); always evaluates the map
+// (the cached x32 fixed-point map cannot reproduce the rounding of u itself).
+__global__ void __launch_bounds__(256) remap_nearest_kernel(const uint8_t* __restrict__ src, int sW, int sH, int ch,
+                                                            CamModel cm, uint8_t* __restrict__ dst, int W, int H)
+{
+    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    float uf, vf;
+    map_uv(cm, x, y, uf, vf);
+    int X = __float2int_rn(uf), Y = __float2int_rn(vf);
+    for (int c = 0; c < ch; ++c) dst[((size_t)y * W + x) * ch + c] = (uint8_t)fetch1(src, sW, sH, X, Y, ch, c);
+}
+
+// ---- fused rectify + x-Sobel ---------------------------------------------------------------------------
+// Tile of TX x TY output pixels; the block rectifies the tile plus a 1-pixel halo into shared memory,
+// writes the interior to `rect`, then applies OpenCV's prefilterXSobel border rules:
+// 3x3 Sobel-x with rows mirrored (reflect-101), columns 0 and W-1 = cap, odd-height last row = cap.
+constexpr int FTX = 64, FTY = 16;
+
+template <bool FLY>
+__global__ void __launch_bounds__(256) rectify_xsobel_kernel(const uint8_t* __restrict__ src, int sW, int sH,
+                                                             const int2* __restrict__ map, CamModel cm,
+                                                             uint8_t* __restrict__ rect, uint8_t* __restrict__ pre,
+                                                             int W, int H, int cap)
+{
+    __shared__ uint8_t tile[FTY + 2][FTX + 2 + 2];
+    const int x0 = blockIdx.x * FTX, y0 = blockIdx.y * FTY;
+    for (int i = threadIdx.x; i < (FTX + 2) * (FTY + 2); i += 256) {
+        int ty = i / (FTX + 2), tx = i - ty * (FTX + 2);
+        int x = x0 + tx - 1, y = y0 + ty - 1;
+        // rows are mirrored for the Sobel taps: the halo row above row 0 is row 1, below row H-1 is row H-2
+        int ys = y < 0 ? 1 : (y >= H ? H - 2 : y);
+        int v = 0;
+        if (x >= 0 && x < W && ys >= 0 && ys < H) {
+            int2 m = FLY ? map_point(cm, x, ys) : __ldg(map + (size_t)ys * W + x);
+            v = sample_linear(src, sW, sH, 1, 0, m);
+            if (tx >= 1 && tx <= FTX && ty >= 1 && ty <= FTY && y < H) rect[(size_t)y * W + x] = (uint8_t)v;
+        }
+        tile[ty][tx] = (uint8_t)v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < FTX * FTY; i += 256) {
+        int ty = i / FTX, tx = i - ty * FTX;
+        int x = x0 + tx, y = y0 + ty;
+        if (x >= W || y >= H) continue;
+        int out = cap;
+        bool last_odd = (H & 1) && (y == H - 1);
+        if (x > 0 && x < W - 1 && !last_odd && H > 1) {
+            int d0 = (int)tile[ty][tx + 2] - (int)tile[ty][tx];
+            int d1 = (int)tile[ty + 1][tx + 2] - (int)tile[ty + 1][tx];
+            int d2 = (int)tile[ty + 2][tx + 2] - (int)tile[ty + 2][tx];
+            int v = d0 + 2 * d1 + d2;
+            out = min(max(v, -cap), cap) + cap;
+        }
+        pre[(size_t)y * W + x] = (uint8_t)out;
+    }
+}
+
+static inline dim3 grid2d(int W, int H) { return dim3((W + 31) / 32, (H + 7) / 8); }
+
+int launch_build_map(const CamModel& cm, int W, int H, int2* map, cudaStream_t st)
+{
+    build_map_kernel<<<grid2d(W, H), 256, 0, st>>>(cm, W, H, map);
+    return 1;
+}
+
+int launch_remap(const uint8_t* src, int sW, int sH, int ch, const int2* map, const CamModel& cm, uint8_t* dst,
+                 int W, int H, cudaStream_t st)
+{
+    dim3 g = grid2d(W, H);
+    if (ch == 1) {
+        if (map) remap_kernel<false, 1><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H);
+        else remap_kernel<true, 1><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H);
+    } else if (ch == 3) {
+        if (map) remap_kernel<false, 3><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H);
+        else remap_kernel<true, 3><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H);
+    } else if (ch == 4) {
+        if (map) remap_kernel<false, 4><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H);
+        else remap_kernel<true, 4><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H);
+    } else
+        return -1;
+    return 1;
+}
+
+int launch_remap_nearest(const uint8_t* src, int sW, int sH, int ch, const int2* map, const CamModel& cm,
+                         uint8_t* dst, int W, int H, cudaStream_t st)
+{
+    (void)map;
+    remap_nearest_kernel<<<grid2d(W, H), 256, 0, st>>>(src, sW, sH, ch, cm, dst, W, H);
+    return 1;
+}
+
+int launch_rectify_xsobel(const uint8_t* src, int sW, int sH, const int2* map, const CamModel& cm, uint8_t* rect,
+                          uint8_t* pre, int W, int H, int cap, cudaStream_t st)
+{
+    dim3 g((W + FTX - 1) / FTX, (H + FTY - 1) / FTY);
+    if (map) rectify_xsobel_kernel<false><<<g, 256, 0, st>>>(src, sW, sH, map, cm, rect, pre, W, H, cap);
+    else rectify_xsobel_kernel<true><<<g, 256, 0, st>>>(src, sW, sH, map, cm, rect, pre, W, H, cap);
+    return 1;
+}
+
+}  // namespace b200s

@@ -1,0 +1,125 @@
+// Disparity -> float plane, cv::reprojectImageTo3D(handleMissingValues = true) and PointCloud2 / DisparityImage
+// payload packing in one pass.  Replaces projectDisparityImageTo3dGPU
+// (src/GPUStereoProcessor.cpp:332-346) and the host loops of GPUSenderPc2::fillInData (src/GpuSenderPc2.cpp:15-72)
+// and GPUSenderDisparity::fillInData (src/GpuSenderDisparity.cpp:18-48).
+// The 4-term products are evaluated in FP64 without FMA contraction, like the CPU code, so the points are
+// bit-identical to cv2's (the 1e-5 bar of the north star needs FP64: pure f32 reaches 2e-5).
+#include "kernels.h"
+
+#include <climits>
+
+namespace b200s {
+
+__device__ __forceinline__ float disp_to_float(int d16, double cxd)
+{
+    // cv::Mat::convertTo(CV_32F, 1/16., -(cx_l - cx_r)): saturate_cast<float>(d * alpha + beta) in double
+    return __double2float_rn(__dadd_rn(__dmul_rn((double)d16, 1.0 / 16.0), -cxd));
+}
+
+__global__ void __launch_bounds__(256) set_int_kernel(int* p, int v) { *p = v; }
+
+__global__ void __launch_bounds__(256) disparity_to_float_kernel(const int16_t* __restrict__ d16, float* __restrict__ df,
+                                                                 int n, double cxd, int* __restrict__ min_d16)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int v = INT_MAX;
+    if (i < n) {
+        v = d16[i];
+        if (df) df[i] = disp_to_float(v, cxd);
+    }
+    v = __reduce_min_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v != INT_MAX) atomicMin(min_d16, v);
+}
+
+__global__ void __launch_bounds__(256) reproject_pack_kernel(const int16_t* __restrict__ d16, int W, int H, double cxd,
+                                                             const double* __restrict__ Q, const int* __restrict__ min_d16,
+                                                             const uint8_t* __restrict__ color, int ch,
+                                                             float* __restrict__ xyz, uint8_t* __restrict__ pc2)
+{
+    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    size_t i = (size_t)y * W + x;
+    const float dfl = disp_to_float(d16[i], cxd);
+    const double d = (double)dfl;
+    const double minDisp = (double)disp_to_float(*min_d16, cxd);
+    double h[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        double s = __dmul_rn(__ldg(Q + r * 4 + 0), (double)x);
+        s = __dadd_rn(s, __dmul_rn(__ldg(Q + r * 4 + 1), (double)y));
+        s = __dadd_rn(s, __dmul_rn(__ldg(Q + r * 4 + 2), d));
+        s = __dadd_rn(s, __ldg(Q + r * 4 + 3));
+        h[r] = s;
+    }
+    float p[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) p[r] = __double2float_rn(__ddiv_rn((double)__double2float_rn(h[r]), h[3]));
+    if (fabs(__dadd_rn(d, -minDisp)) <= (double)1.1920928955078125e-07f) p[2] = 10000.0f;
+    if (xyz) {
+        xyz[i * 3] = p[0]; xyz[i * 3 + 1] = p[1]; xyz[i * 3 + 2] = p[2];
+    }
+    if (pc2) {
+        // isValidPoint (src/GpuSenderPc2.cpp:84-89): z != MISSING_Z and not inf; invalid -> quiet NaN
+        bool valid = (p[2] != 10000.0f) && !isinf(p[2]);
+        uint32_t ux = valid ? __float_as_uint(p[0]) : 0x7fc00000u;
+        uint32_t uy = valid ? __float_as_uint(p[1]) : 0x7fc00000u;
+        uint32_t uz = valid ? __float_as_uint(p[2]) : 0x7fc00000u;
+        uint32_t bgr;
+        if (ch == 3) bgr = (uint32_t)color[i * 3] | ((uint32_t)color[i * 3 + 1] << 8) | ((uint32_t)color[i * 3 + 2] << 16);
+        else { uint32_t g = color ? color[i] : 0; bgr = g | (g << 8) | (g << 16); }
+        uint4* o = (uint4*)(pc2 + i * 32);
+        o[0] = make_uint4(ux, uy, uz, 0u);
+        o[1] = make_uint4(bgr, 0u, 0u, 0u);
+    }
+}
+
+// cv::cuda::drawColorDisp-style HSV map of the integer disparity (reference: computeDisparityImage,
+// src/GPUStereoProcessor.cpp:323-330).  FILTERED / negative -> black.  "next" row of the scope table.
+__global__ void __launch_bounds__(256) disparity_color_kernel(const int16_t* __restrict__ d16, uint8_t* __restrict__ bgra,
+                                                              int n, int nd)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int d = d16[i] >> 4;
+    uint32_t out = 0;
+    if (d > 0 && d < nd) {
+        unsigned H = ((unsigned)(nd - d) * 240u) / (unsigned)nd;
+        unsigned hi = (H / 60u) % 6u;
+        float f = (float)H / 60.f - (float)(H / 60u);
+        unsigned V = 255, p = 0, q = (unsigned)(255.f * (1.f - f)), t = (unsigned)(255.f * f);
+        unsigned r, g, b;
+        switch (hi) {
+            case 0: r = V; g = t; b = p; break;
+            case 1: r = q; g = V; b = p; break;
+            case 2: r = p; g = V; b = t; break;
+            case 3: r = p; g = q; b = V; break;
+            case 4: r = t; g = p; b = V; break;
+            default: r = V; g = p; b = q; break;
+        }
+        out = b | (g << 8) | (r << 16) | (255u << 24);
+    }
+    ((uint32_t*)bgra)[i] = out;
+}
+
+int launch_disparity_to_float(const int16_t* d16, float* df, int n, double cxd, int* min_d16, cudaStream_t st)
+{
+    set_int_kernel<<<1, 1, 0, st>>>(min_d16, INT_MAX);
+    disparity_to_float_kernel<<<(n + 255) / 256, 256, 0, st>>>(d16, df, n, cxd, min_d16);
+    return 2;
+}
+
+int launch_reproject_pack(const int16_t* d16, int W, int H, double cxd, const double* Q, const int* min_d16,
+                          const uint8_t* color, int ch, float* xyz, uint8_t* pc2, cudaStream_t st)
+{
+    dim3 g((W + 31) / 32, (H + 7) / 8);
+    reproject_pack_kernel<<<g, 256, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2);
+    return 1;
+}
+
+int launch_disparity_color(const int16_t* d16, uint8_t* bgra, int n, int nd, cudaStream_t st)
+{
+    disparity_color_kernel<<<(n + 255) / 256, 256, 0, st>>>(d16, bgra, n, nd);
+    return 1;
+}
+
+}  // namespace b200s

@@ -1,0 +1,317 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, the committed cv2 vectors and the
+reference's golden fixtures.  Integer / byte stages are bit-exact; the float stages are compared bit-for-bit too
+(they are evaluated in FP64 without FMA contraction like the CPU code), with the north-star tolerance of 1e-5
+relative as the stated bar for the point cloud."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O, synth  # noqa: E402
+
+
+def _gpu():
+    import ros_gpu_stereo_processor_b200 as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def proc():
+    m = _gpu()
+    p = m.GpuStereoProcessor(0)
+    yield p
+    p.close()
+
+
+def _caminfo(c, W, H):
+    return dict(width=W, height=H, K=c["K"], D=c["D"], R=c["R"], P=c["P"])
+
+
+def _describe(a, b):
+    bad = a != b
+    if not bad.any():
+        return "equal"
+    ys, xs = np.nonzero(bad.reshape(bad.shape[0], bad.shape[1], -1).any(axis=2))
+    return "%d mismatches, cols [%d, %d], rows [%d, %d]; first: got %s want %s at (y=%d, x=%d)" % (
+        bad.sum(), xs.min(), xs.max(), ys.min(), ys.max(), a[ys[0], xs[0]], b[ys[0], xs[0]], ys[0], xs[0])
+
+
+def _set(proc, p):
+    proc.setParams(**p.as_dict())
+
+
+# ---- rectification ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fly", [False, True])
+def test_rectify_matches_reference_goldens(proc, fixtures, calib, fly):
+    # RectifyMonoCpu / RectifyMonoGpu (test/UTest.cpp:247-288): here the GPU result is bit-exact, not just similar
+    m = _gpu()
+    proc.initStereoModel(_caminfo(calib["left"], 752, 480), _caminfo(calib["right"], 752, 480))
+    assert proc.isStereoModelInitialised()
+    proc.setRectifyOnTheFly(fly)
+    for side, bit in (("left", m.SIDE_L), ("right", m.SIDE_R)):
+        proc.uploadMat(m.SRC_RAW | bit, fixtures[side + "_raw"], "mono8")
+        proc.convertRawToMono(bit)
+        proc.rectifyImage(m.SRC_MONO | bit, m.SRC_RECT_MONO | bit, m.INTER_LINEAR)
+        out = proc.downloadMat(m.SRC_RECT_MONO | bit)
+        assert np.array_equal(out, fixtures[side + "_rect"]), side + ": " + _describe(out, fixtures[side + "_rect"])
+    proc.setRectifyOnTheFly(False)
+
+
+@pytest.mark.parametrize("size", [(1280, 720), (1920, 1080)])
+def test_rectify_scaled_calibration(proc, size):
+    W, H = size
+    Lraw, Rraw, cal = synth.synth_raw_pair(W, H, 128, seed=3000)
+    proc.initStereoModel(_caminfo(cal["left"], W, H), _caminfo(cal["right"], W, H))
+    for fly in (False, True):
+        proc.setRectifyOnTheFly(fly)
+        a = proc.rectifyImageLeft(Lraw)
+        b = proc.rectifyImageRight(Rraw)
+        assert np.array_equal(a, O.rectify(Lraw, **cal["left"])), _describe(a, O.rectify(Lraw, **cal["left"]))
+        assert np.array_equal(b, O.rectify(Rraw, **cal["right"]))
+    proc.setRectifyOnTheFly(False)
+
+
+def test_rectify_color_and_conversions(proc, fixtures, calib):
+    m = _gpu()
+    proc.initStereoModel(_caminfo(calib["left"], 752, 480), _caminfo(calib["right"], 752, 480))
+    rng = np.random.default_rng(5)
+    bgr = rng.integers(0, 256, (480, 752, 3), dtype=np.uint8)
+    proc.uploadMat(m.SRC_RAW | m.SIDE_L, bgr, "bgr8")
+    proc.convertRawToColor(m.SIDE_L)
+    proc.convertRawToMono(m.SIDE_L)
+    proc.rectifyImage(m.SRC_COLOR | m.SIDE_L, m.SRC_RECT_COLOR | m.SIDE_L, m.INTER_LINEAR)
+    mx, my = O.build_rect_map(calib["left"]["K"], calib["left"]["D"], calib["left"]["R"], calib["left"]["P"], 752, 480)
+    assert np.array_equal(proc.downloadMat(m.SRC_RECT_COLOR | m.SIDE_L), O.remap_linear(bgr, mx, my))
+    import cv2
+    assert np.array_equal(proc.downloadMat(m.SRC_MONO | m.SIDE_L), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+    # GpuColorConversion* (test/UTest.cpp:190-245) on 1x1 images
+    px = np.array([[[10, 20, 30]]], np.uint8)
+    proc.uploadMat(m.SRC_RAW | m.SIDE_R, px, "bgr8"); proc.convertRawToMono(m.SIDE_R)
+    assert proc.downloadMat(m.SRC_MONO | m.SIDE_R)[0, 0] == 22
+    proc.uploadMat(m.SRC_RAW | m.SIDE_R, px, "rgb8"); proc.convertRawToColor(m.SIDE_R)
+    assert proc.downloadMat(m.SRC_COLOR | m.SIDE_R)[0, 0].tolist() == [30, 20, 10]
+    proc.uploadMat(m.SRC_RAW | m.SIDE_R, np.array([[77]], np.uint8), "mono8"); proc.convertRawToColor(m.SIDE_R)
+    assert proc.downloadMat(m.SRC_COLOR | m.SIDE_R)[0, 0].tolist() == [77, 77, 77]
+
+
+def test_gpu_transfer_roundtrip(proc, fixtures):
+    # GpuTransfer (test/UTest.cpp:179-188)
+    m = _gpu()
+    proc.uploadMat(m.SRC_RAW | m.SIDE_L, fixtures["aloe_L"], "mono8")
+    assert np.array_equal(proc.downloadMat(m.SRC_RAW | m.SIDE_L), fixtures["aloe_L"])
+
+
+# ---- block matching -------------------------------------------------------------------------------------------
+def test_disparity_matches_committed_cv2_vectors(proc, fixtures, cv2_golden):
+    pairs = {"0022": (fixtures["left_rect"], fixtures["right_rect"]), "aloe": (fixtures["aloe_L"], fixtures["aloe_R"])}
+    for name, meta in cv2_golden["meta"].items():
+        p = O.BMParams(**meta["params"])
+        _set(proc, p)
+        L, R = pairs[meta["pair"]]
+        got = proc.computeDisparityBare(L, R)
+        want = cv2_golden["disp_" + name]
+        assert np.array_equal(got, want), name + ": " + _describe(got, want)
+
+
+SWEEP = [
+    dict(), dict(numDisparities=128, blockSize=15, speckleWindowSize=100, speckleRange=4),
+    dict(preFilterType=0, preFilterSize=9), dict(minDisparity=-16, numDisparities=64, blockSize=11),
+    dict(numDisparities=16, blockSize=5, minDisparity=-10, disp12MaxDiff=2),
+    dict(numDisparities=16, blockSize=21, minDisparity=-40, disp12MaxDiff=1),
+    dict(numDisparities=32, blockSize=9, minDisparity=-32, uniquenessRatio=0),
+    dict(numDisparities=64, blockSize=9, disp12MaxDiff=0, speckleWindowSize=50, speckleRange=2, minDisparity=-5),
+    dict(numDisparities=112, blockSize=7, uniquenessRatio=5, disp12MaxDiff=1, textureThreshold=0),
+    dict(numDisparities=32, blockSize=51, preFilterCap=63, uniquenessRatio=30),
+    dict(blockSize=25, preFilterType=0, preFilterSize=21), dict(numDisparities=48, blockSize=5, preFilterCap=1, textureThreshold=0),
+    dict(numDisparities=96, blockSize=31, preFilterCap=31), dict(numDisparities=80, blockSize=21, preFilterCap=63),
+    dict(numDisparities=256, blockSize=11), dict(numDisparities=16, blockSize=5, uniquenessRatio=100),
+]
+
+
+@pytest.mark.parametrize("kw", SWEEP)
+def test_disparity_matches_oracle_synthetic_sweep(proc, kw):
+    p = O.BMParams(**kw)
+    L, R = synth.synth_pair(500, 211, max(p.numDisparities, 16), seed=11)   # odd height: x-Sobel last-row quirk
+    _set(proc, p)
+    got = proc.computeDisparityBare(L, R)
+    want = O.stereobm_compute(L, R, p)
+    assert np.array_equal(got, want), _describe(got, want)
+
+
+def test_disparity_positive_min_disparity(proc):
+    p = O.BMParams(minDisparity=32, numDisparities=64, blockSize=15)
+    L, R = synth.synth_pair(500, 200, 96, seed=5)
+    _set(proc, p)
+    got, want = proc.computeDisparityBare(L, R), O.stereobm_compute(L, R, p)
+    assert np.array_equal(got, want), _describe(got, want)
+
+
+CONFIGS = {   # BASELINE.json configs (matcher part), SURVEY.md 8(d)
+    "C1": (752, 480, dict(numDisparities=64, blockSize=21)),
+    "C2": (1242, 375, dict(numDisparities=128, blockSize=15, speckleWindowSize=100, speckleRange=4)),
+    "C3": (1280, 720, dict(numDisparities=128, blockSize=15)),
+    "C4": (1920, 1080, dict(numDisparities=256, blockSize=11)),
+}
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_disparity_baseline_configs(proc, name):
+    W, H, kw = CONFIGS[name]
+    p = O.BMParams(**kw)
+    L, R = synth.synth_pair(W, H, p.numDisparities, seed=1000 * (1 + list(CONFIGS).index(name)))
+    _set(proc, p)
+    got = proc.computeDisparityBare(L, R)
+    want = O.stereobm_compute(L, R, p)
+    assert np.array_equal(got, want), name + ": " + _describe(got, want)
+    assert (want != (p.minDisparity - 1) * 16).mean() > 0.3   # the synthetic pair really matches
+
+
+def test_disparity_4k_properties(proc):
+    # C5 shape: size-independent properties instead of a full oracle run
+    W, H, nd = 3840, 2160, 256
+    p = O.BMParams(numDisparities=nd, blockSize=11)
+    L, R = synth.synth_pair(W, H, nd, seed=5000)
+    _set(proc, p)
+    got = proc.computeDisparityBare(L, R)
+    FILT = -16
+    r = 5
+    assert (got[:r] == FILT).all() and (got[-r:] == FILT).all() and (got[:, :nd - 1 + r] == FILT).all() and (got[:, -r:] == FILT).all()
+    valid = got != FILT
+    assert valid.mean() > 0.3
+    assert got[valid].min() >= -8 and got[valid].max() <= (nd - 1) * 16 + 8
+    # a horizontal band of the big image must equal the oracle run on that band plus its window halo
+    y0, y1 = 1000, 1064
+    want = O.stereobm_compute(L[y0 - r:y1 + r], R[y0 - r:y1 + r], p)[r:-r]
+    # x-Sobel uses rows y-1..y+1, so the band's first/last halo rows differ; compare the band interior only
+    band = got[y0:y1]
+    assert np.array_equal(band[1:-1], want[1:-1]), _describe(band[1:-1], want[1:-1])
+    # idempotence of the device buffers: a second run gives the same bytes
+    assert np.array_equal(proc.computeDisparityBare(L, R), got)
+
+
+def test_float_disparity_and_mat_variant(proc, fixtures, calib):
+    proc.initStereoModel(_caminfo(calib["left"], 752, 480), _caminfo(calib["right"], 752, 480))
+    p = O.BMParams(numDisparities=64, blockSize=21)
+    _set(proc, p)
+    df = proc.computeDisparity(fixtures["left_rect"], fixtures["right_rect"])   # Mat variant -> CV_32F
+    want = O.disparity_to_float(O.stereobm_compute(fixtures["left_rect"], fixtures["right_rect"], p),
+                                calib["left"]["P"][2] - calib["right"]["P"][2])
+    assert np.array_equal(df, want)
+
+
+# ---- speckle / validate -------------------------------------------------------------------------------------
+def test_speckle_filter_host_entry(proc, cv2_golden):
+    src = cv2_golden["speckle_in"]
+    assert np.array_equal(proc.filterSpecklesRaw(src, -16, 100, 4), cv2_golden["speckle_out_100_4"])
+    assert np.array_equal(proc.filterSpecklesRaw(src, -16, 800, 80), cv2_golden["speckle_out_800_80"])
+    assert np.array_equal(proc.filterSpecklesRaw(src, -16, 30, 0), O.filter_speckles(src, -16, 30, 0))
+    rng = np.random.default_rng(9)
+    noise = (rng.integers(0, 40, (300, 333)) * 16).astype(np.int16)
+    noise[rng.random(noise.shape) < 0.3] = -16
+    for ws, rg in [(5, 16), (50, 32), (1000, 48), (100000, 16)]:
+        assert np.array_equal(proc.filterSpecklesRaw(noise, -16, ws, rg), O.filter_speckles(noise, -16, ws, rg)), (ws, rg)
+    empty = np.full((40, 50), -16, np.int16)
+    assert np.array_equal(proc.filterSpecklesRaw(empty, -16, 10, 1), empty)
+
+
+# ---- reprojection / packing ---------------------------------------------------------------------------------
+def test_pointcloud_and_disparity_messages(proc, fixtures, calib):
+    m = _gpu()
+    proc.initStereoModel(_caminfo(calib["left"], 752, 480), _caminfo(calib["right"], 752, 480))
+    p = O.BMParams(numDisparities=128, blockSize=15, speckleWindowSize=100, speckleRange=4)
+    _set(proc, p)
+    L, R = fixtures["left_rect"], fixtures["right_rect"]
+    proc.uploadMat(m.SRC_RECT_MONO | m.SIDE_L, L, "mono8")
+    proc.uploadMat(m.SRC_RECT_MONO | m.SIDE_R, R, "mono8")
+    proc.computeDisparity(m.SRC_RECT_MONO | m.SIDE_L, m.SRC_RECT_MONO | m.SIDE_R, m.SRC_DISPARITY | m.SIDE_L)
+    d16 = proc.downloadMat(m.SRC_DISPARITY | m.SIDE_L)
+    want_d = O.stereobm_compute(L, R, p)
+    assert np.array_equal(d16, want_d)
+    model = proc.getModel()
+    Q = O.stereo_Q(calib["left"]["P"], calib["right"]["P"])
+    assert np.array_equal(model["Q"], Q)
+    cxd = calib["left"]["P"][2] - calib["right"]["P"][2]
+    df = O.disparity_to_float(want_d, cxd)
+    xyz_want = O.reproject(df, Q)
+    proc.projectDisparityTo3DPoints(m.SRC_DISPARITY | m.SIDE_L, m.SRC_POINTS2 | m.SIDE_L)
+    xyz = proc.downloadMat(m.SRC_POINTS2 | m.SIDE_L)
+    fin = np.isfinite(xyz_want)
+    assert np.array_equal(np.isfinite(xyz), fin)
+    rel = np.abs(xyz[fin] - xyz_want[fin]) / np.maximum(np.abs(xyz_want[fin]), 1e-30)
+    assert rel.max() <= 1e-5            # the north star's bar ...
+    assert np.array_equal(xyz.view(np.uint32), xyz_want.view(np.uint32))   # ... and in fact bit-identical
+    snd = proc.enqueueSendPoints(m.SRC_POINTS2 | m.SIDE_L, m.SRC_RECT_MONO | m.SIDE_L)
+    msg = snd.message
+    assert snd.wasDataSent() and msg["point_step"] == 32 and msg["row_step"] == 32 * 752 and not msg["is_dense"]
+    assert [f["offset"] for f in msg["fields"]] == [0, 4, 8, 16]
+    assert np.array_equal(msg["data"], O.pack_pointcloud2(xyz_want, L))
+    dm = proc.enqueueSendDisparity(m.SRC_DISPARITY | m.SIDE_L).message
+    assert np.array_equal(dm["image"]["data"], df)
+    assert dm["valid_window"] == O.valid_window(752, 480, 0, 128, 15)
+    assert dm["min_disparity"] == 0 and dm["max_disparity"] == 127 and abs(dm["delta_d"] - 1 / 16) < 1e-9
+    assert abs(dm["f"] - 441.238411) < 1e-3 and abs(dm["T"] - 0.100021) < 1e-5
+    im = proc.enqueueSendImage(m.SRC_RECT_MONO | m.SIDE_L, encoding="mono8").message
+    assert im["step"] == 752 and np.array_equal(im["data"].reshape(480, 752), L)
+    proc.computeDisparityImage(m.SRC_DISPARITY | m.SIDE_L, m.SRC_DISPARITY_IMG | m.SIDE_L)
+    assert proc.downloadMat(m.SRC_DISPARITY_IMG | m.SIDE_L).shape == (480, 752, 4)
+    proc.cleanSenders()
+
+
+# ---- fused frame path ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [("C3", 1280, 720, 128, 15, 1), ("C1n", 752, 480, 64, 21, 0)])
+def test_fused_chain_matches_oracle_chain(cfg):
+    name, W, H, nd, b, pft = cfg
+    m = _gpu()
+    proc = m.GpuStereoProcessor(0)
+    Lraw, Rraw, cal = synth.synth_raw_pair(W, H, nd, seed=3000)
+    proc.initStereoModel(_caminfo(cal["left"], W, H), _caminfo(cal["right"], W, H))
+    p = O.BMParams(numDisparities=nd, blockSize=b, preFilterType=pft)
+    _set(proc, p)
+    out = proc.processPair(Lraw, Rraw, rectify=True,
+                           want=("rect_left", "rect_right", "disparity16", "disparity32f", "pointcloud2", "points_xyz"))
+    rl, rr = O.rectify(Lraw, **cal["left"]), O.rectify(Rraw, **cal["right"])
+    assert np.array_equal(out["rect_left"], rl) and np.array_equal(out["rect_right"], rr)
+    d = O.stereobm_compute(rl, rr, p)
+    assert np.array_equal(out["disparity16"], d), _describe(out["disparity16"], d)
+    cxd = cal["left"]["P"][2] - cal["right"]["P"][2]
+    df = O.disparity_to_float(d, cxd)
+    assert np.array_equal(out["disparity32f"], df)
+    xyz = O.reproject(df, O.stereo_Q(cal["left"]["P"], cal["right"]["P"]))
+    assert np.array_equal(out["points_xyz"].view(np.uint32), xyz.view(np.uint32))
+    assert np.array_equal(out["pointcloud2"], O.pack_pointcloud2(xyz, rl))
+    assert (d != -16).mean() > 0.5
+    assert proc.kernelLaunches() > 0
+    proc.close()
+
+
+# ---- error behaviour ----------------------------------------------------------------------------------------
+def test_errors():
+    m = _gpu()
+    proc = m.GpuStereoProcessor(0)
+    cap = m._capi
+    L, R = synth.synth_pair(64, 48, 16, seed=1)
+    with pytest.raises(cap.B200StereoError) as e:   # reference: assert(model_.initialized())
+        proc.uploadMat(m.SRC_MONO | m.SIDE_L, L); proc.rectifyImage(m.SRC_MONO | m.SIDE_L, m.SRC_RECT_MONO | m.SIDE_L)
+    assert e.value.code == cap.ENOTINIT
+    for kw in [dict(numDisparities=24), dict(blockSize=4), dict(blockSize=49), dict(preFilterCap=64), dict(preFilterSize=4),
+               dict(textureThreshold=-1), dict(uniquenessRatio=-1), dict(preFilterType=2)]:
+        base = dict(numDisparities=16, blockSize=9)
+        base.update(kw)
+        proc.setParams(**O.BMParams(**base).as_dict())
+        with pytest.raises(cap.B200StereoError) as e:
+            proc.computeDisparityBare(L, R)
+        assert e.value.code == cap.EINVAL, kw
+    proc.setParams(**O.BMParams(numDisparities=16, blockSize=9).as_dict())
+    with pytest.raises(cap.B200StereoError) as e:
+        proc.downloadMat(m.SRC_POINTS2 | m.SIDE_R)
+    assert e.value.code == cap.ENOBUF
+    proc.uploadMat(m.SRC_RAW | m.SIDE_L, np.zeros((4, 4), np.uint8), "bayer_rggb8")
+    with pytest.raises(cap.B200StereoError) as e:
+        proc.convertRawToMono(m.SIDE_L)
+    assert e.value.code == cap.EUNSUPPORTED
+    # tiny / degenerate images: everything FILTERED, like cv2
+    p = O.BMParams(numDisparities=64, blockSize=9)
+    proc.setParams(**p.as_dict())
+    Ls, Rs = synth.synth_pair(40, 30, 16, seed=2)
+    assert np.array_equal(proc.computeDisparityBare(Ls, Rs), O.stereobm_compute(Ls, Rs, p))
+    proc.close()

