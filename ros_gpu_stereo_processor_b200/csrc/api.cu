@@ -321,7 +321,7 @@ int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, 
         h->launches += launch_roi_mask(disp, cols, rows, cfg, st);
     }
     if (p.speckle_window_size > 0 && p.speckle_range >= 0) {
-        if (w.ccl.ensure(2 * n * sizeof(int))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (speckle scratch)");
+        if (w.ccl.ensure(3 * n * sizeof(int))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (speckle scratch)");
         h->launches += launch_filter_speckles(disp, cols, rows, (p.min_disparity - 1) * 16, p.speckle_window_size,
                                               p.speckle_range, (int*)w.ccl.p, st);
     }
@@ -652,7 +652,7 @@ int b200s_filter_speckles(b200s_handle* h, int disp_id)
     const b200s_params& p = h->prm;
     if (p.speckle_window_size <= 0 || p.speckle_range < 0) return B200S_OK;
     size_t n = (size_t)D->rows * D->cols;
-    if (h->w0.ccl.ensure(2 * n * sizeof(int))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (speckle scratch)");
+    if (h->w0.ccl.ensure(3 * n * sizeof(int))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (speckle scratch)");
     cudaStream_t st = stream_of(h, disp_id);
     h->launches += launch_filter_speckles((int16_t*)D->buf.p, D->cols, D->rows, (p.min_disparity - 1) * 16,
                                           p.speckle_window_size, p.speckle_range, (int*)h->w0.ccl.p, st);
@@ -666,7 +666,7 @@ int b200s_filter_speckles_host(b200s_handle* h, int16_t* img, int rows, int cols
     if (step == 0) step = (size_t)cols * 2;
     size_t n = (size_t)rows * cols;
     DevBuf tmp;
-    if (tmp.ensure(n * 2) || h->w0.ccl.ensure(2 * n * sizeof(int))) { tmp.release(); return fail(h, B200S_ENOMEM, "cudaMalloc failed"); }
+    if (tmp.ensure(n * 2) || h->w0.ccl.ensure(3 * n * sizeof(int))) { tmp.release(); return fail(h, B200S_ENOMEM, "cudaMalloc failed"); }
     cudaStream_t st = h->l_strm;
     cudaError_t e = cudaMemcpy2DAsync(tmp.p, (size_t)cols * 2, img, step, (size_t)cols * 2, rows, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {

@@ -53,7 +53,7 @@ size_t bm_scratch_bytes(int W, int H, const BMConfig& cfg);
 // ---- post.cu ----------------------------------------------------------------------------------------
 int launch_validate_disp12(int16_t* disp, const int16_t* cost, int W, int H, const BMConfig& cfg, cudaStream_t st);
 int launch_roi_mask(int16_t* disp, int W, int H, const BMConfig& cfg, cudaStream_t st);
-// scratch: 2 * W*H int32 (labels, sizes)
+// scratch: 3 * W*H int32 (parents, sizes, roots)
 int launch_filter_speckles(int16_t* img, int W, int H, int newVal, int maxSize, int maxDiff, int* scratch, cudaStream_t st);
 
 // ---- reproject.cu -----------------------------------------------------------------------------------

@@ -113,22 +113,35 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(const int16_t* __restric
     }
 }
 
-__global__ void __launch_bounds__(256) ccl_count_kernel(int* __restrict__ L, int* __restrict__ sz, int n)
+// read-only root lookup: the forest is final here, and no thread may write L while others still walk it
+// (a stale path-halving store could otherwise replace an already flattened label by a non-root ancestor)
+__device__ __forceinline__ int uf_root(const int* __restrict__ L, int i)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || L[i] < 0) return;
-    int root = uf_find(L, i);
-    L[i] = root;
-    atomicAdd(&sz[root], 1);
+    int p = L[i];
+    while (p != i) { i = p; p = L[i]; }
+    return i;
 }
 
-__global__ void __launch_bounds__(256) ccl_apply_kernel(int16_t* __restrict__ img, const int* __restrict__ L,
+__global__ void __launch_bounds__(256) ccl_count_kernel(const int* __restrict__ L, int* __restrict__ root,
+                                                        int* __restrict__ sz, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = -1;
+    if (L[i] >= 0) {
+        r = uf_root(L, i);
+        atomicAdd(&sz[r], 1);
+    }
+    root[i] = r;
+}
+
+__global__ void __launch_bounds__(256) ccl_apply_kernel(int16_t* __restrict__ img, const int* __restrict__ root,
                                                         const int* __restrict__ sz, int n, int newVal, int maxSize)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int root = L[i];
-    if (root >= 0 && sz[root] <= maxSize) img[i] = (int16_t)newVal;
+    int r = root[i];
+    if (r >= 0 && sz[r] <= maxSize) img[i] = (int16_t)newVal;
 }
 
 static inline dim3 grid2d(int W, int H) { return dim3((W + 31) / 32, (H + 7) / 8); }
@@ -157,11 +170,12 @@ int launch_filter_speckles(int16_t* img, int W, int H, int newVal, int maxSize, 
     int n = W * H;
     int* L = scratch;
     int* sz = scratch + n;
+    int* root = scratch + 2 * (size_t)n;
     int nb = (n + 255) / 256;
     ccl_init_kernel<<<nb, 256, 0, st>>>(img, L, sz, n, newVal);
     ccl_merge_kernel<<<grid2d(W, H), 256, 0, st>>>(img, L, W, H, newVal, maxDiff);
-    ccl_count_kernel<<<nb, 256, 0, st>>>(L, sz, n);
-    ccl_apply_kernel<<<nb, 256, 0, st>>>(img, L, sz, n, newVal, maxSize);
+    ccl_count_kernel<<<nb, 256, 0, st>>>(L, root, sz, n);
+    ccl_apply_kernel<<<nb, 256, 0, st>>>(img, root, sz, n, newVal, maxSize);
     return 4;
 }
 
