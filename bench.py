@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the stereo hot path (BASELINE.json metric: stereo frames/s and Mdisp-evals/s; % INT-ALU roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C4]
+    torchrun --nproc-per-node N ... bench.py --gpus N ...     (one rank per GPU, frames sharded, no collective)
+
+Workload (config.workload): BASELINE.json configs[3] -- 1920x1080 mono8 raw pair, camera_info rectification,
+x-Sobel prefilter, StereoBM 256 disparities / block 11 / texture 10 / uniqueness 15, DisparityImage float payload and
+PointCloud2 payload: the full rectify -> disparity -> pc2 chain.  One "step" = one pass of that chain over a batch of
+FRAMES_PER_STEP distinct synthetic frames (per GPU).
+
+  value  frames/s with the raw frames and every output resident in HBM (CUDA events on the slot streams)
+  e2e    frames/s through the C ABI with pinned HOST buffers: H2D of the raw pair and D2H of the rectified pair,
+         the float disparity and the PointCloud2 payload inside the timed region
+  roofline  dominant kernel (bm_fast_kernel): scalar-equivalent integer ops (7 per disparity evaluation,
+         SURVEY.md 8(d)) over the CUDA-event duration of the matcher, against the INT peak measured on this GPU
+         by the library's IADD3 micro-benchmark; the HBM view of the same launch is reported beside it
+  cpu_baseline  the reference's CPU path (cv::remap x2, cv::StereoBM, convertTo, reprojectImageTo3D, PointCloud2
+         fill = ros_cpu_stereo_processing.launch) run with the real OpenCV (cv2) on this box's host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: W, H, nd, block, rectify, speckle(win, range)
+    "C1": dict(W=752, H=480, nd=64, block=21, rectify=False, speckle=(0, 0), idx=1),
+    "C2": dict(W=1242, H=375, nd=128, block=15, rectify=False, speckle=(100, 4), idx=2),
+    "C3": dict(W=1280, H=720, nd=128, block=15, rectify=True, speckle=(0, 0), idx=3),
+    "C4": dict(W=1920, H=1080, nd=256, block=11, rectify=True, speckle=(0, 0), idx=4),
+    "C5": dict(W=3840, H=2160, nd=256, block=11, rectify=True, speckle=(0, 0), idx=5),
+}
+FRAMES_PER_STEP = 16
+N_SLOTS = 4
+
+
+def workload_name(c, name):
+    return "%s: %dx%d mono8 raw pair, %s, xsobel cap31, StereoBM nd=%d block=%d tex10 uniq15%s, DisparityImage f32 + PointCloud2" % (
+        name, c["W"], c["H"], "rectify from camera_info" if c["rectify"] else "pre-rectified", c["nd"], c["block"],
+        (" speckle(%d,%d)" % c["speckle"]) if c["speckle"][0] else "")
+
+
+def evals_per_frame(c):
+    W, H, nd, r = c["W"], c["H"], c["nd"], c["block"] // 2
+    nominal = W * H * nd
+    eff = max(W - (nd - 1) - 2 * r, 0) * max(H - 2 * r, 0) * nd
+    return nominal, eff
+
+
+def make_frames(c, n, seed0):
+    from oracle import synth   # input generation only (seeded synthetic pairs + scaled calibration)
+    frames, cal = [], synth.scaled_calibration(c["W"], c["H"])
+    for i in range(n):
+        if c["rectify"]:
+            L, R, _ = synth.synth_raw_pair(c["W"], c["H"], c["nd"], seed0 + i)
+        else:
+            L, R = synth.synth_pair(c["W"], c["H"], c["nd"], seed0 + i)
+        frames.append((np.ascontiguousarray(L), np.ascontiguousarray(R)))
+    return frames, cal
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(pw) if pw else None, samples=len(sm), reasons=sorted(reasons))
+
+
+def cpu_chain(frames, cal, c, reps_budget_s, threads):
+    """The reference's CPU path with the real OpenCV: returns (frames/s, n_frames_timed)."""
+    import cv2
+    from oracle import oracle as O, cv2_ref as CV
+    cv2.setNumThreads(threads)
+    p = O.BMParams(numDisparities=c["nd"], blockSize=c["block"], speckleWindowSize=c["speckle"][0], speckleRange=c["speckle"][1])
+    bm = CV.make_bm(p)
+    W, H = c["W"], c["H"]
+    maps = None
+    if c["rectify"]:
+        maps = [CV.rect_maps(cal[s]["K"], cal[s]["D"], cal[s]["R"], cal[s]["P"], W, H) for s in ("left", "right")]
+    Q = O.stereo_Q(cal["left"]["P"], cal["right"]["P"])
+    cxd = cal["left"]["P"][2] - cal["right"]["P"][2]
+
+    def one(L, R):
+        if maps:
+            L = cv2.remap(L, maps[0][0], maps[0][1], cv2.INTER_LINEAR)
+            R = cv2.remap(R, maps[1][0], maps[1][1], cv2.INTER_LINEAR)
+        d = bm.compute(L, R)
+        df = d.astype(np.float32) * np.float32(1.0 / 16.0) - np.float32(cxd)     # convertTo(CV_32F, 1/16, -(cx-cx'))
+        xyz = cv2.reprojectImageTo3D(df, Q, handleMissingValues=True)
+        # PointCloud2 fill (GpuSenderPc2.cpp:15-72), vectorised numpy instead of the reference's scalar loops
+        pc = np.zeros((H, W, 8), np.float32)
+        bad = (xyz[..., 2] == 10000.0) | np.isinf(xyz[..., 2])
+        pc[..., :3] = np.where(bad[..., None], np.float32(np.nan), xyz)
+        pc.view(np.uint8).reshape(H, W, 32)[..., 16:19] = L[..., None]
+        return pc
+
+    one(*frames[0])   # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        one(*frames[n % len(frames)])
+        n += 1
+        if time.perf_counter() - t0 > reps_budget_s and n >= 3:
+            break
+    dt = time.perf_counter() - t0
+    return n / dt, n
+
+
+def run_reference(args, c, name, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (cv2 = the OpenCV it calls), all host threads."""
+    if rank != 0:
+        return
+    import cv2
+    threads = os.cpu_count() or 1
+    frames, cal = make_frames(c, 4, 1000 * c["idx"])
+    vals = []
+    for s in range(args.warmup + args.steps):
+        fps, n = cpu_chain(frames, cal, c, reps_budget_s=2.0, threads=threads)
+        if s >= args.warmup:
+            vals.append(fps)
+    fps = float(np.mean(vals))
+    nominal, eff = evals_per_frame(c)
+    line = dict(impl="reference", metric="stereo_frames_per_sec", value=fps, unit="frames/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1000.0 / fps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="u8", data="synthetic", mdisp_evals_per_s=fps * nominal / 1e6,
+                config=dict(workload=workload_name(c, name), frames_per_step=1),
+                cpu_baseline=dict(value=fps, unit="frames/s", cores=threads, kind="reference",
+                                  sample="cv2 %s (the OpenCV functions the reference calls: remap x2, StereoBM, convertTo, reprojectImageTo3D, "
+                                         "PointCloud2 fill) on 4 distinct frames, ~2 s of frames per step" % cv2.__version__),
+                e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def run_ours(args, c, name, rank, world, local_rank):
+    import ctypes as C
+    import torch
+    import ros_gpu_stereo_processor_b200 as m
+    from ros_gpu_stereo_processor_b200 import _capi as capi
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank
+    W, H, nd = c["W"], c["H"], c["nd"]
+    n = W * H
+    frames, cal = make_frames(c, FRAMES_PER_STEP, 1000 * c["idx"] + rank * FRAMES_PER_STEP)
+
+    proc = m.GpuStereoProcessor(dev)
+    info = lambda cc: dict(width=W, height=H, K=cc["K"], D=cc["D"], R=cc["R"], P=cc["P"])
+    proc.initStereoModel(info(cal["left"]), info(cal["right"]))
+    proc.setParams(numDisparities=nd, blockSize=c["block"], minDisparity=0, preFilterType=1, preFilterSize=9, preFilterCap=31,
+                   textureThreshold=10, uniquenessRatio=15, speckleWindowSize=c["speckle"][0], speckleRange=c["speckle"][1],
+                   disp12MaxDiff=-1)
+    proc.configureSlots(N_SLOTS, H, W)
+    want = capi.OUT_DISPARITY32F | capi.OUT_POINTCLOUD2 | (capi.OUT_RECT_L | capi.OUT_RECT_R if c["rectify"] else 0)
+
+    # ---- device-resident inputs (torch only owns the HBM) --------------------------------------------------
+    dL = [torch.from_numpy(f[0]).cuda(dev) for f in frames]
+    dR = [torch.from_numpy(f[1]).cuda(dev) for f in frames]
+    torch.cuda.synchronize(dev)
+    io_dev = capi.FrameIO()
+    io_dev.want, io_dev.rectify, io_dev.inputs_on_device, io_dev.outputs_on_device = want, int(c["rectify"]), 1, 1
+
+    def step_device():
+        for i in range(FRAMES_PER_STEP):
+            proc.processPairAsync(i % N_SLOTS, dL[i].data_ptr(), dR[i].data_ptr(), io_dev)
+
+    # ---- host buffers for the end-to-end leg (pinned) ------------------------------------------------------
+    pins = []
+
+    def pinned(nbytes):
+        a, ptr = proc.hostAlloc(nbytes)
+        pins.append(ptr)
+        return a, ptr
+
+    hL, hR = [], []
+    for f in frames:
+        a, pa = pinned(n); a[:] = f[0].ravel()
+        b, pb = pinned(n); b[:] = f[1].ravel()
+        hL.append(pa); hR.append(pb)
+    ios = []
+    out_views = []
+    for s in range(N_SLOTS):
+        io = capi.FrameIO()
+        io.want, io.rectify, io.inputs_on_device, io.outputs_on_device = want, int(c["rectify"]), 0, 0
+        df, io.disparity32f = pinned(n * 4)
+        pc, io.pointcloud2 = pinned(n * 32)
+        if c["rectify"]:
+            rl, io.rect_left = pinned(n)
+            rr, io.rect_right = pinned(n)
+        ios.append(io)
+        out_views.append((df, pc))
+    h2d = 2 * n * FRAMES_PER_STEP
+    d2h = (n * 4 + n * 32 + (2 * n if c["rectify"] else 0)) * FRAMES_PER_STEP
+
+    def step_host():
+        for i in range(FRAMES_PER_STEP):
+            s = i % N_SLOTS
+            if i >= N_SLOTS:
+                proc.waitSlot(s)          # the slot's pinned output buffers are about to be overwritten
+            proc.processPairAsync(s, hL[i], hR[i], ios[s])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        l0 = proc.kernelLaunches()
+        proc.batchBegin()
+        for _ in range(steps):
+            step_fn()
+        ms = proc.batchEnd()
+        l1 = proc.kernelLaunches()
+        barrier()
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda:%d" % dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, l1 - l0
+
+    sampler = ClockSampler(dev)
+    sampler.start()
+    ms_dev, launches = timed(step_device, args.steps, args.warmup)
+    ms_e2e, _ = timed(step_host, args.steps, max(1, args.warmup))
+    clocks = sampler.stop()
+
+    frames_total = FRAMES_PER_STEP * args.steps * world
+    fps_dev = frames_total / (ms_dev * 1e-3)
+    fps_e2e = frames_total / (ms_e2e * 1e-3)
+    nominal, eff = evals_per_frame(c)
+
+    # ---- roofline of the dominant kernel: matcher alone, one stream, CUDA events around it -----------------
+    roof, cpu_base, int_peaks = None, None, None
+    if rank == 0:
+        proc.enableTiming(True)
+        ts = []
+        for rep in range(2):
+            for i in range(FRAMES_PER_STEP):
+                proc.processPairAsync(0, dL[i].data_ptr(), dR[i].data_ptr(), io_dev)
+                proc.waitSlot(0)
+                t_ms, ev = proc.lastBmTime(0)
+                if rep == 1:
+                    ts.append(t_ms)
+        proc.enableTiming(False)
+        t_bm = float(np.mean(ts)) * 1e-3
+        names = ["iadd3", "vabsdiff4", "viadd16x2", "vimnmx16x2", "imad", "prmt", "lop3", "iadd3+imad"]
+        int_peaks = {}
+        for wch, nm in enumerate(names):
+            ops, mhz = proc.intPeak(wch)
+            int_peaks[nm] = ops / 1e12
+        peak_tops = int_peaks["iadd3"]
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak, hbm_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        if os.path.exists(peaks_file):
+            hbm_peak, hbm_src = float(json.load(open(peaks_file))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        achieved = eff * 7 / t_bm / 1e12
+        alg_bytes = 2 * n + 2 * n     # two prefiltered u8 planes in, one s16 disparity plane out
+        roof = dict(bound="int-alu", kernel="bm_fast_kernel<64>", achieved=achieved, peak=peak_tops, unit="Tops/s (scalar-equivalent int32 lane-ops, 7 per disparity evaluation)",
+                    frac=achieved / peak_tops, peak_source="measured: b200s_int_peak IADD3 dependent chains, all SMs, this run",
+                    kernel_ms=t_bm * 1e3, evals_effective_per_launch=eff, gevals_per_s=eff / t_bm / 1e9, traffic=None,
+                    hbm=dict(achieved=alg_bytes / t_bm / 1e9, peak=hbm_peak, unit="GB/s", frac=alg_bytes / t_bm / 1e9 / hbm_peak,
+                             algorithmic_bytes=alg_bytes, peak_source=hbm_src),
+                    int_peaks_tops=int_peaks, share_of_step=t_bm * FRAMES_PER_STEP / (ms_dev * 1e-3 / args.steps))
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            import cv2
+            fps_cpu, ncpu = cpu_chain(frames, cal, c, reps_budget_s=args.cpu_seconds, threads=threads)
+            cpu_base = dict(value=fps_cpu, unit="frames/s", cores=threads, kind="reference",
+                            sample="cv2 %s full chain (remap x2, StereoBM, convertTo, reprojectImageTo3D, PointCloud2 fill) on %d frames of the same workload, %d threads"
+                                   % (cv2.__version__, ncpu, threads))
+
+    for ptr in pins:
+        proc.hostFree(ptr)
+    proc.close()
+    if rank == 0:
+        line = dict(metric="stereo_frames_per_sec", value=fps_dev, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8", data="synthetic",
+                    mdisp_evals_per_s=fps_dev * nominal / 1e6, mdisp_evals_effective_per_s=fps_dev * eff / 1e6,
+                    config=dict(workload=workload_name(c, name), frames_per_step_per_gpu=FRAMES_PER_STEP, slots=N_SLOTS,
+                                sharding="independent frames per GPU, no collective",
+                                l2="no flush: each step cycles %d distinct frames; per-step working set %.0f MB (inputs %.0f MB + outputs over %d slots) exceeds the 126 MB L2"
+                                   % (FRAMES_PER_STEP, (2 * n * FRAMES_PER_STEP + N_SLOTS * n * 46) / 1e6, 2 * n * FRAMES_PER_STEP / 1e6, N_SLOTS)),
+                    e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps,
+                             mdisp_evals_per_s=fps_e2e * nominal / 1e6),
+                    gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu_base)
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C4", choices=list(CONFIGS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    c = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, c, args.config, rank, world)
+    else:
+        run_ours(args, c, args.config, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

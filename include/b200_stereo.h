@@ -189,6 +189,12 @@ int b200s_slot_device_ptr(b200s_handle* h, int slot, uint32_t which /* one B200S
 /* synchronous convenience: slot 0, process + wait */
 int b200s_process_pair(b200s_handle* h, const void* left, const void* right, const b200s_frame_io* io);
 
+/* Device-side timing of a batch of frames spread over the slots (CUDA events on the slot streams): begin() syncs
+ * the device, records a start event and makes every slot stream wait on it; end() records one event per slot
+ * stream, waits for all of them and returns the longest start->end span in ms. */
+int b200s_batch_begin(b200s_handle* h);
+int b200s_batch_end(b200s_handle* h, float* ms);
+
 /* ---- instrumentation ------------------------------------------------------------------------------------------ */
 /* number of kernels this library has launched on this handle since creation (bench.py's gpu_launches) */
 uint64_t b200s_kernel_launches(const b200s_handle* h);

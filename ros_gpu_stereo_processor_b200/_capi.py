@@ -88,6 +88,8 @@ SYMBOLS = {
     "b200s_wait_slot": (C.c_int, [H, C.c_int]),
     "b200s_slot_device_ptr": (C.c_int, [H, C.c_int, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "b200s_process_pair": (C.c_int, [H, C.c_void_p, C.c_void_p, C.POINTER(FrameIO)]),
+    "b200s_batch_begin": (C.c_int, [H]),
+    "b200s_batch_end": (C.c_int, [H, C.POINTER(C.c_float)]),
     "b200s_kernel_launches": (C.c_uint64, [H]),
     "b200s_last_bm_time": (C.c_int, [H, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
     "b200s_enable_timing": (C.c_int, [H, C.c_int]),

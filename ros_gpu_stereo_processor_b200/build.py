@@ -46,7 +46,7 @@ def build_library(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(LIB, objs):
-        subprocess.check_call([NVCC, "-shared", "-cudart", "static", "-o", LIB] + objs)
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", LIB] + objs)
     return LIB
 
 

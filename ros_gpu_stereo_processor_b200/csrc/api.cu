@@ -107,6 +107,8 @@ struct b200s_handle {
     cudaEvent_t ev_r = nullptr;
     Work w0;                  // scratch of the named-buffer API (runs on l_strm)
     std::vector<Work> slots;
+    std::vector<cudaEvent_t> batch_end;
+    cudaEvent_t batch_start = nullptr;
     int slot_rows = 0, slot_cols = 0;
     uint64_t launches = 0;
 };
@@ -395,6 +397,8 @@ int b200s_destroy(b200s_handle* h)
     for (int s = 0; s < 2; ++s) h->cam[s].map.release();
     h->Qdev.release();
     if (h->ev_r) cudaEventDestroy(h->ev_r);
+    if (h->batch_start) cudaEventDestroy(h->batch_start);
+    for (cudaEvent_t e : h->batch_end) cudaEventDestroy(e);
     if (h->l_strm) cudaStreamDestroy(h->l_strm);
     if (h->r_strm) cudaStreamDestroy(h->r_strm);
     delete h;
@@ -953,6 +957,39 @@ int b200s_process_pair(b200s_handle* h, const void* left, const void* right, con
     int rc = b200s_process_pair_async(h, 0, left, right, io);
     if (rc) return rc;
     return b200s_wait_slot(h, 0);
+}
+
+// ---- batch timing: one start event all slot streams wait on, one end event per slot stream ----------------
+int b200s_batch_begin(b200s_handle* h)
+{
+    if (!h || h->slots.empty()) return B200S_EINVAL;
+    DeviceGuard g(h->device);
+    if (!h->batch_start) CUDA_OK(h, cudaEventCreate(&h->batch_start));
+    while (h->batch_end.size() < h->slots.size()) {
+        cudaEvent_t e;
+        CUDA_OK(h, cudaEventCreate(&e));
+        h->batch_end.push_back(e);
+    }
+    CUDA_OK(h, cudaDeviceSynchronize());
+    CUDA_OK(h, cudaEventRecord(h->batch_start, h->slots[0].st));
+    for (size_t i = 1; i < h->slots.size(); ++i) CUDA_OK(h, cudaStreamWaitEvent(h->slots[i].st, h->batch_start, 0));
+    return B200S_OK;
+}
+
+int b200s_batch_end(b200s_handle* h, float* ms)
+{
+    if (!h || !ms || !h->batch_start || h->batch_end.size() < h->slots.size()) return B200S_EINVAL;
+    DeviceGuard g(h->device);
+    for (size_t i = 0; i < h->slots.size(); ++i) CUDA_OK(h, cudaEventRecord(h->batch_end[i], h->slots[i].st));
+    float best = 0;
+    for (size_t i = 0; i < h->slots.size(); ++i) {
+        CUDA_OK(h, cudaEventSynchronize(h->batch_end[i]));
+        float t = 0;
+        CUDA_OK(h, cudaEventElapsedTime(&t, h->batch_start, h->batch_end[i]));
+        if (t > best) best = t;
+    }
+    *ms = best;
+    return B200S_OK;
 }
 
 // ---- instrumentation -------------------------------------------------------------------------------------

@@ -330,6 +330,36 @@ class GpuStereoProcessor(object):
         self.waitSlot(0)
         return out
 
+    def batchBegin(self):
+        self._ck(self._lib.b200s_batch_begin(self._h))
+
+    def batchEnd(self):
+        ms = C.c_float()
+        self._ck(self._lib.b200s_batch_end(self._h, C.byref(ms)))
+        return ms.value
+
+    def hostAlloc(self, nbytes):
+        """Pinned host buffer as a numpy uint8 array (cudaHostAlloc)."""
+        p = C.c_void_p()
+        rc = self._lib.b200s_host_alloc(C.byref(p), int(nbytes))
+        if rc != 0:
+            raise capi.B200StereoError(rc, "cudaHostAlloc failed")
+        buf = (C.c_uint8 * int(nbytes)).from_address(p.value)
+        return np.frombuffer(buf, np.uint8), p.value
+
+    def hostFree(self, ptr):
+        self._lib.b200s_host_free(C.c_void_p(ptr))
+
+    def slotDevicePtr(self, slot, which):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self._lib.b200s_slot_device_ptr(self._h, int(slot), int(which), C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def devicePtr(self, mat_source):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self._lib.b200s_device_ptr(self._h, int(mat_source), C.byref(p), C.byref(n)))
+        return p.value, n.value
+
     # ---- instrumentation ------------------------------------------------------------------------------
     def kernelLaunches(self):
         return int(self._lib.b200s_kernel_launches(self._h))
