@@ -276,6 +276,19 @@ int ensure_map(b200s_handle* h, int side /*0 L, 1 R*/, cudaStream_t st)
     return check_kernels(h, "build_map");
 }
 
+// pitched prefiltered planes with readable slack on both sides (zeroed once so that stray reads are defined)
+int ensure_pre_planes(b200s_handle* h, Work& w, int rows, int cols)
+{
+    size_t need = plane_bytes(cols, rows);
+    for (DevBuf* b : {&w.preL, &w.preR}) {
+        if (b->cap < need) {
+            if (b->ensure(need)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (prefilter planes)");
+            if (cudaMemset(b->p, 0, need) != cudaSuccess) return fail(h, B200S_ECUDA, "cudaMemset failed (prefilter planes)");
+        }
+    }
+    return B200S_OK;
+}
+
 // prefilter + match + post-filters on rectified device planes; disp must hold rows*cols int16
 int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, bool already_prefiltered, int rows,
                   int cols, int16_t* disp, cudaStream_t st)
@@ -287,20 +300,25 @@ int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, 
         return fail(h, B200S_EINVAL, "SADWindowSize must be odd, be within 5..255 and be not larger than image width or height");
     size_t n = (size_t)rows * cols;
     BMConfig cfg = bm_config(p);
-    const uint8_t *Lp = L, *Rp = R;
+    const size_t pitch = plane_pitch(cols);
     if (!already_prefiltered) {
-        if (w.preL.ensure(n + 64) || w.preR.ensure(n + 64)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (prefilter planes)");
+        int rc2 = ensure_pre_planes(h, w, rows, cols);
+        if (rc2) return rc2;
+        uint8_t* pl = (uint8_t*)w.preL.p + PLANE_LEAD;
+        uint8_t* pr = (uint8_t*)w.preR.p + PLANE_LEAD;
         if (p.pre_filter_type == 1) {
-            h->launches += launch_prefilter_xsobel(L, (uint8_t*)w.preL.p, cols, rows, p.pre_filter_cap, st);
-            h->launches += launch_prefilter_xsobel(R, (uint8_t*)w.preR.p, cols, rows, p.pre_filter_cap, st);
+            h->launches += launch_prefilter_xsobel(L, pl, pitch, cols, rows, p.pre_filter_cap, st);
+            h->launches += launch_prefilter_xsobel(R, pr, pitch, cols, rows, p.pre_filter_cap, st);
         } else {
             if (w.normtmp.ensure(n * sizeof(int))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (prefilter scratch)");
-            h->launches += launch_prefilter_norm(L, (uint8_t*)w.preL.p, cols, rows, p.pre_filter_size, p.pre_filter_cap, (int*)w.normtmp.p, st);
-            h->launches += launch_prefilter_norm(R, (uint8_t*)w.preR.p, cols, rows, p.pre_filter_size, p.pre_filter_cap, (int*)w.normtmp.p, st);
+            h->launches += launch_prefilter_norm(L, pl, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, (int*)w.normtmp.p, st);
+            h->launches += launch_prefilter_norm(R, pr, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, (int*)w.normtmp.p, st);
         }
-        Lp = (const uint8_t*)w.preL.p;
-        Rp = (const uint8_t*)w.preR.p;
     }
+    // the matcher always reads the pitched, slack-padded prefiltered planes of this Work
+    const uint8_t* Lp = (const uint8_t*)w.preL.p + PLANE_LEAD;
+    const uint8_t* Rp = (const uint8_t*)w.preR.p + PLANE_LEAD;
+    (void)L; (void)R;
     int16_t* cost = nullptr;
     if (cfg.disp12MaxDiff >= 0) {
         if (w.cost.ensure(n * sizeof(int16_t))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (cost plane)");
@@ -312,7 +330,7 @@ int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, 
         if (!w.ev_bm0) { cudaEventCreate(&w.ev_bm0); cudaEventCreate(&w.ev_bm1); }
         cudaEventRecord(w.ev_bm0, st);
     }
-    int l = launch_block_match(Lp, Rp, cols, rows, cfg, disp, cost, &sc, st, &w.last_evals);
+    int l = launch_block_match(Lp, Rp, pitch, cols, rows, cfg, disp, cost, &sc, st, &w.last_evals);
     if (h->timing) { cudaEventRecord(w.ev_bm1, st); w.timed = true; }
     if (l < 0) return fail(h, B200S_ECUDA, "block matcher launch failed (code " + std::to_string(l) + "): " + cudaGetErrorString(cudaGetLastError()));
     h->launches += l;
@@ -872,9 +890,11 @@ int b200s_process_pair_async(b200s_handle* h, int slot, const void* left, const 
             mapR = (const int2*)h->cam[1].map.p;
         }
         if (h->prm.pre_filter_type == 1) {
-            if (w.preL.ensure(n + 64) || w.preR.ensure(n + 64)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (prefilter planes)");
-            h->launches += launch_rectify_xsobel(L, cols, rows, mapL, h->cam[0].cm, (uint8_t*)w.rectL.p, (uint8_t*)w.preL.p, cols, rows, h->prm.pre_filter_cap, st);
-            h->launches += launch_rectify_xsobel(R, cols, rows, mapR, h->cam[1].cm, (uint8_t*)w.rectR.p, (uint8_t*)w.preR.p, cols, rows, h->prm.pre_filter_cap, st);
+            int rc2 = ensure_pre_planes(h, w, rows, cols);
+            if (rc2) return rc2;
+            const size_t pitch = plane_pitch(cols);
+            h->launches += launch_rectify_xsobel(L, cols, rows, mapL, h->cam[0].cm, (uint8_t*)w.rectL.p, (uint8_t*)w.preL.p + PLANE_LEAD, pitch, cols, rows, h->prm.pre_filter_cap, st);
+            h->launches += launch_rectify_xsobel(R, cols, rows, mapR, h->cam[1].cm, (uint8_t*)w.rectR.p, (uint8_t*)w.preR.p + PLANE_LEAD, pitch, cols, rows, h->prm.pre_filter_cap, st);
             prefiltered = true;
         } else {
             h->launches += launch_remap(L, cols, rows, 1, mapL, h->cam[0].cm, (uint8_t*)w.rectL.p, cols, rows, st);
@@ -884,8 +904,7 @@ int b200s_process_pair_async(b200s_handle* h, int slot, const void* left, const 
         rr = (const uint8_t*)w.rectR.p;
     }
     if (w.disp.ensure(n * 2 + 64)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (disparity plane)");
-    int rc = run_disparity(h, w, prefiltered ? (const uint8_t*)w.preL.p : rl, prefiltered ? (const uint8_t*)w.preR.p : rr,
-                           prefiltered, rows, cols, (int16_t*)w.disp.p, st);
+    int rc = run_disparity(h, w, rl, rr, prefiltered, rows, cols, (int16_t*)w.disp.p, st);
     if (rc) return rc;
     const bool want_pc = io->want & B200S_OUT_POINTCLOUD2, want_xyz = io->want & B200S_OUT_POINTS_XYZ;
     const bool want_df = io->want & B200S_OUT_DISPARITY32F;

@@ -25,14 +25,15 @@ int launch_remap(const uint8_t* src, int sW, int sH, int ch, const int2* map, co
                  uint8_t* dst, int W, int H, cudaStream_t st);
 // fused rectify (mono) + x-Sobel prefilter: writes the rectified plane and the prefiltered plane in one kernel
 int launch_rectify_xsobel(const uint8_t* src, int sW, int sH, const int2* map, const CamModel& cm,
-                          uint8_t* rect, uint8_t* pre, int W, int H, int cap, cudaStream_t st);
+                          uint8_t* rect, uint8_t* pre, size_t pre_pitch, int W, int H, int cap, cudaStream_t st);
 int launch_remap_nearest(const uint8_t* src, int sW, int sH, int ch, const int2* map, const CamModel& cm,
                          uint8_t* dst, int W, int H, cudaStream_t st);
 
 // ---- prefilter.cu -----------------------------------------------------------------------------------
-int launch_prefilter_xsobel(const uint8_t* src, uint8_t* dst, int W, int H, int cap, cudaStream_t st);
+// dst rows are `dst_pitch` bytes apart (src is tightly packed)
+int launch_prefilter_xsobel(const uint8_t* src, uint8_t* dst, size_t dst_pitch, int W, int H, int cap, cudaStream_t st);
 // scratch: W*H int32
-int launch_prefilter_norm(const uint8_t* src, uint8_t* dst, int W, int H, int ps, int cap, int* scratch, cudaStream_t st);
+int launch_prefilter_norm(const uint8_t* src, uint8_t* dst, size_t dst_pitch, int W, int H, int ps, int cap, int* scratch, cudaStream_t st);
 int launch_bgr_to_gray(const uint8_t* src, uint8_t* dst, int n, int rgb_order, cudaStream_t st);
 int launch_gray_to_bgr(const uint8_t* src, uint8_t* dst, int n, cudaStream_t st);
 int launch_swap_rb(const uint8_t* src, uint8_t* dst, int n, cudaStream_t st);
@@ -46,8 +47,13 @@ struct BMScratch {         // device scratch owned by the caller
 // When cfg.disp12MaxDiff < 0 the valid-ROI mask is applied directly (pixels outside are FILTERED);
 // otherwise all columns [lofs, lofs+width1) of the ROI rows are produced and the caller runs validate + mask.
 // evals (optional) receives the number of (pixel, disparity) evaluations inside the valid ROI.
-int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, int W, int H, const BMConfig& cfg,
+// Lp/Rp: prefiltered planes with row pitch `pitch` (multiple of 16) and at least PLANE_LEAD bytes of readable
+// slack before row 0 and PLANE_TAIL bytes after the last row (the tile loaders read whole aligned words).
+int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg,
                        int16_t* disp, int16_t* cost, BMScratch* scratch, cudaStream_t st, double* evals);
+constexpr size_t PLANE_LEAD = 256, PLANE_TAIL = 4096;
+inline size_t plane_pitch(int W) { return ((size_t)W + 15) / 16 * 16; }
+inline size_t plane_bytes(int W, int H) { return PLANE_LEAD + plane_pitch(W) * H + PLANE_TAIL; }
 size_t bm_scratch_bytes(int W, int H, const BMConfig& cfg);
 
 // ---- post.cu ----------------------------------------------------------------------------------------

@@ -7,7 +7,7 @@ namespace b200s {
 
 // x-Sobel with OpenCV's border rules: rows mirrored (reflect-101), columns 0/W-1 = cap, odd-height last row = cap.
 __global__ void __launch_bounds__(256) xsobel_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
-                                                     int W, int H, int cap)
+                                                     size_t dpitch, int W, int H, int cap)
 {
     int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= W || y >= H) return;
@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(256) xsobel_kernel(const uint8_t* __restrict__
                 ((int)__ldg(r2 + 1) - (int)__ldg(r2 - 1));
         out = min(max(v, -cap), cap) + cap;
     }
-    dst[(size_t)y * W + x] = (uint8_t)out;
+    dst[(size_t)y * dpitch + x] = (uint8_t)out;
 }
 
 // normalised response: vertical box sums (replicate) into scratch, then horizontal box + centre term
@@ -37,8 +37,8 @@ __global__ void __launch_bounds__(256) norm_vsum_kernel(const uint8_t* __restric
 }
 
 __global__ void __launch_bounds__(256) norm_final_kernel(const uint8_t* __restrict__ src, const int* __restrict__ vs,
-                                                         uint8_t* __restrict__ dst, int W, int H, int p2, int scale_g,
-                                                         int scale_s, int cap)
+                                                         uint8_t* __restrict__ dst, size_t dpitch, int W, int H, int p2,
+                                                         int scale_g, int scale_s, int cap)
 {
     int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= W || y >= H) return;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) norm_final_kernel(const uint8_t* __restri
             src[(size_t)min(y + 1, H - 1) * W + x];
     long long val = ((long long)c * scale_g - sum * scale_s) >> 10;
     int v = (int)max(-(long long)cap, min((long long)cap, val)) + cap;
-    dst[(size_t)y * W + x] = (uint8_t)v;
+    dst[(size_t)y * dpitch + x] = (uint8_t)v;
 }
 
 __global__ void bgr_to_gray_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int n, int rgb)
@@ -80,19 +80,19 @@ __global__ void swap_rb_kernel(const uint8_t* __restrict__ src, uint8_t* __restr
 
 static inline dim3 grid2d(int W, int H) { return dim3((W + 31) / 32, (H + 7) / 8); }
 
-int launch_prefilter_xsobel(const uint8_t* src, uint8_t* dst, int W, int H, int cap, cudaStream_t st)
+int launch_prefilter_xsobel(const uint8_t* src, uint8_t* dst, size_t dst_pitch, int W, int H, int cap, cudaStream_t st)
 {
-    xsobel_kernel<<<grid2d(W, H), 256, 0, st>>>(src, dst, W, H, cap);
+    xsobel_kernel<<<grid2d(W, H), 256, 0, st>>>(src, dst, dst_pitch, W, H, cap);
     return 1;
 }
 
-int launch_prefilter_norm(const uint8_t* src, uint8_t* dst, int W, int H, int ps, int cap, int* scratch, cudaStream_t st)
+int launch_prefilter_norm(const uint8_t* src, uint8_t* dst, size_t dst_pitch, int W, int H, int ps, int cap, int* scratch, cudaStream_t st)
 {
     int p2 = ps / 2;
     int scale_g = ps * ps / 8, scale_s = (1024 + scale_g) / (scale_g * 2);
     scale_g *= scale_s;
     norm_vsum_kernel<<<grid2d(W, H), 256, 0, st>>>(src, scratch, W, H, p2);
-    norm_final_kernel<<<grid2d(W, H), 256, 0, st>>>(src, scratch, dst, W, H, p2, scale_g, scale_s, cap);
+    norm_final_kernel<<<grid2d(W, H), 256, 0, st>>>(src, scratch, dst, dst_pitch, W, H, p2, scale_g, scale_s, cap);
     return 2;
 }
 

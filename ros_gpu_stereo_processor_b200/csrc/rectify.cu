@@ -99,7 +99,7 @@ template <bool FLY>
 __global__ void __launch_bounds__(256) rectify_xsobel_kernel(const uint8_t* __restrict__ src, int sW, int sH,
                                                              const int2* __restrict__ map, CamModel cm,
                                                              uint8_t* __restrict__ rect, uint8_t* __restrict__ pre,
-                                                             int W, int H, int cap)
+                                                             size_t ppitch, int W, int H, int cap)
 {
     __shared__ uint8_t tile[FTY + 2][FTX + 2 + 2];
     const int x0 = blockIdx.x * FTX, y0 = blockIdx.y * FTY;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) rectify_xsobel_kernel(const uint8_t* __re
             int v = d0 + 2 * d1 + d2;
             out = min(max(v, -cap), cap) + cap;
         }
-        pre[(size_t)y * W + x] = (uint8_t)out;
+        pre[(size_t)y * ppitch + x] = (uint8_t)out;
     }
 }
 
@@ -169,11 +169,11 @@ int launch_remap_nearest(const uint8_t* src, int sW, int sH, int ch, const int2*
 }
 
 int launch_rectify_xsobel(const uint8_t* src, int sW, int sH, const int2* map, const CamModel& cm, uint8_t* rect,
-                          uint8_t* pre, int W, int H, int cap, cudaStream_t st)
+                          uint8_t* pre, size_t pre_pitch, int W, int H, int cap, cudaStream_t st)
 {
     dim3 g((W + FTX - 1) / FTX, (H + FTY - 1) / FTY);
-    if (map) rectify_xsobel_kernel<false><<<g, 256, 0, st>>>(src, sW, sH, map, cm, rect, pre, W, H, cap);
-    else rectify_xsobel_kernel<true><<<g, 256, 0, st>>>(src, sW, sH, map, cm, rect, pre, W, H, cap);
+    if (map) rectify_xsobel_kernel<false><<<g, 256, 0, st>>>(src, sW, sH, map, cm, rect, pre, pre_pitch, W, H, cap);
+    else rectify_xsobel_kernel<true><<<g, 256, 0, st>>>(src, sW, sH, map, cm, rect, pre, pre_pitch, W, H, cap);
     return 1;
 }
 
