@@ -34,19 +34,20 @@ __global__ void fill_s16_kernel(int16_t* p, size_t n, int16_t v)
 }
 
 // ------------------------------------------------------------------------------------------------------
-// fast kernel (v2)
+// fast kernel (v3)
 //
 // One block = TW output columns x BH output rows, all nd disparities; it marches down the rows.  Per row:
-//   V  thread = (4 adjacent window columns, 16 disparities): abs-diff of the entering and the leaving row
-//      (VABSDIFF4.U8 on 4 disparities at a time; the right-image window of column i is the thread's 20-byte
-//      register window funnel-shifted by i bytes), biased byte delta, widened to u16x2 lanes and added to the
-//      32 column-sum registers; the sums go to shared memory (Cbuf, 16-byte units XOR-swizzled by column).
-//   H  thread = (8 disparities, strip of columns): horizontal sliding sum over the 2r+1 window columns -> Sbuf.
-//   W  LPP lanes per pixel: packed u16x2 minima per 16 disparities -> 32-bit key (sad << 16 | chunk) -> argmin;
-//      exact index inside the winning chunk; uniqueness by a second packed-min pass with the winner and its two
-//      neighbours masked; texture; sub-pixel fit.  While W runs, the next two image rows are staged.
-// Shared memory per row pass: right rows as 4 word-shifted copies (so that every 20-byte window is one
-// aligned LDS.128 + LDS.32), left rows pre-broadcast to 4 bytes.
+//   V  thread = (4 adjacent window columns, two groups of 8 disparities): abs-diff of the entering and the leaving
+//      row (VABSDIFF4.U8, 4 disparities per instruction; the right-image window of column i is the thread's
+//      register window funnel-shifted by i bytes), biased byte delta, widened to u16x2 lanes and added to the 32
+//      column-sum registers; the sums go to shared memory (Cbuf, one row per window column, linear).
+//   H  thread = (8 disparities, strip of columns): horizontal sliding sum over the 2r+1 window columns -> Sbuf,
+//      plus one 32-bit key per (pixel, 8 disparities): packed-u16x2 minimum << 16 | group -> Kbuf.
+//   W  one thread per pixel: min over the keys -> winning group, exact index inside it (lowest index wins ties =
+//      largest disparity), uniqueness from the keys with the three neighbouring groups re-scanned exactly, texture,
+//      sub-pixel fit.  The threads that own no pixel stage the next two image rows meanwhile.
+// All shared-memory layouts are linear with compile-time strides (ND > 0) so that unrolled loops use immediate
+// offsets; row strides are odd multiples of 16 bytes where a warp walks over rows.
 // ------------------------------------------------------------------------------------------------------
 struct FastParams {
     const uint8_t* Lp;    // prefiltered planes, row pitch `pitch` (multiple of 16), with slack before/after
@@ -55,23 +56,21 @@ struct FastParams {
     int16_t* disp;        // tightly packed W
     int16_t* cost;        // may be null
     int W, H, nd, minD, r, cap, texThr, uniq, lofs;
-    int X0base, XB, YA, YB;   // first tile origin (<= XA, aligned), end of output columns, output rows
-    int XA;
-    int TW, BH, ncols;        // tile width, band height, window columns (multiple of 4)
-    int NCQ, NKG;             // V items: column quads x 16-disparity groups
-    int NGH, NS, SWD;         // H items: 8-disparity groups x strips of SWD columns
-    int CW;                   // words per Cbuf/Sbuf row (multiple of 32)
-    int CSB, RLW;             // bytes per right-row copy, words staged per right row
-    int oLb, oRc, oC, oS, oT; // shared memory byte offsets
+    int X0base, XA, XB, YA, YB;   // first tile origin (<= XA, aligned), output columns [XA, XB), output rows
+    int TW, BH, ncols;            // tile width, band height, window columns (= 4 * NCQ)
+    int NCQ, NK;                  // V items: column quads x (nd / 16) disparity groups
+    int NGH, NS, SWD;             // H items: (nd / 8) groups x strips of SWD columns
+    int CWb, SWb, KWb;            // row strides of Cbuf / Sbuf / Kbuf in bytes
+    int NK4;                      // uint4 loads per Kbuf row
+    int CSB, RLW;                 // bytes per right-row copy, words staged per right row
+    int stage_from;               // threads >= stage_from stage rows during phase W
+    int oLb, oRc, oT, oK, oC, oS; // shared memory byte offsets
 };
 
 // position of disparity index k inside a group of four u16 lanes (V-phase lane order is k, k+2, k+1, k+3)
 __device__ __forceinline__ int kpos(int k) { return (k & ~3) | ((k & 1) << 1) | ((k >> 1) & 1); }
-// XOR swizzle of the 16-byte unit index inside an Sbuf row (conflict-free for 1, 2 and 4 lanes per pixel)
-__device__ __forceinline__ int swzS(int x) { return (x & 1) | ((x & 2) << 1) | ((x & 4) >> 1); }
-__device__ __forceinline__ int swzC(int c) { return (c >> 2) & 7; }
 
-__device__ __forceinline__ void stage_rows(const FastParams& P, uint8_t* smem, int tid, int NT, int yi, bool has_old,
+__device__ __forceinline__ void stage_rows(const FastParams& P, uint8_t* smem, int t, int nt, int yi, bool has_old,
                                            int Xl0, int Xr0)
 {
     uint32_t* sLb = (uint32_t*)(smem + P.oLb);
@@ -79,13 +78,13 @@ __device__ __forceinline__ void stage_rows(const FastParams& P, uint8_t* smem, i
     const int b = 2 * P.r + 1;
     const uint8_t* ln = P.Lp + (size_t)yi * P.pitch + Xl0;
     const uint8_t* lo = P.Lp + (size_t)max(yi - b, 0) * P.pitch + Xl0;
-    for (int c = tid; c < P.ncols; c += NT) {
+    for (int c = t; c < P.ncols; c += nt) {
         sLb[c] = (uint32_t)__ldg(ln + c) * 0x01010101u;
         sLb[P.ncols + c] = has_old ? (uint32_t)__ldg(lo + c) * 0x01010101u : 0u;
     }
     const uint32_t* rn = (const uint32_t*)(P.Rp + (size_t)yi * P.pitch + Xr0);          // Xr0 % 4 == 0, pitch % 16 == 0
     const uint32_t* ro = (const uint32_t*)(P.Rp + (size_t)max(yi - b, 0) * P.pitch + Xr0);
-    for (int i = tid; i < 2 * P.RLW; i += NT) {
+    for (int i = t; i < 2 * P.RLW; i += nt) {
         const int s = i >= P.RLW;
         const int wi = i - s * P.RLW;
         uint32_t v = s ? (has_old ? __ldg(ro + wi) : 0u) : __ldg(rn + wi);
@@ -97,37 +96,57 @@ __device__ __forceinline__ void stage_rows(const FastParams& P, uint8_t* smem, i
     }
 }
 
-template <int LPP>
+template <int ND>
 __global__ void __launch_bounds__(384, 2) bm_fast_kernel(const FastParams P)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t* sLb = (const uint32_t*)(smem + P.oLb);   // [2][ncols]  left bytes x 0x01010101
     const uint8_t* sRc = smem + P.oRc;                       // [2][4][CSB] right row, copy j shifted by 4j bytes
-    uint32_t* sC = (uint32_t*)(smem + P.oC);                 // [ncols][CW] column sums, u16x2
-    uint32_t* sS = (uint32_t*)(smem + P.oS);                 // [TW][CW]    window sums, u16x2
     uint32_t* sT = (uint32_t*)(smem + P.oT);                 // [ncols]     texture column sums
+    uint8_t* sK = smem + P.oK;                               // [rowsS][KWb] keys
+    uint8_t* sC = smem + P.oC;                               // [rowsC][CWb] column sums, u16x2
+    uint8_t* sS = smem + P.oS;                               // [rowsS][SWb] window sums, u16x2
+
+    const int nd = ND > 0 ? ND : P.nd;
+    const int CWb = ND > 0 ? ND * 2 : P.CWb;
+    const int SWb = ND > 0 ? ND * 2 + 16 : P.SWb;
+    const int KWb = ND > 0 ? (((ND / 8 + 3) / 4) * 4 + 4) * 4 : P.KWb;
+    const int NK = ND > 0 ? ND / 16 : P.NK;
+    const int NGH = ND > 0 ? ND / 8 : P.NGH;
+    const int NK4 = ND > 0 ? (ND / 8 + 3) / 4 : P.NK4;
 
     const int tid = threadIdx.x, NT = blockDim.x;
     const int X0 = P.X0base + blockIdx.x * P.TW;             // first output column of the tile
     const int yb0 = P.YA + blockIdx.y * P.BH;
     const int yb1 = min(yb0 + P.BH, P.YB);
-    const int r = P.r, b = 2 * r + 1, nd = P.nd;
+    const int r = P.r, b = 2 * r + 1;
     const int Xl0 = X0 - r;               // left image column of window column c = 0
     const int Xr0 = X0 - r - P.lofs;      // right image column of (c = 0, k = 0); multiple of 4 by construction
 
-    // V identity: lanes run over column quads first (bank-conflict-free stores with the column swizzle)
-    const int cq = tid % P.NCQ, kg = tid / P.NCQ;
-    const bool vact = kg < P.NKG;
-    uint32_t C[4][8];
+    // V identity: lanes run over the disparity groups of one column quad (contiguous 16-byte units per store)
+    const int cq = tid / NK, kg = tid - cq * NK;
+    const bool vact = cq < P.NCQ;
+    uint32_t C[4][2][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int w = 0; w < 8; ++w) C[i][w] = 0;
-    for (int c = tid; c < P.ncols; c += NT) sT[c] = 0;
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) C[i][h][w] = 0;
+    const uint8_t* vpn[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int u = kg + h * NK;
+        const int j = (cq + 2 * u) & 3;
+        vpn[h] = sRc + (size_t)j * P.CSB + (4 * cq + 8 * u - 4 * j);
+    }
+    uint8_t* vst = sC + (size_t)(4 * cq) * CWb + 16 * kg;
     // H identity
-    const int gh = tid % P.NGH, hs = tid / P.NGH;
+    const int hs = tid / NGH, gh = tid - hs * NGH;
     const bool hact = hs < P.NS;
 
+    for (int c = tid; c < P.ncols; c += NT) sT[c] = 0;
+    for (int i = tid; i < (P.NS * P.SWD * KWb) / 4; i += NT) ((uint32_t*)sK)[i] = 0xFFFFFFFFu;   // pad keys stay "infinite"
     stage_rows(P, smem, tid, NT, yb0 - r, false, Xl0, Xr0);
     __syncthreads();
 
@@ -137,41 +156,35 @@ __global__ void __launch_bounds__(384, 2) bm_fast_kernel(const FastParams P)
         const bool do_out = yi >= yb0 + r;
         // ---- phase V ------------------------------------------------------------------------------------
         if (vact) {
-            const int j = cq & 3;
-            const int A = 4 * cq + 16 * kg;
-            const uint8_t* pn = sRc + (size_t)j * P.CSB + (A - 4 * j);
-            const uint8_t* po = pn + (size_t)4 * P.CSB;
-            const uint4 rn4 = *(const uint4*)pn;
-            const uint32_t rn5 = *(const uint32_t*)(pn + 16);
-            const uint4 ro4 = *(const uint4*)po;
-            const uint32_t ro5 = *(const uint32_t*)(po + 16);
             const uint4 ln4 = *(const uint4*)(sLb + 4 * cq);
             const uint4 lo4 = *(const uint4*)(sLb + P.ncols + 4 * cq);
-            const uint32_t rn[5] = {rn4.x, rn4.y, rn4.z, rn4.w, rn5};
-            const uint32_t ro[5] = {ro4.x, ro4.y, ro4.z, ro4.w, ro5};
             const uint32_t ln[4] = {ln4.x, ln4.y, ln4.z, ln4.w};
             const uint32_t lo[4] = {lo4.x, lo4.y, lo4.z, lo4.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int h = 0; h < 2; ++h) {
+                const uint4 rn4 = *(const uint4*)vpn[h];
+                const uint4 ro4 = *(const uint4*)(vpn[h] + (size_t)4 * P.CSB);
+                const uint32_t rn[3] = {rn4.x, rn4.y, rn4.z};
+                const uint32_t ro[3] = {ro4.x, ro4.y, ro4.z};
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const uint32_t wn = i ? __funnelshift_r(rn[w], rn[w + 1], 8 * i) : rn[w];
-                    const uint32_t wo = i ? __funnelshift_r(ro[w], ro[w + 1], 8 * i) : ro[w];
-                    const uint32_t an = __vabsdiffu4(ln[i], wn);
-                    const uint32_t ao = __vabsdiffu4(lo[i], wo);
-                    const uint32_t t = an + 0x80808080u - ao;        // per byte: 128 + new - old, no borrow
-                    C[i][2 * w] += t & 0x00ff00ffu;                  // lanes k+0, k+2   (bias 128 per lane kept)
-                    C[i][2 * w + 1] += __byte_perm(t, 0, 0x4341);    // lanes k+1, k+3
+                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        const uint32_t wn = i ? __funnelshift_r(rn[w], rn[w + 1], 8 * i) : rn[w];
+                        const uint32_t wo = i ? __funnelshift_r(ro[w], ro[w + 1], 8 * i) : ro[w];
+                        const uint32_t an = __vabsdiffu4(ln[i], wn);
+                        const uint32_t ao = __vabsdiffu4(lo[i], wo);
+                        const uint32_t t = an + 0x80808080u - ao;          // per byte: 128 + new - old, no borrow
+                        C[i][h][2 * w] += t & 0x00ff00ffu;                 // lanes k+0, k+2   (bias 128 per lane kept)
+                        C[i][h][2 * w + 1] += __byte_perm(t, 0, 0x4341);   // lanes k+1, k+3
+                    }
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c = 4 * cq + i;
-                uint32_t* row = sC + (size_t)c * P.CW;
-                const int sw = swzC(c);
-                *(uint4*)(row + 4 * ((2 * kg) ^ sw)) = make_uint4(C[i][0], C[i][1], C[i][2], C[i][3]);
-                *(uint4*)(row + 4 * ((2 * kg + 1) ^ sw)) = make_uint4(C[i][4], C[i][5], C[i][6], C[i][7]);
-            }
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    *(uint4*)(vst + (size_t)i * CWb + (size_t)h * (16 * NK)) = make_uint4(C[i][h][0], C[i][h][1], C[i][h][2], C[i][h][3]);
         }
         for (int c = tid; c < P.ncols; c += NT) {   // texture column sums live in shared memory (same owner every row)
             const int cap = P.cap;
@@ -187,114 +200,117 @@ __global__ void __launch_bounds__(384, 2) bm_fast_kernel(const FastParams P)
         }
         // ---- phase H ------------------------------------------------------------------------------------
         if (hact) {
-            const int xs = hs * P.SWD, xe = min(P.TW, xs + P.SWD);
-            if (xs < xe) {
-                // every column sum carries a bias of 128 * nrow per lane; remove b of them from the window sum
-                const uint32_t bias = (uint32_t)(128 * nrow * b) * 0x00010001u;
-                uint4 S = make_uint4(0u - bias, 0u - bias, 0u - bias, 0u - bias);
-                for (int c = xs; c < xs + b; ++c) {
-                    const uint4 v = *(const uint4*)(sC + (size_t)c * P.CW + 4 * (gh ^ swzC(c)));
-                    S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
-                }
-                for (int x = xs; x < xe; ++x) {
-                    *(uint4*)(sS + (size_t)x * P.CW + 4 * (gh ^ swzS(x))) = S;
-                    if (x + 1 < xe) {
-                        const int ca = x + b;
-                        const uint4 a = *(const uint4*)(sC + (size_t)ca * P.CW + 4 * (gh ^ swzC(ca)));
-                        const uint4 o = *(const uint4*)(sC + (size_t)x * P.CW + 4 * (gh ^ swzC(x)));
-                        S.x += a.x - o.x; S.y += a.y - o.y; S.z += a.z - o.z; S.w += a.w - o.w;
-                    }
-                }
+            const int xs = hs * P.SWD;
+            const uint8_t* pc = sC + (size_t)xs * CWb + 16 * gh;
+            // every column sum carries a bias of 128 * nrow per lane; remove b of them from the window sum
+            const uint32_t bias = (uint32_t)(128 * nrow * b) * 0x00010001u;
+            uint4 S = make_uint4(0u - bias, 0u - bias, 0u - bias, 0u - bias);
+            for (int c = 0; c < b; ++c) {
+                const uint4 v = *(const uint4*)(pc + (size_t)c * CWb);
+                S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
+            }
+            const uint8_t* pa = pc + (size_t)b * CWb;
+            uint8_t* ps = sS + (size_t)xs * SWb + 16 * gh;
+            uint8_t* pk = sK + (size_t)xs * KWb + 4 * gh;
+#pragma unroll 2
+            for (int x = 0; x < P.SWD; ++x) {
+                *(uint4*)ps = S;
+                uint32_t m = __vimin3_u16x2(S.x, S.y, S.z);
+                m = __vminu2(m, S.w);
+                m = __vminu2(m, m >> 16);
+                *(uint32_t*)pk = (m << 16) | (uint32_t)gh;
+                const uint4 a = *(const uint4*)pa;
+                const uint4 o = *(const uint4*)pc;
+                S.x += a.x - o.x; S.y += a.y - o.y; S.z += a.z - o.z; S.w += a.w - o.w;
+                pa += CWb; pc += CWb; ps += SWb; pk += KWb;
             }
         }
         __syncthreads();
-        // ---- phase W (+ staging of the next rows) ---------------------------------------------------------
-        if (yi + 1 < yb1 + r) stage_rows(P, smem, tid, NT, yi + 1, (yi + 1 - b) >= yb0 - r, Xl0, Xr0);
-        {
+        // ---- phase W (+ staging of the next rows by the threads that own no pixel) ----------------------------
+        if (tid >= P.stage_from && yi + 1 < yb1 + r)
+            stage_rows(P, smem, tid - P.stage_from, NT - P.stage_from, yi + 1, (yi + 1 - b) >= yb0 - r, Xl0, Xr0);
+        if (tid < P.TW) {
+            const int px = tid;
             const int y = yi - r;
             const int16_t FILTERED = (int16_t)((P.minD - 1) * 16);
-            const int q = tid & (LPP - 1);
-            const int npair = nd >> 4;                 // 16-disparity chunks per pixel
-            for (int base = 0; base < P.TW; base += NT / LPP) {
-                const int px = base + tid / LPP;
-                const int x = min(px, P.TW - 1);
-                uint32_t* srow = sS + (size_t)x * P.CW;
-                const int sw = swzS(x);
-                // pass A: per 16 disparities a packed minimum, then key = sad << 16 | chunk (lowest chunk wins ties)
-                uint32_t best = 0xFFFFFFFFu;
-                for (int pc = q; pc < npair; pc += LPP) {
-                    const uint4 u0 = *(const uint4*)(srow + 4 * ((2 * pc) ^ sw));
-                    const uint4 u1 = *(const uint4*)(srow + 4 * ((2 * pc + 1) ^ sw));
-                    uint32_t m = __vimin3_u16x2(u0.x, u0.y, u0.z);
-                    m = __vimin3_u16x2(m, u0.w, u1.x);
-                    m = __vimin3_u16x2(m, u1.y, u1.z);
-                    m = __vminu2(m, u1.w);
-                    m = __vminu2(m, m >> 16);
-                    best = min(best, (m << 16) | (uint32_t)pc);
-                }
-                if (LPP >= 2) best = min(best, __shfl_xor_sync(0xffffffffu, best, 1));
-                if (LPP >= 4) best = min(best, __shfl_xor_sync(0xffffffffu, best, 2));
-                const int minsad = (int)(best >> 16), pcs = (int)(best & 0xffffu);
-                // exact index inside the winning chunk, in disparity-index order (lowest k wins ties)
-                int mind;
-                {
-                    const uint4 u0 = *(const uint4*)(srow + 4 * ((2 * pcs) ^ sw));
-                    const uint4 u1 = *(const uint4*)(srow + 4 * ((2 * pcs + 1) ^ sw));
-                    const uint32_t wv[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-                    int loc = 15;
+            uint8_t* krow = sK + (size_t)px * KWb;
+            uint8_t* srow = sS + (size_t)px * SWb;
+            uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
-                    for (int kk = 15; kk >= 0; --kk) {
-                        // word of k-offset kk: group g4 = kk / 4, inside: (0: w0.lo, 1: w1.lo, 2: w0.hi, 3: w1.hi)
-                        const uint32_t w = wv[2 * (kk >> 2) + (kk & 1)];
-                        const uint32_t v = (kk & 2) ? (w >> 16) : (w & 0xffffu);
-                        if ((int)v == minsad) loc = kk;
-                    }
-                    mind = 16 * pcs + loc;
+            for (int i = 0; i < (ND > 0 ? NK4 : 1); ++i) {
+                if (ND > 0) {
+                    const uint4 k4 = *(const uint4*)(krow + 16 * i);
+                    best = min(min(best, k4.x), min(k4.y, min(k4.z, k4.w)));
                 }
-                int pv = 0, nv = 0;
-                const uint16_t* s16c = (const uint16_t*)srow;
-                if (q == 0) {
-                    const int kp = kpos(mind + 1 < nd ? mind + 1 : nd - 2), kn = kpos(mind > 0 ? mind - 1 : 1);
-                    pv = s16c[8 * ((kp >> 3) ^ sw) + (kp & 7)];
-                    nv = s16c[8 * ((kn >> 3) ^ sw) + (kn & 7)];
+            }
+            if (ND == 0)
+                for (int i = 0; i < NK4; ++i) {
+                    const uint4 k4 = *(const uint4*)(krow + 16 * i);
+                    best = min(min(best, k4.x), min(k4.y, min(k4.z, k4.w)));
                 }
-                bool filtered = false;
-                if (P.uniq > 0) {
-                    if (LPP > 1) __syncwarp();
-                    if (q == 0 && px < P.TW) {   // inactive lanes alias the last row and must not patch it
-                        uint16_t* s16 = (uint16_t*)srow;
-                        int kp = kpos(mind);
-                        s16[8 * ((kp >> 3) ^ sw) + (kp & 7)] = 0xFFFFu;
-                        if (mind > 0) { kp = kpos(mind - 1); s16[8 * ((kp >> 3) ^ sw) + (kp & 7)] = 0xFFFFu; }
-                        if (mind + 1 < nd) { kp = kpos(mind + 1); s16[8 * ((kp >> 3) ^ sw) + (kp & 7)] = 0xFFFFu; }
-                    }
-                    if (LPP > 1) __syncwarp();
-                    uint32_t acc = 0xFFFFFFFFu;
-                    for (int pc = q; pc < npair; pc += LPP) {
-                        const uint4 u0 = *(const uint4*)(srow + 4 * ((2 * pc) ^ sw));
-                        const uint4 u1 = *(const uint4*)(srow + 4 * ((2 * pc + 1) ^ sw));
-                        acc = __vimin3_u16x2(acc, u0.x, u0.y);
-                        acc = __vimin3_u16x2(acc, u0.z, u0.w);
-                        acc = __vimin3_u16x2(acc, u1.x, u1.y);
-                        acc = __vimin3_u16x2(acc, u1.z, u1.w);
-                    }
-                    uint32_t m2 = min(acc & 0xffffu, acc >> 16);
-                    if (LPP >= 2) m2 = min(m2, __shfl_xor_sync(0xffffffffu, m2, 1));
-                    if (LPP >= 4) m2 = min(m2, __shfl_xor_sync(0xffffffffu, m2, 2));
-                    const int thr = minsad + (minsad * P.uniq / 100);
-                    filtered = (int)m2 <= thr;
+            const int minsad = (int)(best >> 16), gs = (int)(best & 0xffffu);
+            // exact index inside the winning group, in disparity-index order (lowest k wins ties)
+            int mind;
+            {
+                const uint4 u = *(const uint4*)(srow + 16 * gs);
+                const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+                int loc = 7;
+#pragma unroll
+                for (int kk = 7; kk >= 0; --kk) {
+                    const uint32_t w = wv[2 * (kk >> 2) + (kk & 1)];
+                    const uint32_t v = (kk & 2) ? (w >> 16) : (w & 0xffffu);
+                    if ((int)v == minsad) loc = kk;
                 }
-                if (q == 0 && px < P.TW) {
-                    const int X = X0 + px;
-                    if (X >= P.XA && X < P.XB) {
-                        int tsum = 0;
-                        for (int c = px; c < px + b; ++c) tsum += (int)sT[c];
-                        int16_t out = FILTERED;
-                        if (tsum >= P.texThr && !filtered) out = subpixel_disp(minsad, mind, pv, nv, nd, P.minD);
-                        P.disp[(size_t)y * P.W + X] = out;
-                        if (P.cost) P.cost[(size_t)y * P.W + X] = (int16_t)minsad;
+                mind = 8 * gs + loc;
+            }
+            uint16_t* s16 = (uint16_t*)srow;
+            const int pv = s16[kpos(mind + 1 < nd ? mind + 1 : nd - 2)];
+            const int nv = s16[kpos(mind > 0 ? mind - 1 : 1)];
+            bool filtered = false;
+            if (P.uniq > 0) {
+                // group level: the keys of the winner's group and of both neighbours are taken out ...
+                const int g0 = max(gs - 1, 0), g2 = min(gs + 1, NGH - 1);
+                ((uint32_t*)krow)[g0] = 0xFFFFFFFFu;
+                ((uint32_t*)krow)[gs] = 0xFFFFFFFFu;
+                ((uint32_t*)krow)[g2] = 0xFFFFFFFFu;
+                // ... and those three groups are re-scanned exactly with mind-1, mind, mind+1 masked
+                s16[kpos(mind)] = 0xFFFFu;
+                if (mind > 0) s16[kpos(mind - 1)] = 0xFFFFu;
+                if (mind + 1 < nd) s16[kpos(mind + 1)] = 0xFFFFu;
+                uint32_t m2k = 0xFFFFFFFFu;
+                if (ND > 0) {
+#pragma unroll
+                    for (int i = 0; i < NK4; ++i) {
+                        const uint4 k4 = *(const uint4*)(krow + 16 * i);
+                        m2k = min(min(m2k, k4.x), min(k4.y, min(k4.z, k4.w)));
+                    }
+                } else {
+                    for (int i = 0; i < NK4; ++i) {
+                        const uint4 k4 = *(const uint4*)(krow + 16 * i);
+                        m2k = min(min(m2k, k4.x), min(k4.y, min(k4.z, k4.w)));
                     }
                 }
+                const uint4 e0 = *(const uint4*)(srow + 16 * g0);
+                const uint4 e1 = *(const uint4*)(srow + 16 * gs);
+                const uint4 e2 = *(const uint4*)(srow + 16 * g2);
+                uint32_t acc = __vimin3_u16x2(e0.x, e0.y, e0.z);
+                acc = __vimin3_u16x2(acc, e0.w, e1.x);
+                acc = __vimin3_u16x2(acc, e1.y, e1.z);
+                acc = __vimin3_u16x2(acc, e1.w, e2.x);
+                acc = __vimin3_u16x2(acc, e2.y, e2.z);
+                acc = __vminu2(acc, e2.w);
+                const uint32_t m2 = min(min(acc & 0xffffu, acc >> 16), m2k >> 16);
+                const int thr = minsad + (minsad * P.uniq / 100);
+                filtered = (int)m2 <= thr;
+            }
+            const int X = X0 + px;
+            if (X >= P.XA && X < P.XB) {
+                int tsum = 0;
+                for (int c = px; c < px + b; ++c) tsum += (int)sT[c];
+                int16_t out = FILTERED;
+                if (tsum >= P.texThr && !filtered) out = subpixel_disp(minsad, mind, pv, nv, nd, P.minD);
+                P.disp[(size_t)y * P.W + X] = out;
+                if (P.cost) P.cost[(size_t)y * P.W + X] = (int16_t)minsad;
             }
         }
         __syncthreads();
@@ -450,12 +466,12 @@ static int run_generic(const GenPlanes& pl, int W, int H, const BMConfig& cfg, c
     return launches;
 }
 
-template <int LPP>
+template <int ND>
 static cudaError_t launch_fast(const FastParams& P, dim3 grid, int nt, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(bm_fast_kernel<LPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(bm_fast_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    bm_fast_kernel<LPP><<<grid, nt, smem, st>>>(P);
+    bm_fast_kernel<ND><<<grid, nt, smem, st>>>(P);
     return cudaGetLastError();
 }
 
@@ -490,53 +506,57 @@ int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W
     if (force_generic) fast_ok = false;
     FastParams P;
     size_t smem = 0;
-    int nt = 0, LPP = 1;
+    int nt = 0;
     dim3 grid;
     if (fast_ok) {
-        const int NKG = cfg.nd / 16;
-        static const int nt_target = getenv("B200S_NT") ? atoi(getenv("B200S_NT")) : 320;
-        int NCQ = std::max(nt_target / NKG, (2 * g.r + 8 + 3) / 4);
-        NCQ = std::min(NCQ, 128);                 // at most 512 window columns per tile
-        int ncols = 4 * NCQ;
-        int TW = (ncols - 2 * g.r) & ~3;
-        nt = ((NCQ * NKG + 31) / 32) * 32;
+        const int NK = cfg.nd / 16, NGH = cfg.nd / 8;
+        static const int nt_target = getenv("B200S_NT") ? atoi(getenv("B200S_NT")) : 384;
+        int NCQ = std::max(nt_target / NK, (2 * g.r + 8 + 3) / 4);
+        NCQ = std::min(NCQ, (384 + 2 * g.r) / 4);  // one W thread per output column, at most 384 threads
+        int TW = (4 * NCQ - 2 * g.r) & ~3;
+        const int X0base = XA - ((XA - g.r - g.lofs) & 3);
+        // do not make the tile wider than the work (keeps shared memory small for narrow images)
+        int need = ((XB - X0base + 3) / 4) * 4;
+        if (TW > need) {
+            TW = need;
+            NCQ = (TW + 2 * g.r + 3) / 4;
+        }
+        nt = ((std::max(NCQ * NK, TW) + 31) / 32) * 32;
         if (TW < 4 || nt > 384) fast_ok = false;
         else {
-            const int X0base = XA - ((XA - g.r - g.lofs) & 3);
-            // do not make the tile wider than the work (keeps shared memory small for narrow images)
-            int need = ((XB - X0base + 3) / 4) * 4;
-            if (TW > need) {
-                TW = need;
-                NCQ = (TW + 2 * g.r + 3) / 4;
-                ncols = 4 * NCQ;
-                nt = ((NCQ * NKG + 31) / 32) * 32;
-            }
+            static const int swd_min = getenv("B200S_SWD") ? atoi(getenv("B200S_SWD")) : 12;
+            int NS = std::max(1, std::min(nt / NGH, (TW + swd_min - 1) / swd_min));
+            int SWD = (((TW + NS - 1) / NS) + 1) & ~1;          // even strip width (the H loop is unrolled by 2)
+            NS = (TW + SWD - 1) / SWD;
+            const int rowsS = NS * SWD;
+            const int ncols = 4 * NCQ;
+            const int rowsC = std::max(ncols, rowsS + 2 * g.r + 2);
             P.Lp = Lp; P.Rp = Rp; P.pitch = pitch; P.disp = disp; P.cost = cost;
             P.W = W; P.H = H; P.nd = cfg.nd; P.minD = cfg.minD; P.r = g.r; P.cap = cfg.cap;
             P.texThr = cfg.textureThreshold; P.uniq = cfg.uniquenessRatio; P.lofs = g.lofs;
             P.X0base = X0base; P.XA = XA; P.XB = XB; P.YA = g.roiY0; P.YB = g.roiY1;
-            P.TW = TW; P.ncols = ncols; P.NCQ = NCQ; P.NKG = NKG;
-            P.NGH = cfg.nd / 8;
-            static const int swd_min = getenv("B200S_SWD") ? atoi(getenv("B200S_SWD")) : 12;
-            P.NS = std::max(1, std::min(nt / P.NGH, (TW + swd_min - 1) / swd_min));
-            P.SWD = (TW + P.NS - 1) / P.NS;
-            P.CW = ((cfg.nd / 2 + 31) / 32) * 32;
+            P.TW = TW; P.ncols = ncols; P.NCQ = NCQ; P.NK = NK;
+            P.NGH = NGH; P.NS = NS; P.SWD = SWD;
+            P.CWb = cfg.nd * 2;
+            P.SWb = cfg.nd * 2 + 16;
+            P.NK4 = (NGH + 3) / 4;
+            P.KWb = (P.NK4 * 4 + 4) * 4;
             P.RLW = (ncols + cfg.nd) / 4 + 1;
             int units = (4 * P.RLW + 15) / 16;
-            while ((units & 7) != 2) ++units;
+            while ((units & 3) != 2) ++units;
             P.CSB = units * 16;
+            P.stage_from = (nt - TW >= 64) ? TW : 0;
             size_t o = 0;
             P.oLb = (int)o; o += 2 * (size_t)ncols * 4;
             o = (o + 15) & ~(size_t)15;
             P.oRc = (int)o; o += 2 * 4 * (size_t)P.CSB;
-            P.oC = (int)o; o += (size_t)ncols * P.CW * 4;
-            P.oS = (int)o; o += (size_t)TW * P.CW * 4;
             P.oT = (int)o; o += (size_t)ncols * 4;
+            o = (o + 15) & ~(size_t)15;
+            P.oK = (int)o; o += (size_t)rowsS * P.KWb;
+            P.oC = (int)o; o += (size_t)rowsC * P.CWb;
+            P.oS = (int)o; o += (size_t)rowsS * P.SWb;
             smem = o;
             if (smem > 200 * 1024) fast_ok = false;
-            static const int lpp_env = getenv("B200S_LPP") ? atoi(getenv("B200S_LPP")) : 0;
-            LPP = (cfg.nd % 64 == 0 && 4 * TW <= nt + nt / 2) ? 4 : ((cfg.nd % 32 == 0 && 2 * TW <= nt + nt / 2) ? 2 : 1);
-            if (lpp_env == 1 || (lpp_env == 2 && cfg.nd % 32 == 0) || (lpp_env == 4 && cfg.nd % 64 == 0)) LPP = lpp_env;
             // band height: about two blocks per SM in one wave; the column-sum bias (128 per row) bounds it
             int tilesX = (XB - X0base + TW - 1) / TW;
             int rows = g.roiY1 - g.roiY0;
@@ -551,9 +571,10 @@ int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W
     GenPlanes gp{Lp, Rp, pitch};
     if (fast_ok) {
         cudaError_t e;
-        if (LPP == 4) e = launch_fast<4>(P, grid, nt, smem, st);
-        else if (LPP == 2) e = launch_fast<2>(P, grid, nt, smem, st);
-        else e = launch_fast<1>(P, grid, nt, smem, st);
+        if (cfg.nd == 256) e = launch_fast<256>(P, grid, nt, smem, st);
+        else if (cfg.nd == 128) e = launch_fast<128>(P, grid, nt, smem, st);
+        else if (cfg.nd == 64) e = launch_fast<64>(P, grid, nt, smem, st);
+        else e = launch_fast<0>(P, grid, nt, smem, st);
         if (e != cudaSuccess) return -1;
         ++launches;
         // border bands that the fast kernel does not cover
