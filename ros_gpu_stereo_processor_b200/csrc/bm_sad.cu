@@ -10,6 +10,7 @@
 //
 // Internal disparity index k in [0, nd): d = nd-1-k+minD; right column of (X, k) is X - lofs + k.
 #include "kernels.h"
+#include "bm_common.cuh"
 
 #include <algorithm>
 #include <climits>
@@ -17,15 +18,8 @@
 
 namespace b200s {
 
-// ------------------------------------------------------------------------------------------------------
-// shared winner arithmetic (A.2.5)
-// ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int16_t subpixel_disp(int minsad, int mind, int p, int n, int nd, int minD)
-{
-    int d = p + n - 2 * minsad + abs(p - n);
-    int v = ((nd - mind - 1 + minD) * 256 + (d != 0 ? (p - n) * 256 / d : 0) + 15) >> 4;
-    return (int16_t)v;
-}
+int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg, int r, int lofs,
+                 int XA, int XB, int YA, int YB, int16_t* disp, int16_t* cost, cudaStream_t st);
 
 __global__ void fill_s16_kernel(int16_t* p, size_t n, int16_t v)
 {
@@ -66,9 +60,6 @@ struct FastParams {
     int stage_from;               // threads >= stage_from stage rows during phase W
     int oLb, oRc, oT, oK, oC, oS; // shared memory byte offsets
 };
-
-// position of disparity index k inside a group of four u16 lanes (V-phase lane order is k, k+2, k+1, k+3)
-__device__ __forceinline__ int kpos(int k) { return (k & ~3) | ((k & 1) << 1) | ((k >> 1) & 1); }
 
 __device__ __forceinline__ void stage_rows(const FastParams& P, uint8_t* smem, int t, int nt, int yi, bool has_old,
                                            int Xl0, int Xr0)
@@ -504,6 +495,7 @@ int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W
     bool fast_ok = g.rofs == 0 && (2 * cfg.cap * cfg.wsz * cfg.wsz < 65535) && XB > XA && (pitch % 16 == 0);
     static const int force_generic = getenv("B200S_FORCE_GENERIC") ? atoi(getenv("B200S_FORCE_GENERIC")) : 0;
     if (force_generic) fast_ok = false;
+    const bool fast_ok_base = fast_ok;
     FastParams P;
     size_t smem = 0;
     int nt = 0;
@@ -569,7 +561,22 @@ int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W
         }
     }
     GenPlanes gp{Lp, Rp, pitch};
-    if (fast_ok) {
+    static const int kernel_sel = getenv("B200S_KERNEL") ? atoi(getenv("B200S_KERNEL")) : 4;
+    bool ws_done = false;
+    if (fast_ok_base && kernel_sel >= 4) {
+        int rc = launch_bm_ws(Lp, Rp, pitch, W, H, cfg, g.r, g.lofs, XA, XB, g.roiY0, g.roiY1, disp, cost, st);
+        if (rc < 0) return -1;
+        ws_done = rc == 1;
+    }
+    if (ws_done) {
+        ++launches;
+        int l = run_generic(gp, W, H, cfg, g, outX0 - g.lofs, XA - g.lofs, disp, cost, sc, st);
+        if (l < 0) return l;
+        launches += l;
+        l = run_generic(gp, W, H, cfg, g, XB - g.lofs, outX1 - g.lofs, disp, cost, sc, st);
+        if (l < 0) return l;
+        launches += l;
+    } else if (fast_ok) {
         cudaError_t e;
         if (cfg.nd == 256) e = launch_fast<256>(P, grid, nt, smem, st);
         else if (cfg.nd == 128) e = launch_fast<128>(P, grid, nt, smem, st);
