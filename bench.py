@@ -12,7 +12,7 @@ FRAMES_PER_STEP distinct synthetic frames (per GPU).
   value  frames/s with the raw frames and every output resident in HBM (CUDA events on the slot streams)
   e2e    frames/s through the C ABI with pinned HOST buffers: H2D of the raw pair and D2H of the rectified pair,
          the float disparity and the PointCloud2 payload inside the timed region
-  roofline  dominant kernel (bm_fast_kernel): scalar-equivalent integer ops (7 per disparity evaluation,
+  roofline  dominant kernel (bm_ws_kernel): scalar-equivalent integer ops (7 per disparity evaluation,
          SURVEY.md 8(d)) over the CUDA-event duration of the matcher, against the INT peak measured on this GPU
          by the library's IADD3 micro-benchmark; the HBM view of the same launch is reported beside it
   cpu_baseline  the reference's CPU path (cv::remap x2, cv::StereoBM, convertTo, reprojectImageTo3D, PointCloud2
@@ -306,7 +306,7 @@ def run_ours(args, c, name, rank, world, local_rank):
             hbm_peak, hbm_src = float(json.load(open(peaks_file))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
         achieved = eff * 7 / t_bm / 1e12
         alg_bytes = 2 * n + 2 * n     # two prefiltered u8 planes in, one s16 disparity plane out
-        roof = dict(bound="int-alu", kernel="bm_fast_kernel<64>", achieved=achieved, peak=peak_tops, unit="Tops/s (scalar-equivalent int32 lane-ops, 7 per disparity evaluation)",
+        roof = dict(bound="int-alu", kernel="bm_ws_kernel<%d> (warp-specialised SAD matcher)" % nd, achieved=achieved, peak=peak_tops, unit="Tops/s (scalar-equivalent int32 lane-ops, 7 per disparity evaluation)",
                     frac=achieved / peak_tops, peak_source="measured: b200s_int_peak IADD3 dependent chains, all SMs, this run",
                     kernel_ms=t_bm * 1e3, evals_effective_per_launch=eff, gevals_per_s=eff / t_bm / 1e9, traffic=None,
                     hbm=dict(achieved=alg_bytes / t_bm / 1e9, peak=hbm_peak, unit="GB/s", frac=alg_bytes / t_bm / 1e9 / hbm_peak,
