@@ -111,6 +111,28 @@ class ClockSampler(object):
                     power_w_max=max(pw) if pw else None, samples=len(sm), reasons=sorted(reasons))
 
 
+def bind_to_gpu_numa(gpu_index):
+    """Pins this process to the CPUs of the GPU's NUMA node (before any pinned allocation) so that the pinned host
+    buffers of the end-to-end leg sit next to the GPU's PCIe root; returns a short description."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bus.startswith("0000"):
+            bus = bus[4:]
+        path = "/sys/bus/pci/devices/%s/" % bus
+        node = open(path + "numa_node").read().strip()
+        cpus = []
+        for part in open(path + "local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return "numa node %s, %d cpus" % (node, len(allowed))
+    except Exception as e:   # best effort only
+        return "not bound (%s)" % type(e).__name__
+
+
 def cpu_chain(frames, cal, c, reps_budget_s, threads):
     """The reference's CPU path with the real OpenCV: returns (frames/s, n_frames_timed)."""
     import cv2
@@ -188,6 +210,8 @@ def run_ours(args, c, name, rank, world, local_rank):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank
+    all_cpus = sorted(os.sched_getaffinity(0))
+    numa = bind_to_gpu_numa(dev)
     W, H, nd = c["W"], c["H"], c["nd"]
     n = W * H
     frames, cal = make_frames(c, FRAMES_PER_STEP, 1000 * c["idx"] + rank * FRAMES_PER_STEP)
@@ -313,7 +337,8 @@ def run_ours(args, c, name, rank, world, local_rank):
                              algorithmic_bytes=alg_bytes, peak_source=hbm_src),
                     int_peaks_tops=int_peaks, share_of_step=t_bm * FRAMES_PER_STEP / (ms_dev * 1e-3 / args.steps))
         if world == 1 and not args.no_cpu:
-            threads = os.cpu_count() or 1
+            os.sched_setaffinity(0, all_cpus)     # the CPU baseline gets every host core again
+            threads = len(all_cpus)
             import cv2
             fps_cpu, ncpu = cpu_chain(frames, cal, c, reps_budget_s=args.cpu_seconds, threads=threads)
             cpu_base = dict(value=fps_cpu, unit="frames/s", cores=threads, kind="reference",
@@ -333,7 +358,7 @@ def run_ours(args, c, name, rank, world, local_rank):
                                    % (FRAMES_PER_STEP, (2 * n * FRAMES_PER_STEP + N_SLOTS * n * 46) / 1e6, 2 * n * FRAMES_PER_STEP / 1e6, N_SLOTS)),
                     e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps,
                              mdisp_evals_per_s=fps_e2e * nominal / 1e6),
-                    gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu_base)
+                    gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu_base, host_binding=numa)
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -18,17 +18,43 @@ __device__ __forceinline__ float disp_to_float(int d16, double cxd)
 
 __global__ void __launch_bounds__(256) set_int_kernel(int* p, int v) { *p = v; }
 
+// 8 disparities per thread (one 16-byte load), block-level min, one atomic per block
 __global__ void __launch_bounds__(256) disparity_to_float_kernel(const int16_t* __restrict__ d16, float* __restrict__ df,
                                                                  int n, double cxd, int* __restrict__ min_d16)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int wmin[8];
+    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
     int v = INT_MAX;
-    if (i < n) {
-        v = d16[i];
-        if (df) df[i] = disp_to_float(v, cxd);
+    if (i0 + 8 <= n) {
+        const uint4 q = *(const uint4*)(d16 + i0);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int a = (int)(int16_t)(w[k] & 0xffffu), b = (int)(int16_t)(w[k] >> 16);
+            v = min(v, min(a, b));
+            f[2 * k] = disp_to_float(a, cxd);
+            f[2 * k + 1] = disp_to_float(b, cxd);
+        }
+        if (df) {
+            *(float4*)(df + i0) = make_float4(f[0], f[1], f[2], f[3]);
+            *(float4*)(df + i0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+        }
+    } else {
+        for (int i = i0; i < n; ++i) {
+            const int a = d16[i];
+            v = min(v, a);
+            if (df) df[i] = disp_to_float(a, cxd);
+        }
     }
     v = __reduce_min_sync(0xffffffffu, v);
-    if ((threadIdx.x & 31) == 0 && v != INT_MAX) atomicMin(min_d16, v);
+    if ((threadIdx.x & 31) == 0) wmin[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        v = wmin[threadIdx.x];
+        v = __reduce_min_sync(0xffu, v);
+        if (threadIdx.x == 0 && v != INT_MAX) atomicMin(min_d16, v);
+    }
 }
 
 __global__ void __launch_bounds__(256) reproject_pack_kernel(const int16_t* __restrict__ d16, int W, int H, double cxd,
@@ -103,9 +129,9 @@ __global__ void __launch_bounds__(256) disparity_color_kernel(const int16_t* __r
 
 int launch_disparity_to_float(const int16_t* d16, float* df, int n, double cxd, int* min_d16, cudaStream_t st)
 {
-    set_int_kernel<<<1, 1, 0, st>>>(min_d16, INT_MAX);
-    disparity_to_float_kernel<<<(n + 255) / 256, 256, 0, st>>>(d16, df, n, cxd, min_d16);
-    return 2;
+    cudaMemsetAsync(min_d16, 0x7f, sizeof(int), st);     // 0x7f7f7f7f: larger than any int16
+    disparity_to_float_kernel<<<(n + 2047) / 2048, 256, 0, st>>>(d16, df, n, cxd, min_d16);
+    return 1;
 }
 
 int launch_reproject_pack(const int16_t* d16, int W, int H, double cxd, const double* Q, const int* min_d16,

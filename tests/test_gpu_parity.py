@@ -315,3 +315,43 @@ def test_errors():
     Ls, Rs = synth.synth_pair(40, 30, 16, seed=2)
     assert np.array_equal(proc.computeDisparityBare(Ls, Rs), O.stereobm_compute(Ls, Rs, p))
     proc.close()
+
+
+# ---- C++ host facade (include/b200_gpuimageproc/GpuStereoProcessor.hpp) ---------------------------------------
+def test_cpp_facade_chain(tmp_path):
+    """Compiles tests/cpp/facade_test.cpp against the C ABI and runs the reference's gtest flow
+    (RectifyMonoGpu / DisparityGpu / PointCloud, test/UTest.cpp:262-398) through the C++ class."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "ros_gpu_stereo_processor_b200")
+    exe = str(tmp_path / "facade_test")
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "facade_test.cpp"),
+                           "-o", exe, "-L" + pkg, "-lb200stereo", "-Wl,-rpath," + pkg])
+    W, H, nd, b = 640, 360, 64, 9
+    Lraw, Rraw, cal = synth.synth_raw_pair(W, H, nd, seed=77)
+    for side in ("left", "right"):
+        c = cal[side]
+        with open(tmp_path / (side + ".yaml"), "w") as f:   # camera_calibration_parsers layout (test_data/left.yaml)
+            f.write("image_width: %d\nimage_height: %d\ncamera_name: narrow_stereo/%s\n" % (W, H, side))
+            for name, key, rows, cols in (("camera_matrix", "K", 3, 3), ("distortion_coefficients", "D", 1, 5),
+                                          ("rectification_matrix", "R", 3, 3), ("projection_matrix", "P", 3, 4)):
+                if name == "distortion_coefficients":
+                    f.write("distortion_model: plumb_bob\n")
+                f.write("%s:\n  rows: %d\n  cols: %d\n  data: [%s]\n" % (name, rows, cols, ", ".join(repr(float(v)) for v in c[key])))
+    (tmp_path / "in.bin").write_bytes(Lraw.tobytes() + Rraw.tobytes())
+    out = subprocess.run([exe, str(tmp_path / "left.yaml"), str(tmp_path / "right.yaml"), str(tmp_path / "in.bin"),
+                          str(tmp_path / "out.bin"), str(W), str(H), str(nd), str(b)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr + out.stdout
+    raw = np.fromfile(tmp_path / "out.bin", np.uint8)
+    n = W * H
+    rl, rr = raw[:n].reshape(H, W), raw[n:2 * n].reshape(H, W)
+    d = raw[2 * n:4 * n].view(np.int16).reshape(H, W)
+    pc = raw[4 * n:].reshape(H, W, 32)
+    wl, wr = O.rectify(Lraw, **cal["left"]), O.rectify(Rraw, **cal["right"])
+    assert np.array_equal(rl, wl) and np.array_equal(rr, wr)
+    p = O.BMParams(numDisparities=nd, blockSize=b)
+    wd = O.stereobm_compute(wl, wr, p)
+    assert np.array_equal(d, wd), _describe(d, wd)
+    df = O.disparity_to_float(wd, cal["left"]["P"][2] - cal["right"]["P"][2])
+    assert np.array_equal(pc, O.pack_pointcloud2(O.reproject(df, O.stereo_Q(cal["left"]["P"], cal["right"]["P"])), wl))
