@@ -334,10 +334,16 @@ int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
     const size_t smem_max = 227 * 1024 - 1024;
     const int X0base = XA - ((XA - r - lofs) & 3);
     const int need = ((XB - X0base + 3) / 4) * 4;
-    WsParams P;
+    WsParams P, best;
     size_t smem = 0;
     int nt = 0;
     bool ok = false;
+    double best_cost = 1e300;
+    int best_bands = 1;
+    const int rows = YB - YA;
+    static const int n_sm = getenv("B200S_WS_BLOCKS") ? atoi(getenv("B200S_WS_BLOCKS")) : 148;
+    // Enumerate tile widths; cost model: waves x (band rows + warm-up rows) x window columns (the V role dominates).
+    // Small images prefer narrow tiles and short bands so that the grid still covers the SMs.
     for (int NCQ = std::min(128, (need + 2 * r + 3) / 4); 4 * NCQ - 2 * r >= 8; --NCQ) {
         int TW = std::min((4 * NCQ - 2 * r) & ~3, need);
         int nVw = (NCQ * NK + 31) / 32, nWw = (TW + 31) / 32;
@@ -354,32 +360,37 @@ int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
         while ((units & 3) != 2) ++units;
         P.CSB = units * 16;
         size_t o = 0;
-        for (int s = 0; s < 2; ++s) { P.oStage[s] = (int)o; o += 2 * (size_t)ncols * 4 + 8 * (size_t)P.CSB; o = (o + 15) & ~(size_t)15; }
+        for (int s2 = 0; s2 < 2; ++s2) { P.oStage[s2] = (int)o; o += 2 * (size_t)ncols * 4 + 8 * (size_t)P.CSB; o = (o + 15) & ~(size_t)15; }
         P.oTc = (int)o; o += 8 * (size_t)ncols * 4; o = (o + 15) & ~(size_t)15;
-        for (int s = 0; s < 2; ++s) { P.oK[s] = (int)o; o += (size_t)rowsS * P.KWb; }
-        for (int s = 0; s < 2; ++s) { P.oC[s] = (int)o; o += (size_t)rowsC * P.CWb; }
-        for (int s = 0; s < 2; ++s) { P.oS[s] = (int)o; o += (size_t)rowsS * P.SWb; }
+        for (int s2 = 0; s2 < 2; ++s2) { P.oK[s2] = (int)o; o += (size_t)rowsS * P.KWb; }
+        for (int s2 = 0; s2 < 2; ++s2) { P.oC[s2] = (int)o; o += (size_t)rowsC * P.CWb; }
+        for (int s2 = 0; s2 < 2; ++s2) { P.oS[s2] = (int)o; o += (size_t)rowsS * P.SWb; }
         if (o > smem_max) continue;
-        smem = o;
         P.TW = TW; P.ncols = ncols; P.NCQ = NCQ; P.NK = NK; P.NGH = NGH; P.NS = NS; P.SWD = SWD;
         P.nVw = nVw; P.nHw = nHw; P.nWw = nWw; P.rowsS = rowsS; P.rowsC = rowsC;
-        nt = 32 * (nVw + nHw + nWw + 2);
-        ok = true;
-        break;
+        const int tilesX = (XB - X0base + TW - 1) / TW;
+        const int max_bands = std::max(1, rows / (2 * r + 4));
+        for (int bands = 1; bands <= max_bands; ++bands) {
+            int BH = (rows + bands - 1) / bands;
+            if (BH > 480 - 2 * r) continue;                      // the per-row bias of the column sums bounds the band
+            int nb = tilesX * ((rows + BH - 1) / BH);
+            int waves = (nb + n_sm - 1) / n_sm;
+            double cost = (double)waves * (BH + 2 * r + 6) * (ncols + 16);   // +6 rows: pipeline fill/drain
+            if (cost < best_cost) {
+                best_cost = cost; best = P; best_bands = bands; smem = o;
+                nt = 32 * (nVw + nHw + nWw + 2);
+                ok = true;
+            }
+        }
     }
     if (!ok || nt > 768) return 0;
+    P = best;
     P.Lp = Lp; P.Rp = Rp; P.pitch = pitch; P.disp = disp; P.cost = cost;
     P.W = W; P.H = H; P.nd = nd; P.minD = cfg.minD; P.r = r; P.cap = cfg.cap;
     P.texThr = cfg.textureThreshold; P.uniq = cfg.uniquenessRatio; P.lofs = lofs;
     P.X0base = X0base; P.XA = XA; P.XB = XB; P.YA = YA; P.YB = YB;
-    // one block per SM: bands sized so that the grid is about one wave (148 SMs), the bias bounds the band height
     const int tilesX = (XB - X0base + P.TW - 1) / P.TW;
-    const int rows = YB - YA;
-    static const int want_blocks = getenv("B200S_WS_BLOCKS") ? atoi(getenv("B200S_WS_BLOCKS")) : 148;
-    int bands = std::max(1, std::min((want_blocks + tilesX / 2) / tilesX, std::max(1, rows / (4 * r + 8))));
-    P.BH = (rows + bands - 1) / bands;
-    const int bh_max = 480 - 2 * r;
-    if (P.BH > bh_max) P.BH = bh_max;
+    P.BH = (rows + best_bands - 1) / best_bands;
     dim3 grid(tilesX, (rows + P.BH - 1) / P.BH);
     cudaError_t e;
     if (nd == 256) e = launch_ws<256>(P, grid, nt, smem, st);
