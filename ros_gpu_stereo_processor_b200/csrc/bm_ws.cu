@@ -27,7 +27,8 @@ struct WsParams {
     int X0base, XA, XB, YA, YB;
     int TW, BH, ncols, NCQ, NK, NGH, NS, SWD;
     int CWb, SWb, KWb, NK4, CSB, RLW;
-    int nVw, nHw, nWw;     // warps per role; two stager warps follow
+    int nVw, nHw, nWw;     // warps per role; nSw (1 or 2) stager warps follow
+    int nSw;
     int rowsS, rowsC;
     int oStage[2];         // per buffer: Lb [2][ncols] words, then Rc [2][4][CSB] bytes
     int oTc;               // [8][ncols] words: texture column sums, ring indexed by output row & 7
@@ -37,14 +38,21 @@ struct WsParams {
 enum { B_FULL_STAGE = 1, B_EMPTY_STAGE = 3, B_FULL_C = 5, B_EMPTY_C = 7, B_FULL_S = 9, B_EMPTY_S = 11 };
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// producer side: publish the shared-memory writes, then arrive
 __device__ __forceinline__ void bar_arrive(int id, int n)
 {
-    __threadfence_block();
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
+// consumer side: the buffer was only read (and the loaded values already consumed), nothing to publish
+__device__ __forceinline__ void bar_release(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <int ND>
-__global__ void __launch_bounds__(768, 1) bm_ws_kernel(const WsParams P)
+// register budget: ptxas rounds the block up to a multiple of 128 threads, so 640 threads -> 96 registers (the ring
+// variant of the H role needs them), 768 threads -> 80 registers
+template <int RB> struct WsBounds { static constexpr int threads = RB > 0 ? 640 : 768; };
+
+template <int ND, int RB>
+__global__ void __launch_bounds__(WsBounds<RB>::threads, 1) bm_ws_kernel(const WsParams P)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int nd = ND > 0 ? ND : P.nd;
@@ -57,7 +65,7 @@ __global__ void __launch_bounds__(768, 1) bm_ws_kernel(const WsParams P)
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
-    const int NVt = P.nVw * 32, NHt = P.nHw * 32, NWt = P.nWw * 32;
+    const int NVt = P.nVw * 32, NHt = P.nHw * 32, NWt = P.nWw * 32, NSt = P.nSw * 32;
     const int X0 = P.X0base + blockIdx.x * P.TW;
     const int yb0 = P.YA + blockIdx.y * P.BH;
     const int yb1 = min(yb0 + P.BH, P.YB);
@@ -84,7 +92,6 @@ __global__ void __launch_bounds__(768, 1) bm_ws_kernel(const WsParams P)
             for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int w = 0; w < 4; ++w) C[i][h][w] = 0;
-        int tcol[4] = {0, 0, 0, 0};
         int voff[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -95,8 +102,7 @@ __global__ void __launch_bounds__(768, 1) bm_ws_kernel(const WsParams P)
         const int cstore = (4 * cq) * CWb + 16 * kg;
         for (int j = 0; j < nIn; ++j) {
             const int sb = j & 1;
-            const bool has_old = j >= b;
-            bar_sync(B_FULL_STAGE + sb, NVt + 32);
+            bar_sync(B_FULL_STAGE + sb, NVt + NSt);
             if (vact) {
                 const uint8_t* st = smem + P.oStage[sb];
                 const uint4 ln4 = *(const uint4*)(st + 16 * cq);
@@ -123,13 +129,8 @@ __global__ void __launch_bounds__(768, 1) bm_ws_kernel(const WsParams P)
                         }
                     }
                 }
-                if (kg == 0) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        tcol[i] += abs((int)(ln[i] & 0xffu) - P.cap) - (has_old ? abs((int)(lo[i] & 0xffu) - P.cap) : 0);
-                }
             }
-            bar_arrive(B_EMPTY_STAGE + sb, NVt + 32);   // after the loaded values were consumed
+            bar_release(B_EMPTY_STAGE + sb, NVt + NSt);   // after the loaded values were consumed
             if (j >= 2 * r) {
                 const int o = j - 2 * r, cb = o & 1;
                 if (o >= 2) bar_sync(B_EMPTY_C + cb, NVt + NHt);
@@ -140,10 +141,6 @@ __global__ void __launch_bounds__(768, 1) bm_ws_kernel(const WsParams P)
 #pragma unroll
                         for (int h = 0; h < 2; ++h)
                             *(uint4*)(dst + i * CWb + h * (16 * NK)) = make_uint4(C[i][h][0], C[i][h][1], C[i][h][2], C[i][h][3]);
-                    if (kg == 0) {
-                        int* tc = (int*)(smem + P.oTc) + (o & 7) * P.ncols + 4 * cq;
-                        *(int4*)tc = make_int4(tcol[0], tcol[1], tcol[2], tcol[3]);
-                    }
                 }
                 bar_arrive(B_FULL_C + cb, NVt + NHt);
             }
@@ -163,27 +160,56 @@ __global__ void __launch_bounds__(768, 1) bm_ws_kernel(const WsParams P)
                 // every column sum carries a bias of 128 per accumulated row and lane; remove b columns' worth
                 const uint32_t bias = (uint32_t)(128 * (o + 2 * r + 1) * b) * 0x00010001u;
                 uint4 S = make_uint4(0u - bias, 0u - bias, 0u - bias, 0u - bias);
-                for (int c = 0; c < b; ++c) {
-                    const uint4 v = *(const uint4*)(pc + c * CWb);
-                    S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
-                }
-                const uint8_t* pa = pc + b * CWb;
                 uint8_t* ps = smem + P.oS[cb] + xs * SWb + 16 * gh;
                 uint8_t* pk = smem + P.oK[cb] + xs * KWb + 4 * gh;
-#pragma unroll 2
-                for (int x = 0; x < P.SWD; ++x) {
-                    *(uint4*)ps = S;
-                    uint32_t m = __vimin3_u16x2(S.x, S.y, S.z);
-                    m = __vminu2(m, S.w);
-                    m = __vminu2(m, m >> 16);
-                    *(uint32_t*)pk = (m << 16) | (uint32_t)gh;
-                    const uint4 a = *(const uint4*)pa;
-                    const uint4 ov = *(const uint4*)pc;
-                    S.x += a.x - ov.x; S.y += a.y - ov.y; S.z += a.z - ov.z; S.w += a.w - ov.w;
-                    pa += CWb; pc += CWb; ps += SWb; pk += KWb;
+#define B200S_H_EMIT(OFFS, OFFK)                                                     \
+    {                                                                                \
+        *(uint4*)(ps + (OFFS)) = S;                                                  \
+        uint32_t m_ = __vimin3_u16x2(S.x, S.y, S.z);                                 \
+        m_ = __vminu2(m_, S.w);                                                      \
+        m_ = __vminu2(m_, m_ >> 16);                                                 \
+        *(uint32_t*)(pk + (OFFK)) = (m_ << 16) | (uint32_t)gh;                       \
+    }
+                if (RB > 0) {
+                    // the leaving column comes from a register ring (window width RB = 2r+1 is compile time):
+                    // one LDS.128 per column instead of two; strips are whole multiples of RB
+                    uint4 ring[RB > 0 ? RB : 1];
+#pragma unroll
+                    for (int c = 0; c < RB; ++c) {
+                        ring[c] = *(const uint4*)(pc + c * CWb);
+                        S.x += ring[c].x; S.y += ring[c].y; S.z += ring[c].z; S.w += ring[c].w;
+                    }
+                    const uint8_t* pa = pc + RB * CWb;
+                    for (int x0 = 0; x0 < P.SWD; x0 += RB) {
+#pragma unroll
+                        for (int i = 0; i < RB; ++i) {
+                            B200S_H_EMIT(i * SWb, i * KWb)
+                            const uint4 a = *(const uint4*)(pa + i * CWb);
+                            S.x += a.x - ring[i].x; S.y += a.y - ring[i].y; S.z += a.z - ring[i].z; S.w += a.w - ring[i].w;
+                            ring[i] = a;
+                        }
+                        pa += RB * CWb; ps += RB * SWb; pk += RB * KWb;
+                    }
+                } else {
+                    for (int c = 0; c < b; ++c) {
+                        const uint4 v = *(const uint4*)(pc + c * CWb);
+                        S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
+                    }
+                    const uint8_t* pa = pc + b * CWb;
+                    for (int x0 = 0; x0 < P.SWD; x0 += 4) {     // SWD is a multiple of 4
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            B200S_H_EMIT(i * SWb, i * KWb)
+                            const uint4 a = *(const uint4*)(pa + i * CWb);
+                            const uint4 ov = *(const uint4*)(pc + i * CWb);
+                            S.x += a.x - ov.x; S.y += a.y - ov.y; S.z += a.z - ov.z; S.w += a.w - ov.w;
+                        }
+                        pa += 4 * CWb; pc += 4 * CWb; ps += 4 * SWb; pk += 4 * KWb;
+                    }
                 }
+#undef B200S_H_EMIT
             }
-            bar_arrive(B_EMPTY_C + cb, NVt + NHt);
+            bar_release(B_EMPTY_C + cb, NVt + NHt);
             bar_arrive(B_FULL_S + cb, NHt + NWt);
         }
     } else if (warp < P.nVw + P.nHw + P.nWw) {
@@ -275,53 +301,77 @@ __global__ void __launch_bounds__(768, 1) bm_ws_kernel(const WsParams P)
                     if (P.cost) P.cost[(size_t)y * P.W + X] = (int16_t)minsad;
                 }
             }
-            bar_arrive(B_EMPTY_S + cb, NHt + NWt);
+            bar_release(B_EMPTY_S + cb, NHt + NWt);
         }
     } else {
-        // =============================== stager role: warp s stages the input rows j = s, s + 2, ... ============
+        // =============================== stager role ===========================================================
+        // stager 0: left rows (pre-broadcast) + running texture column sums; stager 1: right rows (4 shifted copies)
         const int s = warp - (P.nVw + P.nHw + P.nWw);
         const int lane = tid & 31;
         const int Xl0 = X0 - r;
         const int Xr0 = X0 - r - P.lofs;     // multiple of 4 by construction
-        uint32_t* sLb = (uint32_t*)(smem + P.oStage[s]);
-        uint8_t* sRc = smem + P.oStage[s] + 2 * P.ncols * 4;
-        for (int j = s; j < nIn; j += 2) {
+        int* trun = (int*)(smem + P.oTc) + 8 * P.ncols;    // [ncols] running sums, owned lane-wise by stager 0
+        if (s == 0)
+            for (int c = lane; c < P.ncols; c += 32) trun[c] = 0;
+        for (int j = 0; j < nIn; ++j) {
+            const int sb = j & 1;
             const int yi = y_in0 + j;
             const bool has_old = j >= b;
-            const uint8_t* ln = P.Lp + (size_t)yi * P.pitch + Xl0;
-            const uint8_t* lo = P.Lp + (size_t)max(yi - b, 0) * P.pitch + Xl0;
-            const uint32_t* rn = (const uint32_t*)(P.Rp + (size_t)yi * P.pitch + Xr0);
-            const uint32_t* ro = (const uint32_t*)(P.Rp + (size_t)max(yi - b, 0) * P.pitch + Xr0);
-            if (j >= 2) bar_sync(B_EMPTY_STAGE + s, NVt + 32);
-            for (int c = lane; c < P.ncols; c += 32) {
-                const uint32_t a = __ldg(ln + c), o2 = has_old ? __ldg(lo + c) : 0u;
-                sLb[c] = a * 0x01010101u;
-                sLb[P.ncols + c] = o2 * 0x01010101u;
+            if (j >= 2) bar_sync(B_EMPTY_STAGE + sb, NVt + NSt);
+            if (s == 0) {   // with a single stager warp it does both halves
+                const uint8_t* ln = P.Lp + (size_t)yi * P.pitch + Xl0;
+                const uint8_t* lo = P.Lp + (size_t)max(yi - b, 0) * P.pitch + Xl0;
+                uint32_t* sLb = (uint32_t*)(smem + P.oStage[sb]);
+                const bool publish = j >= 2 * r;
+                int* tpub = (int*)(smem + P.oTc) + ((j - 2 * r) & 7) * P.ncols;
+                for (int c = lane; c < P.ncols; c += 32) {
+                    const int a = (int)__ldg(ln + c), o2 = has_old ? (int)__ldg(lo + c) : 0;
+                    sLb[c] = (uint32_t)a * 0x01010101u;
+                    sLb[P.ncols + c] = (uint32_t)o2 * 0x01010101u;
+                    const int t = trun[c] + abs(a - P.cap) - (has_old ? abs(o2 - P.cap) : 0);
+                    trun[c] = t;
+                    if (publish) tpub[c] = t;     // texture column sums of output row j - 2r (ring of 8 rows)
+                }
             }
-            for (int wi = lane; wi < P.RLW; wi += 32) {
-                const uint32_t vn = __ldg(rn + wi), vo = has_old ? __ldg(ro + wi) : 0u;
-                uint8_t* cp = sRc + 4 * wi;
-                // copy jj holds row[a + 4 jj] at byte a
+            if (s == P.nSw - 1) {
+                const uint32_t* rn = (const uint32_t*)(P.Rp + (size_t)yi * P.pitch + Xr0);
+                const uint32_t* ro = (const uint32_t*)(P.Rp + (size_t)max(yi - b, 0) * P.pitch + Xr0);
+                uint8_t* sRc = smem + P.oStage[sb] + 2 * P.ncols * 4;
+                for (int wi = lane; wi < P.RLW; wi += 32) {
+                    const uint32_t vn = __ldg(rn + wi), vo = has_old ? __ldg(ro + wi) : 0u;
+                    uint8_t* cp = sRc + 4 * wi;
+                    // copy jj holds row[a + 4 jj] at byte a
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-                    if (wi >= jj) {
-                        *(uint32_t*)(cp + jj * P.CSB - 4 * jj) = vn;
-                        *(uint32_t*)(cp + (4 + jj) * P.CSB - 4 * jj) = vo;
-                    }
+                    for (int jj = 0; jj < 4; ++jj)
+                        if (wi >= jj) {
+                            *(uint32_t*)(cp + jj * P.CSB - 4 * jj) = vn;
+                            *(uint32_t*)(cp + (4 + jj) * P.CSB - 4 * jj) = vo;
+                        }
+                }
             }
-            bar_arrive(B_FULL_STAGE + s, NVt + 32);
+            bar_arrive(B_FULL_STAGE + sb, NVt + NSt);
         }
     }
 }
 
-template <int ND>
-static cudaError_t launch_ws(const WsParams& P, dim3 grid, int nt, size_t smem, cudaStream_t st)
+template <int ND, int RB>
+static cudaError_t launch_ws2(const WsParams& P, dim3 grid, int nt, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(bm_ws_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(bm_ws_kernel<ND, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    bm_ws_kernel<ND><<<grid, nt, smem, st>>>(P);
+    bm_ws_kernel<ND, RB><<<grid, nt, smem, st>>>(P);
     return cudaGetLastError();
 }
+
+template <int ND>
+static cudaError_t launch_ws(const WsParams& P, int rb, dim3 grid, int nt, size_t smem, cudaStream_t st)
+{
+    if (rb == 11) return launch_ws2<ND, 11>(P, grid, nt, smem, st);
+    if (rb == 9) return launch_ws2<ND, 9>(P, grid, nt, smem, st);
+    return launch_ws2<ND, 0>(P, grid, nt, smem, st);
+}
+
+static inline bool ring_width_supported(int b) { return b == 9 || b == 11; }
 
 // returns 1 when launched, 0 when this configuration is not handled (caller falls back), < 0 on CUDA errors
 int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg, int r, int lofs,
@@ -331,6 +381,11 @@ int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
     const int NK = nd / 16, NGH = nd / 8;
     static const int max_warps = getenv("B200S_WS_WARPS") ? atoi(getenv("B200S_WS_WARPS")) : 24;
     static const int swd_min = getenv("B200S_SWD") ? atoi(getenv("B200S_SWD")) : 12;
+    static const int ring_mult = getenv("B200S_RING_MULT") ? atoi(getenv("B200S_RING_MULT")) : 2;
+    // the register-ring variant of the H role (one LDS.128 per column) measured slower on B200 (fewer, longer strips:
+    // 323 us vs 274 us on C4) and is off unless B200S_RING=1
+    static const int ring_on = getenv("B200S_RING") ? atoi(getenv("B200S_RING")) : 0;
+    const int rb = (ring_on && ring_width_supported(2 * r + 1)) ? 2 * r + 1 : 0;
     const size_t smem_max = 227 * 1024 - 1024;
     const int X0base = XA - ((XA - r - lofs) & 3);
     const int need = ((XB - X0base + 3) / 4) * 4;
@@ -347,11 +402,19 @@ int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
     for (int NCQ = std::min(128, (need + 2 * r + 3) / 4); 4 * NCQ - 2 * r >= 8; --NCQ) {
         int TW = std::min((4 * NCQ - 2 * r) & ~3, need);
         int nVw = (NCQ * NK + 31) / 32, nWw = (TW + 31) / 32;
-        int NS = std::max(1, (TW + swd_min - 1) / swd_min);
-        int SWD = (((TW + NS - 1) / NS) + 1) & ~1;
-        NS = (TW + SWD - 1) / SWD;
+        int NS, SWD;
+        if (rb) {                               // strips are whole multiples of the window width (register ring)
+            SWD = rb * ring_mult;
+            NS = (TW + SWD - 1) / SWD;
+        } else {
+            NS = std::max(1, (TW + swd_min - 1) / swd_min);
+            SWD = (((TW + NS - 1) / NS) + 3) & ~3;  // multiple of 4 (the H loop is unrolled by 4)
+            NS = (TW + SWD - 1) / SWD;
+        }
         int nHw = (NS * NGH + 31) / 32;
-        if (nVw + nHw + nWw + 2 > max_warps) continue;
+        const int warp_cap = rb ? std::min(max_warps, 20) : max_warps;   // ring variant: 640 threads, 96 registers
+        int nSw = (nVw + nHw + nWw + 2 <= warp_cap) ? 2 : 1;
+        if (nVw + nHw + nWw + nSw > warp_cap) continue;
         const int ncols = 4 * NCQ;
         const int rowsS = NS * SWD, rowsC = std::max(ncols, rowsS + 2 * r + 2);
         P.CWb = nd * 2; P.SWb = nd * 2 + 16; P.NK4 = (NGH + 3) / 4; P.KWb = (P.NK4 * 4 + 4) * 4;
@@ -361,13 +424,13 @@ int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
         P.CSB = units * 16;
         size_t o = 0;
         for (int s2 = 0; s2 < 2; ++s2) { P.oStage[s2] = (int)o; o += 2 * (size_t)ncols * 4 + 8 * (size_t)P.CSB; o = (o + 15) & ~(size_t)15; }
-        P.oTc = (int)o; o += 8 * (size_t)ncols * 4; o = (o + 15) & ~(size_t)15;
+        P.oTc = (int)o; o += 9 * (size_t)ncols * 4; o = (o + 15) & ~(size_t)15;
         for (int s2 = 0; s2 < 2; ++s2) { P.oK[s2] = (int)o; o += (size_t)rowsS * P.KWb; }
         for (int s2 = 0; s2 < 2; ++s2) { P.oC[s2] = (int)o; o += (size_t)rowsC * P.CWb; }
         for (int s2 = 0; s2 < 2; ++s2) { P.oS[s2] = (int)o; o += (size_t)rowsS * P.SWb; }
         if (o > smem_max) continue;
         P.TW = TW; P.ncols = ncols; P.NCQ = NCQ; P.NK = NK; P.NGH = NGH; P.NS = NS; P.SWD = SWD;
-        P.nVw = nVw; P.nHw = nHw; P.nWw = nWw; P.rowsS = rowsS; P.rowsC = rowsC;
+        P.nVw = nVw; P.nHw = nHw; P.nWw = nWw; P.nSw = nSw; P.rowsS = rowsS; P.rowsC = rowsC;
         const int tilesX = (XB - X0base + TW - 1) / TW;
         const int max_bands = std::max(1, rows / (2 * r + 4));
         for (int bands = 1; bands <= max_bands; ++bands) {
@@ -378,7 +441,7 @@ int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
             double cost = (double)waves * (BH + 2 * r + 6) * (ncols + 16);   // +6 rows: pipeline fill/drain
             if (cost < best_cost) {
                 best_cost = cost; best = P; best_bands = bands; smem = o;
-                nt = 32 * (nVw + nHw + nWw + 2);
+                nt = 32 * (nVw + nHw + nWw + nSw);
                 ok = true;
             }
         }
@@ -393,10 +456,10 @@ int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
     P.BH = (rows + best_bands - 1) / best_bands;
     dim3 grid(tilesX, (rows + P.BH - 1) / P.BH);
     cudaError_t e;
-    if (nd == 256) e = launch_ws<256>(P, grid, nt, smem, st);
-    else if (nd == 128) e = launch_ws<128>(P, grid, nt, smem, st);
-    else if (nd == 64) e = launch_ws<64>(P, grid, nt, smem, st);
-    else e = launch_ws<0>(P, grid, nt, smem, st);
+    if (nd == 256) e = launch_ws<256>(P, rb, grid, nt, smem, st);
+    else if (nd == 128) e = launch_ws<128>(P, rb, grid, nt, smem, st);
+    else if (nd == 64) e = launch_ws<64>(P, rb, grid, nt, smem, st);
+    else e = launch_ws<0>(P, rb, grid, nt, smem, st);
     return e == cudaSuccess ? 1 : -1;
 }
 
