@@ -893,8 +893,9 @@ int b200s_process_pair_async(b200s_handle* h, int slot, const void* left, const 
             int rc2 = ensure_pre_planes(h, w, rows, cols);
             if (rc2) return rc2;
             const size_t pitch = plane_pitch(cols);
-            h->launches += launch_rectify_xsobel(L, cols, rows, mapL, h->cam[0].cm, (uint8_t*)w.rectL.p, (uint8_t*)w.preL.p + PLANE_LEAD, pitch, cols, rows, h->prm.pre_filter_cap, st);
-            h->launches += launch_rectify_xsobel(R, cols, rows, mapR, h->cam[1].cm, (uint8_t*)w.rectR.p, (uint8_t*)w.preR.p + PLANE_LEAD, pitch, cols, rows, h->prm.pre_filter_cap, st);
+            h->launches += launch_rectify_xsobel_pair(L, R, cols, rows, mapL, mapR, h->cam[0].cm, h->cam[1].cm, (uint8_t*)w.rectL.p,
+                                                      (uint8_t*)w.rectR.p, (uint8_t*)w.preL.p + PLANE_LEAD,
+                                                      (uint8_t*)w.preR.p + PLANE_LEAD, pitch, cols, rows, h->prm.pre_filter_cap, st);
             prefiltered = true;
         } else {
             h->launches += launch_remap(L, cols, rows, 1, mapL, h->cam[0].cm, (uint8_t*)w.rectL.p, cols, rows, st);

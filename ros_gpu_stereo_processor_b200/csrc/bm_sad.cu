@@ -27,6 +27,15 @@ __global__ void fill_s16_kernel(int16_t* p, size_t n, int16_t v)
     if (i < n) p[i] = v;
 }
 
+// FILTERED everywhere outside [x0, x1) x [y0, y1) (that rectangle is written completely by the matcher kernels)
+__global__ void __launch_bounds__(256) fill_border_kernel(int16_t* __restrict__ p, int W, int H, int x0, int x1, int y0, int y1, int16_t v)
+{
+    const int y = blockIdx.y;
+    const bool full = y < y0 || y >= y1;
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    if (x < W && (full || x < x0 || x >= x1)) p[(size_t)y * W + x] = v;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // fast kernel (v3)
 //
@@ -473,17 +482,23 @@ int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W
     const int16_t FILTERED = (int16_t)((cfg.minD - 1) * 16);
     int launches = 0;
     size_t n = (size_t)W * H;
-    fill_s16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(disp, n, FILTERED);
-    ++launches;
     if (cost) { cudaMemsetAsync(cost, 0, n * sizeof(int16_t), st); }
     if (evals) *evals = 0;
-    if (g.degenerate) return launches;
+    if (g.degenerate) {
+        fill_s16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(disp, n, FILTERED);
+        return launches + 1;
+    }
     const bool need_bands = cfg.disp12MaxDiff >= 0;
     // columns (in X) the matcher produces at all, and the ones that can reach the output
     const int compX0 = g.lofs, compX1 = std::min(W, g.lofs + g.width1);
     const int outX0 = need_bands ? compX0 : std::max(compX0, g.roiX0);
     const int outX1 = need_bands ? compX1 : std::min(compX1, g.roiX1);
-    if (outX1 <= outX0) return launches;
+    if (outX1 <= outX0) {
+        fill_s16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(disp, n, FILTERED);
+        return launches + 1;
+    }
+    fill_border_kernel<<<dim3((W + 255) / 256, H), 256, 0, st>>>(disp, W, H, outX0, outX1, g.roiY0, g.roiY1, FILTERED);
+    ++launches;
     if (evals) {
         int ex0 = std::max(compX0, g.roiX0), ex1 = std::min(compX1, g.roiX1);
         *evals = ex1 > ex0 ? (double)(ex1 - ex0) * (g.roiY1 - g.roiY0) * cfg.nd : 0.0;

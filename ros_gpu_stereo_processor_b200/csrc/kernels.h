@@ -24,8 +24,10 @@ int launch_build_map(const CamModel& cm, int W, int H, int2* map, cudaStream_t s
 int launch_remap(const uint8_t* src, int sW, int sH, int ch, const int2* map, const CamModel& cm,
                  uint8_t* dst, int W, int H, cudaStream_t st);
 // fused rectify (mono) + x-Sobel prefilter: writes the rectified plane and the prefiltered plane in one kernel
-int launch_rectify_xsobel(const uint8_t* src, int sW, int sH, const int2* map, const CamModel& cm,
-                          uint8_t* rect, uint8_t* pre, size_t pre_pitch, int W, int H, int cap, cudaStream_t st);
+// both sides in one launch (blockIdx.z = side)
+int launch_rectify_xsobel_pair(const uint8_t* srcL, const uint8_t* srcR, int sW, int sH, const int2* mapL, const int2* mapR,
+                               const CamModel& cmL, const CamModel& cmR, uint8_t* rectL, uint8_t* rectR, uint8_t* preL,
+                               uint8_t* preR, size_t pre_pitch, int W, int H, int cap, cudaStream_t st);
 int launch_remap_nearest(const uint8_t* src, int sW, int sH, int ch, const int2* map, const CamModel& cm,
                          uint8_t* dst, int W, int H, cudaStream_t st);
 

@@ -94,26 +94,60 @@ __global__ void __launch_bounds__(256) remap_nearest_kernel(const uint8_t* __res
 // writes the interior to `rect`, then applies OpenCV's prefilterXSobel border rules:
 // 3x3 Sobel-x with rows mirrored (reflect-101), columns 0 and W-1 = cap, odd-height last row = cap.
 constexpr int FTX = 64, FTY = 16;
+constexpr int FT_N = (FTX + 2) * (FTY + 2);          // tile + halo pixels
+constexpr int FT_PER = (FT_N + 255) / 256;           // pixels per thread
 
+struct RectSide {
+    const uint8_t* src;
+    const int2* map;
+    uint8_t* rect;
+    uint8_t* pre;
+    CamModel cm;
+};
+
+// blockIdx.z selects the side, so that one launch rectifies and prefilters the left and the right image.
+// Each thread first fetches (or evaluates) the map entries of its FT_PER tile pixels, then issues all 4*FT_PER
+// gathers, then blends: the dependent global loads of different pixels overlap.
 template <bool FLY>
-__global__ void __launch_bounds__(256) rectify_xsobel_kernel(const uint8_t* __restrict__ src, int sW, int sH,
-                                                             const int2* __restrict__ map, CamModel cm,
-                                                             uint8_t* __restrict__ rect, uint8_t* __restrict__ pre,
-                                                             size_t ppitch, int W, int H, int cap)
+__global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSide sr, int sW, int sH, size_t ppitch,
+                                                             int W, int H, int cap)
 {
     __shared__ uint8_t tile[FTY + 2][FTX + 2 + 2];
+    const RectSide& S = blockIdx.z ? sr : sl;
+    const uint8_t* __restrict__ src = S.src;
     const int x0 = blockIdx.x * FTX, y0 = blockIdx.y * FTY;
-    for (int i = threadIdx.x; i < (FTX + 2) * (FTY + 2); i += 256) {
-        int ty = i / (FTX + 2), tx = i - ty * (FTX + 2);
-        int x = x0 + tx - 1, y = y0 + ty - 1;
+    int2 m[FT_PER];
+    bool ok[FT_PER];
+#pragma unroll
+    for (int k = 0; k < FT_PER; ++k) {
+        const int i = threadIdx.x + 256 * k;
+        const int ty = i / (FTX + 2), tx = i - ty * (FTX + 2);
+        const int x = x0 + tx - 1, y = y0 + ty - 1;
         // rows are mirrored for the Sobel taps: the halo row above row 0 is row 1, below row H-1 is row H-2
-        int ys = y < 0 ? 1 : (y >= H ? H - 2 : y);
-        int v = 0;
-        if (x >= 0 && x < W && ys >= 0 && ys < H) {
-            int2 m = FLY ? map_point(cm, x, ys) : __ldg(map + (size_t)ys * W + x);
-            v = sample_linear(src, sW, sH, 1, 0, m);
-            if (tx >= 1 && tx <= FTX && ty >= 1 && ty <= FTY && y < H) rect[(size_t)y * W + x] = (uint8_t)v;
-        }
+        const int ys = y < 0 ? 1 : (y >= H ? H - 2 : y);
+        ok[k] = i < FT_N && x >= 0 && x < W && ys >= 0 && ys < H;
+        m[k] = make_int2(0, 0);
+        if (ok[k]) m[k] = FLY ? map_point(S.cm, x, ys) : __ldg(S.map + (size_t)ys * W + x);
+    }
+    int s00[FT_PER], s01[FT_PER], s10[FT_PER], s11[FT_PER];
+#pragma unroll
+    for (int k = 0; k < FT_PER; ++k) {
+        const int X0 = sat16(m[k].x >> 5), Y0 = sat16(m[k].y >> 5);
+        s00[k] = ok[k] ? fetch1(src, sW, sH, X0, Y0, 1, 0) : 0;
+        s01[k] = ok[k] ? fetch1(src, sW, sH, X0 + 1, Y0, 1, 0) : 0;
+        s10[k] = ok[k] ? fetch1(src, sW, sH, X0, Y0 + 1, 1, 0) : 0;
+        s11[k] = ok[k] ? fetch1(src, sW, sH, X0 + 1, Y0 + 1, 1, 0) : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < FT_PER; ++k) {
+        const int i = threadIdx.x + 256 * k;
+        if (i >= FT_N) continue;
+        const int ty = i / (FTX + 2), tx = i - ty * (FTX + 2);
+        const int x = x0 + tx - 1, y = y0 + ty - 1;
+        const int a = m[k].x & 31, b = m[k].y & 31;
+        const int acc = (32 - a) * (32 - b) * s00[k] + a * (32 - b) * s01[k] + (32 - a) * b * s10[k] + a * b * s11[k];
+        const int v = ok[k] ? (acc + 512) >> 10 : 0;
+        if (ok[k] && tx >= 1 && tx <= FTX && ty >= 1 && ty <= FTY && y < H) S.rect[(size_t)y * W + x] = (uint8_t)v;
         tile[ty][tx] = (uint8_t)v;
     }
     __syncthreads();
@@ -130,7 +164,7 @@ __global__ void __launch_bounds__(256) rectify_xsobel_kernel(const uint8_t* __re
             int v = d0 + 2 * d1 + d2;
             out = min(max(v, -cap), cap) + cap;
         }
-        pre[(size_t)y * ppitch + x] = (uint8_t)out;
+        S.pre[(size_t)y * ppitch + x] = (uint8_t)out;
     }
 }
 
@@ -168,12 +202,14 @@ int launch_remap_nearest(const uint8_t* src, int sW, int sH, int ch, const int2*
     return 1;
 }
 
-int launch_rectify_xsobel(const uint8_t* src, int sW, int sH, const int2* map, const CamModel& cm, uint8_t* rect,
-                          uint8_t* pre, size_t pre_pitch, int W, int H, int cap, cudaStream_t st)
+int launch_rectify_xsobel_pair(const uint8_t* srcL, const uint8_t* srcR, int sW, int sH, const int2* mapL, const int2* mapR,
+                               const CamModel& cmL, const CamModel& cmR, uint8_t* rectL, uint8_t* rectR, uint8_t* preL,
+                               uint8_t* preR, size_t pre_pitch, int W, int H, int cap, cudaStream_t st)
 {
-    dim3 g((W + FTX - 1) / FTX, (H + FTY - 1) / FTY);
-    if (map) rectify_xsobel_kernel<false><<<g, 256, 0, st>>>(src, sW, sH, map, cm, rect, pre, pre_pitch, W, H, cap);
-    else rectify_xsobel_kernel<true><<<g, 256, 0, st>>>(src, sW, sH, map, cm, rect, pre, pre_pitch, W, H, cap);
+    dim3 g((W + FTX - 1) / FTX, (H + FTY - 1) / FTY, 2);
+    RectSide l{srcL, mapL, rectL, preL, cmL}, r{srcR, mapR, rectR, preR, cmR};
+    if (mapL && mapR) rectify_xsobel_kernel<false><<<g, 256, 0, st>>>(l, r, sW, sH, pre_pitch, W, H, cap);
+    else rectify_xsobel_kernel<true><<<g, 256, 0, st>>>(l, r, sW, sH, pre_pitch, W, H, cap);
     return 1;
 }
 

@@ -65,9 +65,21 @@ __global__ void __launch_bounds__(256) reproject_pack_kernel(const int16_t* __re
     int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= W || y >= H) return;
     size_t i = (size_t)y * W + x;
-    const float dfl = disp_to_float(d16[i], cxd);
+    const int dv = d16[i], dmin = *min_d16;
+    if (!xyz && dv == dmin) {
+        // missing value (d == min over the image): cv::reprojectImageTo3D sets Z = 10000, which isValidPoint rejects,
+        // so the record is NaN xyz + colour whatever X and Y were; no arithmetic needed
+        uint32_t bgr;
+        if (ch == 3) bgr = (uint32_t)color[i * 3] | ((uint32_t)color[i * 3 + 1] << 8) | ((uint32_t)color[i * 3 + 2] << 16);
+        else { uint32_t g = color ? color[i] : 0; bgr = g | (g << 8) | (g << 16); }
+        uint4* o = (uint4*)(pc2 + i * 32);
+        o[0] = make_uint4(0x7fc00000u, 0x7fc00000u, 0x7fc00000u, 0u);
+        o[1] = make_uint4(bgr, 0u, 0u, 0u);
+        return;
+    }
+    const float dfl = disp_to_float(dv, cxd);
     const double d = (double)dfl;
-    const double minDisp = (double)disp_to_float(*min_d16, cxd);
+    const double minDisp = (double)disp_to_float(dmin, cxd);
     double h[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
