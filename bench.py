@@ -329,11 +329,16 @@ def run_ours(args, c, name, rank, world, local_rank):
         hbm_peak, hbm_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         if os.path.exists(peaks_file):
             hbm_peak, hbm_src = float(json.load(open(peaks_file))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        traffic = None
+        tf = os.path.join(ROOT, "profiles", "bm_traffic.json")
+        if name == "C4" and os.path.exists(tf):
+            t_ = json.load(open(tf))
+            traffic = t_["dram_bytes_read"] + t_["dram_bytes_write"]
         achieved = eff * 7 / t_bm / 1e12
         alg_bytes = 2 * n + 2 * n     # two prefiltered u8 planes in, one s16 disparity plane out
         roof = dict(bound="int-alu", kernel="bm_ws_kernel<%d> (warp-specialised SAD matcher)" % nd, achieved=achieved, peak=peak_tops, unit="Tops/s (scalar-equivalent int32 lane-ops, 7 per disparity evaluation)",
                     frac=achieved / peak_tops, peak_source="measured: b200s_int_peak IADD3 dependent chains, all SMs, this run",
-                    kernel_ms=t_bm * 1e3, evals_effective_per_launch=eff, gevals_per_s=eff / t_bm / 1e9, traffic=None,
+                    kernel_ms=t_bm * 1e3, evals_effective_per_launch=eff, gevals_per_s=eff / t_bm / 1e9, traffic=traffic,
                     hbm=dict(achieved=alg_bytes / t_bm / 1e9, peak=hbm_peak, unit="GB/s", frac=alg_bytes / t_bm / 1e9 / hbm_peak,
                              algorithmic_bytes=alg_bytes, peak_source=hbm_src),
                     int_peaks_tops=int_peaks, share_of_step=t_bm * FRAMES_PER_STEP / (ms_dev * 1e-3 / args.steps))

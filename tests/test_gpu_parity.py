@@ -355,3 +355,34 @@ def test_cpp_facade_chain(tmp_path):
     assert np.array_equal(d, wd), _describe(d, wd)
     df = O.disparity_to_float(wd, cal["left"]["P"][2] - cal["right"]["P"][2])
     assert np.array_equal(pc, O.pack_pointcloud2(O.reproject(df, O.stereo_Q(cal["left"]["P"], cal["right"]["P"])), wl))
+
+
+# ---- the fallback matcher kernels stay bit-exact too ------------------------------------------------------------
+@pytest.mark.parametrize("env", [{"B200S_KERNEL": "3"}, {"B200S_FORCE_GENERIC": "1"}, {"B200S_RING": "1"}])
+def test_fallback_matcher_kernels(env, tmp_path):
+    """bm_fast_kernel (non-specialised), the generic int32 path and the register-ring H variant are selected by
+    environment switches read once per process, so each runs in its own interpreter."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import ros_gpu_stereo_processor_b200 as m
+from oracle import oracle as O, synth
+p = m.GpuStereoProcessor(0)
+cases = [(500, 211, 64, 21, {}), (640, 200, 128, 11, dict(disp12MaxDiff=1)), (400, 160, 48, 9, dict(minDisparity=-8)),
+         (700, 150, 256, 11, dict(uniquenessRatio=0)), (300, 120, 16, 5, dict(textureThreshold=0))]
+for (W, H, nd, b, kw) in cases:
+    L, R = synth.synth_pair(W, H, max(nd, 16), 3)
+    q = O.BMParams(numDisparities=nd, blockSize=b, **kw)
+    p.setParams(**q.as_dict())
+    got, want = p.computeDisparityBare(L, R), O.stereobm_compute(L, R, q)
+    assert np.array_equal(got, want), (W, H, nd, b, kw, int((got != want).sum()))
+print("ok")
+''' % root
+    e = dict(os.environ)
+    e.update(env)
+    out = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
