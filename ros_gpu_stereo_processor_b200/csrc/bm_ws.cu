@@ -196,15 +196,20 @@ __global__ void __launch_bounds__(WsBounds<RB>::threads, 1) bm_ws_kernel(const W
                         S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
                     }
                     const uint8_t* pa = pc + b * CWb;
-                    for (int x0 = 0; x0 < P.SWD; x0 += 4) {     // SWD is a multiple of 4
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            B200S_H_EMIT(i * SWb, i * KWb)
-                            const uint4 a = *(const uint4*)(pa + i * CWb);
-                            const uint4 ov = *(const uint4*)(pc + i * CWb);
-                            S.x += a.x - ov.x; S.y += a.y - ov.y; S.z += a.z - ov.z; S.w += a.w - ov.w;
-                        }
-                        pa += 4 * CWb; pc += 4 * CWb; ps += 4 * SWb; pk += 4 * KWb;
+                    // software pipeline: the entering/leaving columns of the next pair are loaded before the stores of
+                    // the current pair (the compiler will not hoist shared loads over shared stores by itself)
+                    uint4 a0 = *(const uint4*)(pa), o0 = *(const uint4*)(pc);
+                    uint4 a1 = *(const uint4*)(pa + CWb), o1 = *(const uint4*)(pc + CWb);
+                    for (int x0 = 0; x0 < P.SWD; x0 += 2) {     // SWD is a multiple of 4; Cbuf has spare rows behind
+                        pa += 2 * CWb; pc += 2 * CWb;
+                        const uint4 na0 = *(const uint4*)(pa), no0 = *(const uint4*)(pc);
+                        const uint4 na1 = *(const uint4*)(pa + CWb), no1 = *(const uint4*)(pc + CWb);
+                        B200S_H_EMIT(0, 0)
+                        S.x += a0.x - o0.x; S.y += a0.y - o0.y; S.z += a0.z - o0.z; S.w += a0.w - o0.w;
+                        B200S_H_EMIT(SWb, KWb)
+                        S.x += a1.x - o1.x; S.y += a1.y - o1.y; S.z += a1.z - o1.z; S.w += a1.w - o1.w;
+                        a0 = na0; o0 = no0; a1 = na1; o1 = no1;
+                        ps += 2 * SWb; pk += 2 * KWb;
                     }
                 }
 #undef B200S_H_EMIT
@@ -416,7 +421,7 @@ int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
         int nSw = (nVw + nHw + nWw + 2 <= warp_cap) ? 2 : 1;
         if (nVw + nHw + nWw + nSw > warp_cap) continue;
         const int ncols = 4 * NCQ;
-        const int rowsS = NS * SWD, rowsC = std::max(ncols, rowsS + 2 * r + 2);
+        const int rowsS = NS * SWD, rowsC = std::max(ncols, rowsS + 2 * r + 4);
         P.CWb = nd * 2; P.SWb = nd * 2 + 16; P.NK4 = (NGH + 3) / 4; P.KWb = (P.NK4 * 4 + 4) * 4;
         P.RLW = (ncols + nd) / 4 + 1;
         int units = (4 * P.RLW + 15) / 16;
