@@ -385,7 +385,10 @@ int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
     const int nd = cfg.nd;
     const int NK = nd / 16, NGH = nd / 8;
     static const int max_warps = getenv("B200S_WS_WARPS") ? atoi(getenv("B200S_WS_WARPS")) : 24;
-    static const int swd_min = getenv("B200S_SWD") ? atoi(getenv("B200S_SWD")) : 12;
+    // H strip width: longer strips amortise the 2r+1 warm-up loads (the kernel is bound by shared-memory wavefronts),
+    // shorter ones give more H warps; measured best on B200: 21 columns at nd = 256, ~14 below
+    static const int swd_env = getenv("B200S_SWD") ? atoi(getenv("B200S_SWD")) : 0;
+    const int swd_min = swd_env > 0 ? swd_env : (nd >= 256 ? 21 : 14);
     static const int ring_mult = getenv("B200S_RING_MULT") ? atoi(getenv("B200S_RING_MULT")) : 2;
     // the register-ring variant of the H role (one LDS.128 per column) measured slower on B200 (fewer, longer strips:
     // 323 us vs 274 us on C4) and is off unless B200S_RING=1
@@ -413,7 +416,7 @@ int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
             NS = (TW + SWD - 1) / SWD;
         } else {
             NS = std::max(1, (TW + swd_min - 1) / swd_min);
-            SWD = (((TW + NS - 1) / NS) + 3) & ~3;  // multiple of 4 (the H loop is unrolled by 4)
+            SWD = (((TW + NS - 1) / NS) + 1) & ~1;  // even (the H loop handles two columns per iteration)
             NS = (TW + SWD - 1) / SWD;
         }
         int nHw = (NS * NGH + 31) / 32;
