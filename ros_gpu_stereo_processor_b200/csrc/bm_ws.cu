@@ -27,7 +27,7 @@ struct WsParams {
     int X0base, XA, XB, YA, YB;
     int TW, BH, ncols, NCQ, NK, NGH, NS, SWD;
     int CWb, SWb, KWb, NK4, CSB, RLW;
-    int nVw, nHw, nWw;     // warps per role; nSw (1 or 2) stager warps follow
+    int nVw, nHw, nWw;     // warps per role; nSw (1..4) stager warps follow
     int nSw;
     int rowsS, rowsC;
     int oStage[2];         // per buffer: Lb [2][ncols] words, then Rc [2][4][CSB] bytes
@@ -180,13 +180,15 @@ __global__ void __launch_bounds__(WsBounds<RB>::threads, 1) bm_ws_kernel(const W
                         S.x += ring[c].x; S.y += ring[c].y; S.z += ring[c].z; S.w += ring[c].w;
                     }
                     const uint8_t* pa = pc + RB * CWb;
+                    uint4 a = *(const uint4*)pa;                 // entering column of the first pixel, loaded ahead
                     for (int x0 = 0; x0 < P.SWD; x0 += RB) {
 #pragma unroll
                         for (int i = 0; i < RB; ++i) {
+                            const uint4 an = *(const uint4*)(pa + (i + 1) * CWb);   // next pixel's entering column
                             B200S_H_EMIT(i * SWb, i * KWb)
-                            const uint4 a = *(const uint4*)(pa + i * CWb);
                             S.x += a.x - ring[i].x; S.y += a.y - ring[i].y; S.z += a.z - ring[i].z; S.w += a.w - ring[i].w;
                             ring[i] = a;
+                            a = an;
                         }
                         pa += RB * CWb; ps += RB * SWb; pk += RB * KWb;
                     }
@@ -338,11 +340,13 @@ __global__ void __launch_bounds__(WsBounds<RB>::threads, 1) bm_ws_kernel(const W
                     if (publish) tpub[c] = t;     // texture column sums of output row j - 2r (ring of 8 rows)
                 }
             }
-            if (s == P.nSw - 1) {
+            if (s >= 1 || P.nSw == 1) {   // right rows: the words are spread over the remaining stager warps
                 const uint32_t* rn = (const uint32_t*)(P.Rp + (size_t)yi * P.pitch + Xr0);
                 const uint32_t* ro = (const uint32_t*)(P.Rp + (size_t)max(yi - b, 0) * P.pitch + Xr0);
                 uint8_t* sRc = smem + P.oStage[sb] + 2 * P.ncols * 4;
-                for (int wi = lane; wi < P.RLW; wi += 32) {
+                const int nrw = P.nSw > 1 ? P.nSw - 1 : 1, rw = P.nSw > 1 ? s - 1 : 0;
+#pragma unroll 2
+                for (int wi = rw * 32 + lane; wi < P.RLW; wi += 32 * nrw) {
                     const uint32_t vn = __ldg(rn + wi), vo = has_old ? __ldg(ro + wi) : 0u;
                     uint8_t* cp = sRc + 4 * wi;
                     // copy jj holds row[a + 4 jj] at byte a
@@ -421,7 +425,8 @@ int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
         }
         int nHw = (NS * NGH + 31) / 32;
         const int warp_cap = rb ? std::min(max_warps, 20) : max_warps;   // ring variant: 640 threads, 96 registers
-        int nSw = (nVw + nHw + nWw + 2 <= warp_cap) ? 2 : 1;
+        static const int stagers_env = getenv("B200S_STAGERS") ? atoi(getenv("B200S_STAGERS")) : 4;
+        int nSw = std::max(1, std::min(stagers_env, warp_cap - (nVw + nHw + nWw)));   // staging sits on the critical path
         if (nVw + nHw + nWw + nSw > warp_cap) continue;
         const int ncols = 4 * NCQ;
         const int rowsS = NS * SWD, rowsC = std::max(ncols, rowsS + 2 * r + 4);
