@@ -376,11 +376,10 @@ template <int ND>
 static cudaError_t launch_ws(const WsParams& P, int rb, dim3 grid, int nt, size_t smem, cudaStream_t st)
 {
     if (rb == 11) return launch_ws2<ND, 11>(P, grid, nt, smem, st);
-    if (rb == 9) return launch_ws2<ND, 9>(P, grid, nt, smem, st);
     return launch_ws2<ND, 0>(P, grid, nt, smem, st);
 }
 
-static inline bool ring_width_supported(int b) { return b == 9 || b == 11; }
+static inline bool ring_width_supported(int b) { return b == 11; }
 
 // returns 1 when launched, 0 when this configuration is not handled (caller falls back), < 0 on CUDA errors
 int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg, int r, int lofs,
@@ -427,6 +426,8 @@ int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
         const int warp_cap = rb ? std::min(max_warps, 20) : max_warps;   // ring variant: 640 threads, 96 registers
         static const int stagers_env = getenv("B200S_STAGERS") ? atoi(getenv("B200S_STAGERS")) : 4;
         int nSw = std::max(1, std::min(stagers_env, warp_cap - (nVw + nHw + nWw)));   // staging sits on the critical path
+        static const int min_stagers = getenv("B200S_MIN_STAGERS") ? atoi(getenv("B200S_MIN_STAGERS")) : 2;
+        if (nSw < min_stagers && NCQ > 8) continue;   // a single stager warp costs ~15 % (measured); prefer a narrower tile
         if (nVw + nHw + nWw + nSw > warp_cap) continue;
         const int ncols = 4 * NCQ;
         const int rowsS = NS * SWD, rowsC = std::max(ncols, rowsS + 2 * r + 4);
