@@ -235,3 +235,24 @@ def valid_window(W, H, minD, nd, wsz):
     top = border
     bottom = H - 1 - border
     return dict(x_offset=left, y_offset=top, width=right - left, height=bottom - top)
+
+
+def draw_color_disp(d16, nd):
+    """cv::cuda::drawColorDisp restated (opencv_contrib cudastereo util.cu, cvtPixel) on d = clamp(d16 >> 4, 0, 255).
+    PARITY UNPINNED: the upstream kernel is not in /root/reference and cv2 has no CUDA modules; no golden exists."""
+    d = np.clip(np.asarray(d16, np.int32) >> 4, 0, 255)
+    a = (nd - d).astype(np.int64) * 240
+    H = (np.sign(a) * (np.abs(a) // nd)) & 0xFFFFFFFF   # C int division (truncating), then conversion to unsigned
+    H = H.astype(np.uint32)
+    hi = (H // 60) % 6
+    f = (H.astype(np.float32) / np.float32(60.0)) - (H // 60).astype(np.float32)
+    one, zero = np.ones_like(f), np.zeros_like(f)
+    q, t = one - f, f
+    x = np.select([hi == 0, hi == 1, hi == 2, hi == 3, hi == 4], [zero, zero, t, one, one], q)
+    y = np.select([hi == 0, hi == 1, hi == 2, hi == 3, hi == 4], [t, one, one, q, zero], zero)
+    z = np.select([hi == 0, hi == 1, hi == 2, hi == 3, hi == 4], [one, q, zero, zero, t], one)
+    out = np.empty(d.shape + (4,), np.uint8)
+    for c, v in enumerate((x, y, z)):
+        out[..., c] = (np.clip(v, 0, 1).astype(np.float32) * np.float32(255.0)).astype(np.uint32).astype(np.uint8)
+    out[..., 3] = 255
+    return out

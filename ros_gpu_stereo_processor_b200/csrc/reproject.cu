@@ -111,32 +111,33 @@ __global__ void __launch_bounds__(256) reproject_pack_kernel(const int16_t* __re
     }
 }
 
-// cv::cuda::drawColorDisp-style HSV map of the integer disparity (reference: computeDisparityImage,
-// src/GPUStereoProcessor.cpp:323-330).  FILTERED / negative -> black.  "next" row of the scope table.
+// cv::cuda::drawColorDisp (opencv_contrib cudastereo, util.cu cvtPixel) on the integer disparity d = clamp(d16 >> 4, 0, 255),
+// the u8 value the reference's matcher plane holds (invalid = 0 -> hue 240 = blue).  Reference call site:
+// computeDisparityImage, src/GPUStereoProcessor.cpp:323-330.  "next" row 1 of the scope table; the upstream kernel is
+// not in /root/reference and cv2 has no CUDA modules, so this is a restatement without a golden (parity unpinned).
 __global__ void __launch_bounds__(256) disparity_color_kernel(const int16_t* __restrict__ d16, uint8_t* __restrict__ bgra,
                                                               int n, int nd)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int d = d16[i] >> 4;
-    uint32_t out = 0;
-    if (d > 0 && d < nd) {
-        unsigned H = ((unsigned)(nd - d) * 240u) / (unsigned)nd;
-        unsigned hi = (H / 60u) % 6u;
-        float f = (float)H / 60.f - (float)(H / 60u);
-        unsigned V = 255, p = 0, q = (unsigned)(255.f * (1.f - f)), t = (unsigned)(255.f * f);
-        unsigned r, g, b;
-        switch (hi) {
-            case 0: r = V; g = t; b = p; break;
-            case 1: r = q; g = V; b = p; break;
-            case 2: r = p; g = V; b = t; break;
-            case 3: r = p; g = q; b = V; break;
-            case 4: r = t; g = p; b = V; break;
-            default: r = V; g = p; b = q; break;
-        }
-        out = b | (g << 8) | (r << 16) | (255u << 24);
+    const int d = min(max((int)d16[i] >> 4, 0), 255);
+    const unsigned H = (unsigned)(((nd - d) * 240) / nd);   // int division, then unsigned, like upstream
+    const unsigned hi = (H / 60u) % 6u;
+    const float f = __fsub_rn(__fdiv_rn((float)H, 60.f), (float)(H / 60u));
+    const float V = 1.f, p = 0.f, q = __fsub_rn(1.f, f), t = f;     // S = V = 1: p = 0, q = 1 - f, t = 1 - (1 - f) = f
+    float x, y, z;                                                   // x = blue, y = green, z = red
+    switch (hi) {
+        case 0: x = p; y = t; z = V; break;
+        case 1: x = p; y = V; z = q; break;
+        case 2: x = t; y = V; z = p; break;
+        case 3: x = V; y = q; z = p; break;
+        case 4: x = V; y = p; z = t; break;
+        default: x = q; y = p; z = V; break;
     }
-    ((uint32_t*)bgra)[i] = out;
+    const unsigned bb = (unsigned)__fmul_rn(fmaxf(0.f, fminf(x, 1.f)), 255.f);
+    const unsigned gg = (unsigned)__fmul_rn(fmaxf(0.f, fminf(y, 1.f)), 255.f);
+    const unsigned rr = (unsigned)__fmul_rn(fmaxf(0.f, fminf(z, 1.f)), 255.f);
+    ((uint32_t*)bgra)[i] = bb | (gg << 8) | (rr << 16) | (255u << 24);
 }
 
 int launch_disparity_to_float(const int16_t* d16, float* df, int n, double cxd, int* min_d16, cudaStream_t st)

@@ -252,8 +252,9 @@ def test_pointcloud_and_disparity_messages(proc, fixtures, calib):
     assert abs(dm["f"] - 441.238411) < 1e-3 and abs(dm["T"] - 0.100021) < 1e-5
     im = proc.enqueueSendImage(m.SRC_RECT_MONO | m.SIDE_L, encoding="mono8").message
     assert im["step"] == 752 and np.array_equal(im["data"].reshape(480, 752), L)
-    proc.computeDisparityImage(m.SRC_DISPARITY | m.SIDE_L, m.SRC_DISPARITY_IMG | m.SIDE_L)
-    assert proc.downloadMat(m.SRC_DISPARITY_IMG | m.SIDE_L).shape == (480, 752, 4)
+    proc.computeDisparityImage(m.SRC_DISPARITY | m.SIDE_L, m.SRC_DISPARITY_IMG | m.SIDE_L)   # disparity_vis topic (BGRA8)
+    vis = proc.downloadMat(m.SRC_DISPARITY_IMG | m.SIDE_L)
+    assert np.array_equal(vis, O.draw_color_disp(want_d, 128))
     proc.cleanSenders()
 
 
