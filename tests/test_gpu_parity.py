@@ -387,3 +387,38 @@ print("ok")
     e.update(env)
     out = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
+# ---- ragged / extreme shapes ------------------------------------------------------------------------------------
+RAGGED = [
+    (97, 53, dict(numDisparities=16, blockSize=5)),
+    (333, 111, dict(numDisparities=48, blockSize=7, disp12MaxDiff=0)),
+    (1001, 97, dict(numDisparities=112, blockSize=9, uniquenessRatio=40)),
+    (139, 41, dict(numDisparities=128, blockSize=5)),                       # only a handful of computable columns
+    (131, 64, dict(numDisparities=128, blockSize=5)),                       # width1 < block: ROI empty -> all FILTERED
+    (641, 23, dict(numDisparities=32, blockSize=21, textureThreshold=500)),  # two computable rows
+    (257, 129, dict(numDisparities=64, blockSize=33, preFilterCap=15)),     # 2*cap*b^2 = 32670: 16-bit path, big window
+    (257, 129, dict(numDisparities=64, blockSize=33, preFilterCap=63)),     # 137214 >= 65535: generic int32 path
+    (2049, 65, dict(numDisparities=256, blockSize=11, speckleWindowSize=30, speckleRange=16)),
+    (300, 200, dict(numDisparities=16, blockSize=5, minDisparity=-40)),     # nd-1+minD < 0: rofs > 0, generic path
+]
+
+
+@pytest.mark.parametrize("case", RAGGED)
+def test_disparity_ragged_shapes(proc, case):
+    W, H, kw = case
+    p = O.BMParams(**kw)
+    L, R = synth.synth_pair(W, H, max(p.numDisparities, 16), seed=W * 7 + H)
+    _set(proc, p)
+    got = proc.computeDisparityBare(L, R)
+    want = O.stereobm_compute(L, R, p)
+    assert np.array_equal(got, want), _describe(got, want)
+
+
+def test_block_not_smaller_than_image_is_rejected(proc):
+    m = _gpu()
+    L, R = synth.synth_pair(64, 21, 16, seed=3)
+    _set(proc, O.BMParams(numDisparities=16, blockSize=21))
+    with pytest.raises(m._capi.B200StereoError) as e:   # cv2: "SADWindowSize must be ... not larger than image width or height"
+        proc.computeDisparityBare(L, R)
+    assert e.value.code == m._capi.EINVAL
