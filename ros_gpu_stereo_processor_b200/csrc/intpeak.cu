@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, uint32_t a
             if (WHICH == 4) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y), "r"(z));
             if (WHICH == 5) asm volatile("prmt.b32 %0, %0, %1, 0x4341;" : "+r"(x[i]) : "r"(y));
             if (WHICH == 6) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(y), "r"(z));
+            if (WHICH == 8) x[i] = __shfl_down_sync(0xffffffffu, x[i], 1) + y;
             if (WHICH == 7) {
                 if (i & 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y), "r"(z));
                 else asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(x[i]) : "r"(y), "r"(z));
@@ -78,6 +79,7 @@ int run_int_peak(int which, double* lane_ops_per_s, double* sm_mhz, cudaStream_t
         case 5: ms = time_variant<5>(dbuf, blocks, st); break;
         case 6: ms = time_variant<6>(dbuf, blocks, st); break;
         case 7: ms = time_variant<7>(dbuf, blocks, st); break;
+        case 8: ms = time_variant<8>(dbuf, blocks, st); break;
         default: cudaFree(dbuf); return -1;
     }
     cudaFree(dbuf);
