@@ -101,6 +101,7 @@ struct b200s_handle {
     Camera cam[2];
     double Q[16];
     double baseline = 0, fx_right = 0, cxd = 0;
+    unsigned qmask = 0xFFFFu;
     DevBuf Qdev;
     std::unordered_map<int, Mat> mats;
     cudaStream_t l_strm = nullptr, r_strm = nullptr;
@@ -447,6 +448,10 @@ int b200s_set_calibration(b200s_handle* h, const b200s_caminfo* left, const b200
     h->Q[5] = fx * Tx;       h->Q[7] = -fx * cy * Tx;
     h->Q[11] = fx * fy * Tx;
     h->Q[14] = -fy;          h->Q[15] = fy * (cx - cxr);
+    h->qmask = 0;
+    for (int i = 0; i < 16; ++i)
+        if (h->Q[i] != 0.0) h->qmask |= 1u << i;
+    // a NaN/Inf coordinate cannot occur (x, y are pixel indices, d is a finite float), so skipping zero terms is exact
     h->baseline = -Pr[3] / Pr[0];
     h->fx_right = Pr[0];
     h->cxd = cx - cxr;
@@ -732,7 +737,7 @@ int b200s_project_to_3d(b200s_handle* h, int disp_id, int points_id)
     if (rc) return rc;
     cudaStream_t st = stream_of(h, disp_id);
     h->launches += launch_disparity_to_float((const int16_t*)D->buf.p, nullptr, rows * cols, h->cxd, (int*)h->w0.misc.p, st);
-    h->launches += launch_reproject_pack((const int16_t*)D->buf.p, cols, rows, h->cxd, (const double*)h->Qdev.p,
+    h->launches += launch_reproject_pack((const int16_t*)D->buf.p, cols, rows, h->cxd, (const double*)h->Qdev.p, h->qmask,
                                          (const int*)h->w0.misc.p, nullptr, 1, (float*)P->buf.p, nullptr, st);
     return check_kernels(h, "project_to_3d");
 }
@@ -824,7 +829,7 @@ int b200s_pack_pointcloud2(b200s_handle* h, int disp_id, int color_id, void* dst
     CUDA_OK(h, cudaEventRecord(h->ev_r, h->r_strm));
     CUDA_OK(h, cudaStreamWaitEvent(st, h->ev_r, 0));
     h->launches += launch_disparity_to_float((const int16_t*)D->buf.p, nullptr, (int)n, h->cxd, (int*)h->w0.misc.p, st);
-    h->launches += launch_reproject_pack((const int16_t*)D->buf.p, D->cols, D->rows, h->cxd, (const double*)h->Qdev.p,
+    h->launches += launch_reproject_pack((const int16_t*)D->buf.p, D->cols, D->rows, h->cxd, (const double*)h->Qdev.p, h->qmask,
                                          (const int*)h->w0.misc.p, (const uint8_t*)Cc->buf.p, Cc->type == B200S_8UC3 ? 3 : 1,
                                          nullptr, (uint8_t*)h->w0.pc2.p, st);
     CUDA_OK(h, cudaMemcpyAsync(dst, h->w0.pc2.p, n * 32, cudaMemcpyDeviceToHost, st));
@@ -919,7 +924,7 @@ int b200s_process_pair_async(b200s_handle* h, int slot, const void* left, const 
     if (want_pc || want_xyz) {
         if (want_pc && w.pc2.ensure(n * 32)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (point cloud)");
         if (want_xyz && w.xyz.ensure(n * 12)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (points)");
-        h->launches += launch_reproject_pack((const int16_t*)w.disp.p, cols, rows, h->cxd, (const double*)h->Qdev.p,
+        h->launches += launch_reproject_pack((const int16_t*)w.disp.p, cols, rows, h->cxd, (const double*)h->Qdev.p, h->qmask,
                                              (const int*)w.misc.p, rl, 1, want_xyz ? (float*)w.xyz.p : nullptr,
                                              want_pc ? (uint8_t*)w.pc2.p : nullptr, st);
     }

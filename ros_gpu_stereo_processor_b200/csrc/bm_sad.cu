@@ -27,13 +27,27 @@ __global__ void fill_s16_kernel(int16_t* p, size_t n, int16_t v)
     if (i < n) p[i] = v;
 }
 
-// FILTERED everywhere outside [x0, x1) x [y0, y1) (that rectangle is written completely by the matcher kernels)
+// FILTERED everywhere outside [x0, x1) x [y0, y1) (that rectangle is written completely by the matcher kernels).
+// The thread index space is compact: first the nb = x0 + (W - x1) border columns of every row, then the interior
+// columns of the rows above y0 and below y1.
 __global__ void __launch_bounds__(256) fill_border_kernel(int16_t* __restrict__ p, int W, int H, int x0, int x1, int y0, int y1, int16_t v)
 {
-    const int y = blockIdx.y;
-    const bool full = y < y0 || y >= y1;
-    const int x = blockIdx.x * 256 + threadIdx.x;
-    if (x < W && (full || x < x0 || x >= x1)) p[(size_t)y * W + x] = v;
+    const int nb = x0 + (W - x1), ni = x1 - x0, nrows_tb = y0 + (H - y1);
+    const long long n_side = (long long)nb * H, total = n_side + (long long)ni * nrows_tb;
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    int x, y;
+    if (i < n_side) {
+        y = (int)(i / nb);
+        const int c = (int)(i - (long long)y * nb);
+        x = c < x0 ? c : x1 + (c - x0);
+    } else {
+        i -= n_side;
+        const int rr = (int)(i / ni);
+        x = x0 + (int)(i - (long long)rr * ni);
+        y = rr < y0 ? rr : y1 + (rr - y0);
+    }
+    p[(size_t)y * W + x] = v;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -497,7 +511,11 @@ int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W
         fill_s16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(disp, n, FILTERED);
         return launches + 1;
     }
-    fill_border_kernel<<<dim3((W + 255) / 256, H), 256, 0, st>>>(disp, W, H, outX0, outX1, g.roiY0, g.roiY1, FILTERED);
+    {
+        const long long nfill = (long long)(outX0 + (W - outX1)) * H + (long long)(outX1 - outX0) * (g.roiY0 + (H - g.roiY1));
+        if (nfill > 0)
+            fill_border_kernel<<<(unsigned)((nfill + 255) / 256), 256, 0, st>>>(disp, W, H, outX0, outX1, g.roiY0, g.roiY1, FILTERED);
+    }
     ++launches;
     if (evals) {
         int ex0 = std::max(compX0, g.roiX0), ex1 = std::min(compX1, g.roiX1);

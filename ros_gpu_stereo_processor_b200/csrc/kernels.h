@@ -69,7 +69,8 @@ int launch_filter_speckles(int16_t* img, int W, int H, int newVal, int maxSize, 
 int launch_disparity_to_float(const int16_t* d16, float* df, int n, double cxd, int* min_d16, cudaStream_t st);
 // cv::reprojectImageTo3D(handleMissingValues=true) fused with PointCloud2 packing.
 // xyz (f32 x3, optional) and pc2 (32 B records, optional); color: ch = 1 (mono replicated) or 3 (BGR)
-int launch_reproject_pack(const int16_t* d16, int W, int H, double cxd, const double* Q, const int* min_d16,
+// qmask: bit (4*r + c) set when Q[r][c] != 0 (zero terms are skipped; the result is bit-identical)
+int launch_reproject_pack(const int16_t* d16, int W, int H, double cxd, const double* Q, unsigned qmask, const int* min_d16,
                           const uint8_t* color, int ch, float* xyz, uint8_t* pc2, cudaStream_t st);
 int launch_disparity_color(const int16_t* d16, uint8_t* bgra, int n, int nd, cudaStream_t st);
 

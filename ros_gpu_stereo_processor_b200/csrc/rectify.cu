@@ -147,24 +147,41 @@ __global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSi
         const int a = m[k].x & 31, b = m[k].y & 31;
         const int acc = (32 - a) * (32 - b) * s00[k] + a * (32 - b) * s01[k] + (32 - a) * b * s10[k] + a * b * s11[k];
         const int v = ok[k] ? (acc + 512) >> 10 : 0;
-        if (ok[k] && tx >= 1 && tx <= FTX && ty >= 1 && ty <= FTY && y < H) S.rect[(size_t)y * W + x] = (uint8_t)v;
         tile[ty][tx] = (uint8_t)v;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < FTX * FTY; i += 256) {
-        int ty = i / FTX, tx = i - ty * FTX;
-        int x = x0 + tx, y = y0 + ty;
-        if (x >= W || y >= H) continue;
-        int out = cap;
-        bool last_odd = (H & 1) && (y == H - 1);
-        if (x > 0 && x < W - 1 && !last_odd && H > 1) {
-            int d0 = (int)tile[ty][tx + 2] - (int)tile[ty][tx];
-            int d1 = (int)tile[ty + 1][tx + 2] - (int)tile[ty + 1][tx];
-            int d2 = (int)tile[ty + 2][tx + 2] - (int)tile[ty + 2][tx];
-            int v = d0 + 2 * d1 + d2;
-            out = min(max(v, -cap), cap) + cap;
+    // each thread finishes 4 adjacent pixels: one 32-bit store to the (pitched) prefiltered plane, and one to the
+    // rectified plane when its rows are word aligned
+    {
+        const int ty = threadIdx.x >> 4, tx = (threadIdx.x & 15) * 4;
+        const int x = x0 + tx, y = y0 + ty;
+        if (x < W && y < H) {
+            const bool last_odd = (H & 1) && (y == H - 1);
+            uint32_t pre4 = 0, rect4 = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int xi = x + i;
+                int out = cap;
+                if (xi > 0 && xi < W - 1 && !last_odd && H > 1) {
+                    int d0 = (int)tile[ty][tx + i + 2] - (int)tile[ty][tx + i];
+                    int d1 = (int)tile[ty + 1][tx + i + 2] - (int)tile[ty + 1][tx + i];
+                    int d2 = (int)tile[ty + 2][tx + i + 2] - (int)tile[ty + 2][tx + i];
+                    int v = d0 + 2 * d1 + d2;
+                    out = min(max(v, -cap), cap) + cap;
+                }
+                pre4 |= (uint32_t)out << (8 * i);
+                rect4 |= (uint32_t)tile[ty + 1][tx + i + 1] << (8 * i);
+            }
+            uint8_t* pp = S.pre + (size_t)y * ppitch + x;
+            uint8_t* rp = S.rect + (size_t)y * W + x;
+            if (x + 3 < W) {
+                *(uint32_t*)pp = pre4;                               // ppitch % 16 == 0 and x % 4 == 0
+                if ((W & 3) == 0) *(uint32_t*)rp = rect4;
+                else { rp[0] = (uint8_t)rect4; rp[1] = (uint8_t)(rect4 >> 8); rp[2] = (uint8_t)(rect4 >> 16); rp[3] = (uint8_t)(rect4 >> 24); }
+            } else {
+                for (int i = 0; i < 4 && x + i < W; ++i) { pp[i] = (uint8_t)(pre4 >> (8 * i)); rp[i] = (uint8_t)(rect4 >> (8 * i)); }
+            }
         }
-        S.pre[(size_t)y * ppitch + x] = (uint8_t)out;
     }
 }
 

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) disparity_to_float_kernel(const int16_t* 
 __global__ void __launch_bounds__(256) reproject_pack_kernel(const int16_t* __restrict__ d16, int W, int H, double cxd,
                                                              const double* __restrict__ Q, const int* __restrict__ min_d16,
                                                              const uint8_t* __restrict__ color, int ch,
-                                                             float* __restrict__ xyz, uint8_t* __restrict__ pc2)
+                                                             float* __restrict__ xyz, uint8_t* __restrict__ pc2, unsigned qmask)
 {
     int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= W || y >= H) return;
@@ -83,10 +83,12 @@ __global__ void __launch_bounds__(256) reproject_pack_kernel(const int16_t* __re
     double h[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        double s = __dmul_rn(__ldg(Q + r * 4 + 0), (double)x);
-        s = __dadd_rn(s, __dmul_rn(__ldg(Q + r * 4 + 1), (double)y));
-        s = __dadd_rn(s, __dmul_rn(__ldg(Q + r * 4 + 2), d));
-        s = __dadd_rn(s, __ldg(Q + r * 4 + 3));
+        // entries of Q that are exactly zero are skipped (qmask bit = entry is non-zero): 0 * v = +-0 and s + (+-0) = s,
+        // so the sum is bit-identical to the full 4-term product of cv::reprojectImageTo3D (finite v)
+        double s = (qmask >> (r * 4 + 0)) & 1u ? __dmul_rn(__ldg(Q + r * 4 + 0), (double)x) : 0.0;
+        if ((qmask >> (r * 4 + 1)) & 1u) s = __dadd_rn(s, __dmul_rn(__ldg(Q + r * 4 + 1), (double)y));
+        if ((qmask >> (r * 4 + 2)) & 1u) s = __dadd_rn(s, __dmul_rn(__ldg(Q + r * 4 + 2), d));
+        if ((qmask >> (r * 4 + 3)) & 1u) s = __dadd_rn(s, __ldg(Q + r * 4 + 3));
         h[r] = s;
     }
     float p[3];
@@ -147,11 +149,11 @@ int launch_disparity_to_float(const int16_t* d16, float* df, int n, double cxd, 
     return 1;
 }
 
-int launch_reproject_pack(const int16_t* d16, int W, int H, double cxd, const double* Q, const int* min_d16,
+int launch_reproject_pack(const int16_t* d16, int W, int H, double cxd, const double* Q, unsigned qmask, const int* min_d16,
                           const uint8_t* color, int ch, float* xyz, uint8_t* pc2, cudaStream_t st)
 {
     dim3 g((W + 31) / 32, (H + 7) / 8);
-    reproject_pack_kernel<<<g, 256, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2);
+    reproject_pack_kernel<<<g, 256, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask);
     return 1;
 }
 
