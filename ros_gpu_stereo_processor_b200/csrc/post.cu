@@ -86,28 +86,103 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b)
     }
 }
 
-__global__ void __launch_bounds__(256) ccl_init_kernel(const int16_t* __restrict__ img, int* __restrict__ L,
-                                                       int* __restrict__ sz, int n, int newVal)
+// ---- stage 1: connected components inside 64x16 tiles, entirely in shared memory -------------------------------
+constexpr int CTX = 64, CTY = 16;
+
+__device__ __forceinline__ int sm_find(volatile int* L, int i)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    L[i] = (img[i] != newVal) ? i : -1;
-    sz[i] = 0;
+    int p = L[i];
+    while (p != i) {
+        int gp = L[p];
+        if (gp != p) L[i] = gp;   // path halving (a stale write still points at an ancestor)
+        i = p;
+        p = gp;
+    }
+    return i;
 }
 
-__global__ void __launch_bounds__(256) ccl_merge_kernel(const int16_t* __restrict__ img, int* __restrict__ L, int W,
-                                                        int H, int newVal, int maxDiff)
+__device__ __forceinline__ void sm_union(int* L, int a, int b)
+{
+    while (true) {
+        a = sm_find(L, a);
+        b = sm_find(L, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        int old = atomicCAS(&L[a], a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// writes L[i] = global index of the tile-local root (or -1 for newVal pixels) and clears sz
+__global__ void __launch_bounds__(256) ccl_local_kernel(const int16_t* __restrict__ img, int* __restrict__ L,
+                                                        int* __restrict__ sz, int W, int H, int newVal, int maxDiff)
+{
+    __shared__ int16_t v[CTY * CTX];
+    __shared__ int lab[CTY * CTX];
+    const int x0 = blockIdx.x * CTX, y0 = blockIdx.y * CTY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = threadIdx.x + 256 * k;
+        const int tx = idx & (CTX - 1), ty = idx >> 6;
+        const int x = x0 + tx, y = y0 + ty;
+        int val = newVal;
+        if (x < W && y < H) {
+            val = img[(size_t)y * W + x];
+            sz[(size_t)y * W + x] = 0;
+        }
+        v[idx] = (int16_t)val;
+        lab[idx] = val != newVal ? idx : -1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = threadIdx.x + 256 * k;
+        const int tx = idx & (CTX - 1), ty = idx >> 6;
+        const int a = v[idx];
+        if (a == newVal) continue;
+        if (tx + 1 < CTX) {
+            const int u = v[idx + 1];
+            if (u != newVal && abs(u - a) <= maxDiff) sm_union(lab, idx, idx + 1);
+        }
+        if (ty + 1 < CTY) {
+            const int u = v[idx + CTX];
+            if (u != newVal && abs(u - a) <= maxDiff) sm_union(lab, idx, idx + CTX);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = threadIdx.x + 256 * k;
+        const int tx = idx & (CTX - 1), ty = idx >> 6;
+        const int x = x0 + tx, y = y0 + ty;
+        if (x >= W || y >= H) continue;
+        int g = -1;
+        if (lab[idx] >= 0) {
+            const int r = sm_find(lab, idx);
+            g = (y0 + (r >> 6)) * W + x0 + (r & (CTX - 1));   // raster order is preserved: root index <= own index
+        }
+        L[(size_t)y * W + x] = g;
+    }
+}
+
+// ---- stage 2: unions across tile borders (global union-find) ----------------------------------------------------
+__global__ void __launch_bounds__(256) ccl_border_kernel(const int16_t* __restrict__ img, int* __restrict__ L, int W,
+                                                         int H, int newVal, int maxDiff)
 {
     int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= W || y >= H) return;
+    const bool right_edge = ((x & (CTX - 1)) == CTX - 1) && x + 1 < W;
+    const bool bottom_edge = ((y & (CTY - 1)) == CTY - 1) && y + 1 < H;
+    if (!right_edge && !bottom_edge) return;
     int i = y * W + x;
     int v = img[i];
     if (v == newVal) return;
-    if (x + 1 < W) {
+    if (right_edge) {
         int u = img[i + 1];
         if (u != newVal && abs(u - v) <= maxDiff) uf_union(L, i, i + 1);
     }
-    if (y + 1 < H) {
+    if (bottom_edge) {
         int u = img[i + W];
         if (u != newVal && abs(u - v) <= maxDiff) uf_union(L, i, i + W);
     }
@@ -126,13 +201,13 @@ __global__ void __launch_bounds__(256) ccl_count_kernel(const int* __restrict__ 
                                                         int* __restrict__ sz, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     int r = -1;
-    if (L[i] >= 0) {
-        r = uf_root(L, i);
-        atomicAdd(&sz[r], 1);
-    }
-    root[i] = r;
+    if (i < n && L[i] >= 0) r = uf_root(L, i);
+    if (i < n) root[i] = r;
+    // warp-aggregated histogram: the lanes that share a root send one atomicAdd (big components would otherwise
+    // serialise hundreds of thousands of atomics on one address)
+    const unsigned peers = __match_any_sync(0xffffffffu, r);
+    if (r >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sz[r], __popc(peers));
 }
 
 __global__ void __launch_bounds__(256) ccl_apply_kernel(int16_t* __restrict__ img, const int* __restrict__ root,
@@ -172,8 +247,8 @@ int launch_filter_speckles(int16_t* img, int W, int H, int newVal, int maxSize, 
     int* sz = scratch + n;
     int* root = scratch + 2 * (size_t)n;
     int nb = (n + 255) / 256;
-    ccl_init_kernel<<<nb, 256, 0, st>>>(img, L, sz, n, newVal);
-    ccl_merge_kernel<<<grid2d(W, H), 256, 0, st>>>(img, L, W, H, newVal, maxDiff);
+    ccl_local_kernel<<<dim3((W + CTX - 1) / CTX, (H + CTY - 1) / CTY), 256, 0, st>>>(img, L, sz, W, H, newVal, maxDiff);
+    ccl_border_kernel<<<grid2d(W, H), 256, 0, st>>>(img, L, W, H, newVal, maxDiff);
     ccl_count_kernel<<<nb, 256, 0, st>>>(L, root, sz, n);
     ccl_apply_kernel<<<nb, 256, 0, st>>>(img, root, sz, n, newVal, maxSize);
     return 4;
