@@ -114,12 +114,15 @@ __device__ __forceinline__ void sm_union(int* L, int a, int b)
     }
 }
 
-// writes L[i] = global index of the tile-local root (or -1 for newVal pixels) and clears sz
+// Stage 1.  Rows first: a warp scans two rows and labels every pixel with the first pixel of its horizontal run
+// (inclusive max-scan of run starts with shuffles), so only run pairs -- not pixels -- need a union in the vertical pass.
+// Writes L[i] = global index of the tile-local root (or -1 for newVal pixels) and clears sz.
 __global__ void __launch_bounds__(256) ccl_local_kernel(const int16_t* __restrict__ img, int* __restrict__ L,
                                                         int* __restrict__ sz, int W, int H, int newVal, int maxDiff)
 {
     __shared__ int16_t v[CTY * CTX];
-    __shared__ int lab[CTY * CTX];
+    __shared__ int16_t rs[CTY * CTX];     // immutable run start (tile index) of every pixel, -1 for newVal
+    __shared__ int lab[CTY * CTX];        // union-find parents over tile indices (only run starts ever get hooked)
     const int x0 = blockIdx.x * CTX, y0 = blockIdx.y * CTY;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -132,23 +135,49 @@ __global__ void __launch_bounds__(256) ccl_local_kernel(const int16_t* __restric
             sz[(size_t)y * W + x] = 0;
         }
         v[idx] = (int16_t)val;
-        lab[idx] = val != newVal ? idx : -1;
+    }
+    __syncthreads();
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int base = (2 * warp + rr) * CTX;
+            const int a0 = v[base + 2 * lane], a1 = v[base + 2 * lane + 1];
+            const int left = __shfl_up_sync(0xffffffffu, a1, 1);
+            const bool val0 = a0 != newVal, val1 = a1 != newVal;
+            const bool conn0 = val0 && lane > 0 && left != newVal && abs(a0 - left) <= maxDiff;
+            const bool conn1 = val1 && val0 && abs(a1 - a0) <= maxDiff;
+            const int s0 = conn0 ? -1 : 2 * lane, s1 = conn1 ? -1 : 2 * lane + 1;
+            int e = max(s0, s1);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, e, d);
+                if (lane >= d) e = max(e, t);
+            }
+            int E = __shfl_up_sync(0xffffffffu, e, 1);
+            if (lane == 0) E = -1;
+            const int st0 = max(E, s0), st1 = s1 >= 0 ? s1 : st0;
+            rs[base + 2 * lane] = (int16_t)(val0 ? base + st0 : -1);
+            rs[base + 2 * lane + 1] = (int16_t)(val1 ? base + st1 : -1);
+            lab[base + 2 * lane] = val0 ? base + st0 : -1;
+            lab[base + 2 * lane + 1] = val1 ? base + st1 : -1;
+        }
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int idx = threadIdx.x + 256 * k;
         const int tx = idx & (CTX - 1), ty = idx >> 6;
-        const int a = v[idx];
-        if (a == newVal) continue;
-        if (tx + 1 < CTX) {
-            const int u = v[idx + 1];
-            if (u != newVal && abs(u - a) <= maxDiff) sm_union(lab, idx, idx + 1);
+        if (ty + 1 >= CTY) continue;
+        const int a = v[idx], u = v[idx + CTX];
+        if (a == newVal || u == newVal || abs(u - a) > maxDiff) continue;
+        // one union per pair of touching runs: only where the pair of runs starts to be connected
+        bool first = tx == 0 || rs[idx] != rs[idx - 1] || rs[idx + CTX] != rs[idx + CTX - 1];
+        if (!first) {
+            const int al = v[idx - 1], ul = v[idx + CTX - 1];
+            first = abs(ul - al) > maxDiff;     // both left pixels are valid here (they are in the same runs)
         }
-        if (ty + 1 < CTY) {
-            const int u = v[idx + CTX];
-            if (u != newVal && abs(u - a) <= maxDiff) sm_union(lab, idx, idx + CTX);
-        }
+        if (first) sm_union(lab, rs[idx], rs[idx + CTX]);
     }
     __syncthreads();
 #pragma unroll
@@ -158,34 +187,38 @@ __global__ void __launch_bounds__(256) ccl_local_kernel(const int16_t* __restric
         const int x = x0 + tx, y = y0 + ty;
         if (x >= W || y >= H) continue;
         int g = -1;
-        if (lab[idx] >= 0) {
-            const int r = sm_find(lab, idx);
+        if (rs[idx] >= 0) {
+            const int r = sm_find(lab, rs[idx]);
             g = (y0 + (r >> 6)) * W + x0 + (r & (CTX - 1));   // raster order is preserved: root index <= own index
         }
         L[(size_t)y * W + x] = g;
     }
 }
 
-// ---- stage 2: unions across tile borders (global union-find) ----------------------------------------------------
+// ---- stage 2: unions across tile borders (global union-find), one thread per border pixel ------------------------
 __global__ void __launch_bounds__(256) ccl_border_kernel(const int16_t* __restrict__ img, int* __restrict__ L, int W,
                                                          int H, int newVal, int maxDiff)
 {
-    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= W || y >= H) return;
-    const bool right_edge = ((x & (CTX - 1)) == CTX - 1) && x + 1 < W;
-    const bool bottom_edge = ((y & (CTY - 1)) == CTY - 1) && y + 1 < H;
-    if (!right_edge && !bottom_edge) return;
-    int i = y * W + x;
-    int v = img[i];
-    if (v == newVal) return;
-    if (right_edge) {
-        int u = img[i + 1];
-        if (u != newVal && abs(u - v) <= maxDiff) uf_union(L, i, i + 1);
+    const int ncx = (W - 1) / CTX;            // tile columns that have a right neighbour
+    const int ncy = (H - 1) / CTY;            // tile rows that have a lower neighbour
+    const long long nR = (long long)ncx * H, total = nR + (long long)ncy * W;
+    long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (t >= total) return;
+    int x, y, j;
+    if (t < nR) {
+        y = (int)(t / ncx);
+        x = ((int)(t - (long long)y * ncx) + 1) * CTX - 1;
+        j = y * W + x + 1;
+    } else {
+        t -= nR;
+        const int ry = (int)(t / W);
+        x = (int)(t - (long long)ry * W);
+        y = (ry + 1) * CTY - 1;
+        j = (y + 1) * W + x;
     }
-    if (bottom_edge) {
-        int u = img[i + W];
-        if (u != newVal && abs(u - v) <= maxDiff) uf_union(L, i, i + W);
-    }
+    const int i = y * W + x;
+    const int a = img[i], u = img[j];
+    if (a != newVal && u != newVal && abs(u - a) <= maxDiff) uf_union(L, i, j);
 }
 
 // read-only root lookup: the forest is final here, and no thread may write L while others still walk it
@@ -197,17 +230,54 @@ __device__ __forceinline__ int uf_root(const int* __restrict__ L, int i)
     return i;
 }
 
-__global__ void __launch_bounds__(256) ccl_count_kernel(const int* __restrict__ L, int* __restrict__ root,
-                                                        int* __restrict__ sz, int n)
+// ---- stage 3: per tile, count pixels per tile-local root in shared memory, resolve each local root's global root
+// once, add the counts to the global histogram and record the global root of every pixel --------------------------
+__global__ void __launch_bounds__(256) ccl_finalize_kernel(const int* __restrict__ L, int* __restrict__ root,
+                                                           int* __restrict__ sz, int W, int H)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int r = -1;
-    if (i < n && L[i] >= 0) r = uf_root(L, i);
-    if (i < n) root[i] = r;
-    // warp-aggregated histogram: the lanes that share a root send one atomicAdd (big components would otherwise
-    // serialise hundreds of thousands of atomics on one address)
-    const unsigned peers = __match_any_sync(0xffffffffu, r);
-    if (r >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sz[r], __popc(peers));
+    __shared__ int cnt[CTY * CTX];
+    __shared__ int groot[CTY * CTX];
+    const int x0 = blockIdx.x * CTX, y0 = blockIdx.y * CTY;
+    int bucket[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cnt[threadIdx.x + 256 * k] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = threadIdx.x + 256 * k;
+        const int tx = idx & (CTX - 1), ty = idx >> 6;
+        const int x = x0 + tx, y = y0 + ty;
+        bucket[k] = -1;
+        if (x < W && y < H) {
+            const int p = L[(size_t)y * W + x];
+            if (p >= 0) {
+                // parent inside this tile (the tile-local root) -> its bucket; otherwise (own root, or a border pixel whose
+                // parent was shortened to another tile by path halving) the pixel is its own bucket
+                const int px = p % W - x0, py = p / W - y0;
+                bucket[k] = ((unsigned)px < (unsigned)CTX && (unsigned)py < (unsigned)CTY) ? py * CTX + px : idx;
+                atomicAdd(&cnt[bucket[k]], 1);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = threadIdx.x + 256 * k;
+        const int c = cnt[idx];
+        if (c > 0) {
+            const int g = uf_root(L, (y0 + (idx >> 6)) * W + x0 + (idx & (CTX - 1)));
+            groot[idx] = g;
+            atomicAdd(&sz[g], c);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = threadIdx.x + 256 * k;
+        const int tx = idx & (CTX - 1), ty = idx >> 6;
+        const int x = x0 + tx, y = y0 + ty;
+        if (x < W && y < H) root[(size_t)y * W + x] = bucket[k] >= 0 ? groot[bucket[k]] : -1;
+    }
 }
 
 __global__ void __launch_bounds__(256) ccl_apply_kernel(int16_t* __restrict__ img, const int* __restrict__ root,
@@ -248,8 +318,11 @@ int launch_filter_speckles(int16_t* img, int W, int H, int newVal, int maxSize, 
     int* root = scratch + 2 * (size_t)n;
     int nb = (n + 255) / 256;
     ccl_local_kernel<<<dim3((W + CTX - 1) / CTX, (H + CTY - 1) / CTY), 256, 0, st>>>(img, L, sz, W, H, newVal, maxDiff);
-    ccl_border_kernel<<<grid2d(W, H), 256, 0, st>>>(img, L, W, H, newVal, maxDiff);
-    ccl_count_kernel<<<nb, 256, 0, st>>>(L, root, sz, n);
+    {
+        const long long nbp = (long long)((W - 1) / CTX) * H + (long long)((H - 1) / CTY) * W;
+        if (nbp > 0) ccl_border_kernel<<<(unsigned)((nbp + 255) / 256), 256, 0, st>>>(img, L, W, H, newVal, maxDiff);
+    }
+    ccl_finalize_kernel<<<dim3((W + CTX - 1) / CTX, (H + CTY - 1) / CTY), 256, 0, st>>>(L, root, sz, W, H);
     ccl_apply_kernel<<<nb, 256, 0, st>>>(img, root, sz, n, newVal, maxSize);
     return 4;
 }
