@@ -20,6 +20,8 @@ namespace b200s {
 
 int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg, int r, int lofs,
                  int XA, int XB, int YA, int YB, int16_t* disp, int16_t* cost, cudaStream_t st);
+int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg, int r, int lofs,
+                 int XA, int XB, int YA, int YB, int16_t* disp, int16_t* cost, cudaStream_t st);
 
 __global__ void fill_s16_kernel(int16_t* p, size_t n, int16_t v)
 {
@@ -596,7 +598,12 @@ int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W
     GenPlanes gp{Lp, Rp, pitch};
     static const int kernel_sel = getenv("B200S_KERNEL") ? atoi(getenv("B200S_KERNEL")) : 4;
     bool ws_done = false;
-    if (fast_ok_base && kernel_sel >= 4) {
+    if (fast_ok_base && kernel_sel >= 7) {
+        int rc = launch_bm_vh(Lp, Rp, pitch, W, H, cfg, g.r, g.lofs, XA, XB, g.roiY0, g.roiY1, disp, cost, st);
+        if (rc < 0) return -1;
+        ws_done = rc == 1;
+    }
+    if (!ws_done && fast_ok_base && kernel_sel >= 4) {
         int rc = launch_bm_ws(Lp, Rp, pitch, W, H, cfg, g.r, g.lofs, XA, XB, g.roiY0, g.roiY1, disp, cost, st);
         if (rc < 0) return -1;
         ws_done = rc == 1;

@@ -1,0 +1,439 @@
+// SAD block matcher v7 for sm_100a: both window sums of cv::StereoBM live in registers.
+//
+// The v4 kernel (bm_ws.cu) keeps the vertical column sums in registers and pushes them through shared memory for the
+// horizontal sliding sum; more than half of its shared-memory wavefronts -- its binding resource -- are that traffic.
+// Here one thread owns 16 adjacent output columns x 4 disparities and keeps the finished window sums S of those 64
+// (pixel, disparity) pairs in 32 registers for the whole band:
+//
+//   per input row   E[e]  = 64 + |L-R|(entering row) - |L-R|(leaving row)       packed bytes, 4 disparities per word,
+//                           for the 16 + 2r window columns of the thread (VABSDIFF4.U8; halo columns are recomputed
+//                           instead of exchanged)
+//                   R_0   = sum of the first 2r+1 E words (byte-pair sums, then widened to u16x2 lanes)
+//                   R_i+1 = R_i +/- widen(128 +/- (E[i+2r+1] - E[i]))                 horizontal sliding, in registers
+//                   S[i] += R_i                                                      vertical sliding, in registers
+// The sign of the delta word alternates with i, so the +128 of its byte lanes cancels every second step instead of
+// costing a subtraction per step: R (and with it S) of the odd columns carries a known bias of 128 per accumulated
+// row, which the W role removes from the handful of values it finally uses (a common offset does not move the argmin).
+//
+// Everything is exact integer arithmetic: the staged bytes are clamped to 2*cap <= 62, so no byte lane of E or of the
+// delta word can wrap, and the u16x2 registers are only ever combined linearly (a register is the integer
+// lo + 65536 * hi, valid whenever the final lanes are inside [0, 65535], which 2*cap*block^2 < 65535 guarantees).
+//
+// Roles (one block per SM, warp-specialised, PTX named barriers, double-buffered shared memory):
+//   stager warps   global rows -> stage[j & 1]  (left bytes pre-broadcast, right row as 4 word-shifted copies)
+//   VH warps       stage -> S registers -> Sbuf[o & 1] (all window sums of the row) + Kbuf[o & 1] (min per 4 disparities)
+//   W warps        Sbuf/Kbuf -> disparity (argmin, uniqueness, texture, sub-pixel), one thread per pixel
+#include "kernels.h"
+#include "bm_common.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace b200s {
+
+struct VhParams {
+    const uint8_t* Lp;
+    const uint8_t* Rp;
+    size_t pitch;
+    int16_t* disp;
+    int16_t* cost;
+    int W, H, nd, minD, r, cap, texThr, uniq, lofs;
+    int X0base, XA, XB, YA, YB;
+    int TW, BH, ncols, ncolsP;       // tile width (16 * NCB), band height, window columns (TW + 2r), padded stride (words)
+    int NCB, G4;                     // column blocks, nd / 4
+    int SWb, KWb, NK16, CSB, RLW;    // Sbuf / Kbuf row strides, LDS.128 per key row
+    int nVw, nWw, nSw;
+    int oStage[2];                   // per buffer: Lb [2][ncolsP] words, then Rc [2][4][CSB] bytes
+    int oTc;                         // [8][ncols] words texture column sums (ring over output rows) + [ncols] running sums
+    int oS[2], oK[2];
+};
+
+namespace vh {
+
+enum { B_FULL_STAGE = 1, B_EMPTY_STAGE = 3, B_FULL_S = 5, B_EMPTY_S = 7 };
+
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n)
+{
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void bar_release(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+constexpr int NC = 16;               // output columns per VH thread
+
+}  // namespace vh
+
+template <int R, int ND>
+__global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
+{
+    using namespace vh;
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int B = 2 * R + 1;
+    constexpr int NE = NC + 2 * R;                 // window columns per VH thread
+    constexpr int NLQ = (NE + 3) / 4;              // LDS.128 per left row
+    constexpr int NWD = (NE + 2) / 4 + 1;          // right-row words a thread needs
+    constexpr int NRQ = (NWD + 3) / 4;             // LDS.128 per right row
+    const int nd = ND > 0 ? ND : P.nd;
+    const int SWb = ND > 0 ? ND * 2 + 16 : P.SWb;
+    const int KWb = ND > 0 ? (((ND / 4 + 3) / 4) * 4 + 4) * 4 : P.KWb;
+    const int NK16 = ND > 0 ? (ND / 4 + 3) / 4 : P.NK16;
+    const int G4 = ND > 0 ? ND / 4 : P.G4;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int NVt = P.nVw * 32, NWt = P.nWw * 32, NSt = P.nSw * 32;
+    const int X0 = P.X0base + blockIdx.x * P.TW;
+    const int yb0 = P.YA + blockIdx.y * P.BH;
+    const int yb1 = min(yb0 + P.BH, P.YB);
+    const int r = R, b = B;
+    const int nIn = yb1 - yb0 + 2 * r;     // input rows consumed
+    const int nOut = yb1 - yb0;            // output rows produced
+    const int y_in0 = yb0 - r;             // image row of input index 0
+
+    // pad keys stay "infinite" for the whole kernel
+    for (int i = tid; i < (P.TW * KWb) / 4; i += blockDim.x) {
+        ((uint32_t*)(smem + P.oK[0]))[i] = 0xFFFFFFFFu;
+        ((uint32_t*)(smem + P.oK[1]))[i] = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+
+    if (warp < P.nVw) {
+        // =============================== VH role ==============================================================
+        const int cb = tid / G4;                            // the planner makes NCB * G4 a whole number of warps
+        const int g4 = tid - cb * G4;
+        const int jj = g4 & 3;
+        const int loffs = 64 * cb;                                                   // left words of this block
+        const int roffs = 2 * P.ncolsP * 4 + jj * P.CSB + (16 * cb + 4 * g4 - 4 * jj);   // right window, entering row
+        const int soffs = (NC * cb) * SWb + 8 * g4;
+        const int koffs = (NC * cb) * KWb + 4 * g4;
+        uint32_t Se[NC], So[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) Se[i] = So[i] = 0;
+
+        for (int j = 0; j < nIn; ++j) {
+            const int sb = j & 1;
+            bar_sync(B_FULL_STAGE + sb, NVt + NSt);
+            uint32_t E[NE];
+            {
+                const uint8_t* st = smem + P.oStage[sb];
+                uint32_t wn[4 * NRQ], wo[4 * NRQ];
+#pragma unroll
+                for (int q = 0; q < NRQ; ++q) {
+                    const uint4 a = *(const uint4*)(st + roffs + 16 * q);
+                    const uint4 o4 = *(const uint4*)(st + roffs + 4 * P.CSB + 16 * q);
+                    wn[4 * q] = a.x; wn[4 * q + 1] = a.y; wn[4 * q + 2] = a.z; wn[4 * q + 3] = a.w;
+                    wo[4 * q] = o4.x; wo[4 * q + 1] = o4.y; wo[4 * q + 2] = o4.z; wo[4 * q + 3] = o4.w;
+                }
+#pragma unroll
+                for (int q = 0; q < NLQ; ++q) {
+                    const uint4 ln4 = *(const uint4*)(st + loffs + 16 * q);
+                    const uint4 lo4 = *(const uint4*)(st + 4 * P.ncolsP + loffs + 16 * q);
+                    const uint32_t ln[4] = {ln4.x, ln4.y, ln4.z, ln4.w};
+                    const uint32_t lo[4] = {lo4.x, lo4.y, lo4.z, lo4.w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int e = 4 * q + c;
+                        if (e < NE) {
+                            const uint32_t rn = c ? __funnelshift_r(wn[q], wn[q + 1], 8 * c) : wn[q];
+                            const uint32_t ro = c ? __funnelshift_r(wo[q], wo[q + 1], 8 * c) : wo[q];
+                            E[e] = __vabsdiffu4(ln[c], rn) + 0x40404040u - __vabsdiffu4(lo[c], ro);   // bytes in [2, 126]
+                        }
+                    }
+                }
+            }
+            bar_release(B_EMPTY_STAGE + sb, NVt + NSt);   // the staged rows are in registers now
+
+            // horizontal window sum of the first pixel: byte-pair sums (<= 252), then widened
+            uint32_t Re, Ro;
+            {
+                uint32_t se = 0, so = 0;
+#pragma unroll
+                for (int m = 0; m < R; ++m) {
+                    const uint32_t p = E[2 * m] + E[2 * m + 1];
+                    se += p & 0x00ff00ffu;
+                    so += __byte_perm(p, 0, 0x4341);
+                }
+                se += E[2 * R] & 0x00ff00ffu;
+                so += __byte_perm(E[2 * R], 0, 0x4341);
+                Re = se - (uint32_t)(64 * B) * 0x00010001u;
+                Ro = so - (uint32_t)(64 * B) * 0x00010001u;
+            }
+            const bool emit = j >= 2 * r;
+            const int cbuf = (j - 2 * r) & 1;
+            if (emit && j - 2 * r >= 2) bar_sync(B_EMPTY_S + cbuf, NVt + NWt);
+            uint8_t* ps = smem + P.oS[cbuf] + soffs;
+            uint8_t* pk = smem + P.oK[cbuf] + koffs;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                Se[i] += Re;
+                So[i] += Ro;
+                if (emit) {
+                    uint32_t m = __vminu2(Se[i], So[i]);
+                    m = __vminu2(m, m << 16);                       // high half: min of the 4 disparities, low half: 0
+                    *(uint2*)(ps + i * SWb) = make_uint2(Se[i], So[i]);
+                    *(uint32_t*)(pk + i * KWb) = m + (uint32_t)g4;
+                }
+                if (i + 1 < NC) {
+                    if (!(i & 1)) {
+                        const uint32_t D = E[i + B] + 0x80808080u - E[i];      // bytes 128 + d in [4, 252]
+                        const uint32_t Do = __byte_perm(D, 0, 0x4341);
+                        Re += D - (Do << 8);                                    // even byte lanes = D & 0x00ff00ff
+                        Ro += Do;
+                    } else {
+                        const uint32_t D = E[i] + 0x80808080u - E[i + B];      // bytes 128 - d
+                        const uint32_t Do = __byte_perm(D, 0, 0x4341);
+                        Re -= D - (Do << 8);
+                        Ro -= Do;
+                    }
+                }
+            }
+            if (emit) bar_arrive(B_FULL_S + cbuf, NVt + NWt);
+        }
+    } else if (warp < P.nVw + P.nWw) {
+        // =============================== W role ===============================================================
+        const int px = tid - NVt;
+        const bool wact = px < P.TW;
+        const int16_t FILTERED = (int16_t)((P.minD - 1) * 16);
+        const int X = X0 + px;
+        const bool wout = wact && X >= P.XA && X < P.XB;
+        for (int o = 0; o < nOut; ++o) {
+            const int cb = o & 1;
+            bar_sync(B_FULL_S + cb, NVt + NWt);
+            if (wact) {
+                uint8_t* krow = smem + P.oK[cb] + px * KWb;
+                uint8_t* srow = smem + P.oS[cb] + px * SWb;
+                // odd columns of a VH thread carry 128 per accumulated input row on every window sum
+                const int bias = (px & 1) ? 128 * (o + 2 * r + 1) : 0;
+                uint32_t best = 0xFFFFFFFFu;
+                if (ND > 0) {
+#pragma unroll
+                    for (int i = 0; i < NK16; ++i) {
+                        const uint4 k4 = *(const uint4*)(krow + 16 * i);
+                        best = min(min(best, k4.x), min(k4.y, min(k4.z, k4.w)));
+                    }
+                } else {
+                    for (int i = 0; i < NK16; ++i) {
+                        const uint4 k4 = *(const uint4*)(krow + 16 * i);
+                        best = min(min(best, k4.x), min(k4.y, min(k4.z, k4.w)));
+                    }
+                }
+                const int minsad_b = (int)(best >> 16), gs = (int)(best & 0xffffu);
+                int mind;
+                {
+                    const uint2 u = *(const uint2*)(srow + 8 * gs);          // u16 order: k, k+2, k+1, k+3
+                    int loc = 3;
+                    if ((int)(u.x >> 16) == minsad_b) loc = 2;
+                    if ((int)(u.y & 0xffffu) == minsad_b) loc = 1;
+                    if ((int)(u.x & 0xffffu) == minsad_b) loc = 0;
+                    mind = 4 * gs + loc;
+                }
+                uint16_t* s16 = (uint16_t*)srow;
+                const int minsad = minsad_b - bias;
+                const int pv = (int)s16[kpos(mind + 1 < nd ? mind + 1 : nd - 2)] - bias;
+                const int nv = (int)s16[kpos(mind > 0 ? mind - 1 : 1)] - bias;
+                bool filtered = false;
+                if (P.uniq > 0) {
+                    const int g0 = max(gs - 1, 0), g2 = min(gs + 1, G4 - 1);
+                    ((uint32_t*)krow)[g0] = 0xFFFFFFFFu;
+                    ((uint32_t*)krow)[gs] = 0xFFFFFFFFu;
+                    ((uint32_t*)krow)[g2] = 0xFFFFFFFFu;
+                    s16[kpos(mind)] = 0xFFFFu;
+                    if (mind > 0) s16[kpos(mind - 1)] = 0xFFFFu;
+                    if (mind + 1 < nd) s16[kpos(mind + 1)] = 0xFFFFu;
+                    uint32_t m2k = 0xFFFFFFFFu;
+                    if (ND > 0) {
+#pragma unroll
+                        for (int i = 0; i < NK16; ++i) {
+                            const uint4 k4 = *(const uint4*)(krow + 16 * i);
+                            m2k = min(min(m2k, k4.x), min(k4.y, min(k4.z, k4.w)));
+                        }
+                    } else {
+                        for (int i = 0; i < NK16; ++i) {
+                            const uint4 k4 = *(const uint4*)(krow + 16 * i);
+                            m2k = min(min(m2k, k4.x), min(k4.y, min(k4.z, k4.w)));
+                        }
+                    }
+                    const uint2 e0 = *(const uint2*)(srow + 8 * g0);
+                    const uint2 e1 = *(const uint2*)(srow + 8 * gs);
+                    const uint2 e2 = *(const uint2*)(srow + 8 * g2);
+                    uint32_t acc = __vimin3_u16x2(e0.x, e0.y, e1.x);
+                    acc = __vimin3_u16x2(acc, e1.y, e2.x);
+                    acc = __vminu2(acc, e2.y);
+                    const int m2 = (int)min(min(acc & 0xffffu, acc >> 16), m2k >> 16) - bias;
+                    const int thr = minsad + (minsad * P.uniq / 100);
+                    filtered = m2 <= thr;
+                }
+                if (wout) {
+                    const int* tc = (const int*)(smem + P.oTc) + (o & 7) * P.ncols + px;
+                    int tsum = 0;
+                    for (int c = 0; c < b; ++c) tsum += tc[c];
+                    int16_t out = FILTERED;
+                    if (tsum >= P.texThr && !filtered) out = subpixel_disp(minsad, mind, pv, nv, nd, P.minD);
+                    const int y = yb0 + o;
+                    P.disp[(size_t)y * P.W + X] = out;
+                    if (P.cost) P.cost[(size_t)y * P.W + X] = (int16_t)minsad;
+                }
+            }
+            bar_release(B_EMPTY_S + cb, NVt + NWt);
+        }
+    } else {
+        // =============================== stager role ===========================================================
+        // stager 0: left rows (pre-broadcast, clamped) + running texture column sums; the others: right rows
+        const int s = warp - (P.nVw + P.nWw);
+        const int lane = tid & 31;
+        const int Xl0 = X0 - r;
+        const int Xr0 = X0 - r - P.lofs;     // multiple of 4 by construction
+        const uint32_t clampw = (uint32_t)(2 * P.cap) * 0x01010101u;
+        int* trun = (int*)(smem + P.oTc) + 8 * P.ncols;    // [ncols] running sums, owned lane-wise by stager 0
+        if (s == 0)
+            for (int c = lane; c < P.ncols; c += 32) trun[c] = 0;
+        for (int j = 0; j < nIn; ++j) {
+            const int sb = j & 1;
+            const int yi = y_in0 + j;
+            const bool has_old = j >= b;
+            if (j >= 2) bar_sync(B_EMPTY_STAGE + sb, NVt + NSt);
+            if (s == 0) {   // with a single stager warp it does both halves
+                const uint8_t* ln = P.Lp + (size_t)yi * P.pitch + Xl0;
+                const uint8_t* lo = P.Lp + (size_t)max(yi - b, 0) * P.pitch + Xl0;
+                uint32_t* sLb = (uint32_t*)(smem + P.oStage[sb]);
+                const bool publish = j >= 2 * r;
+                int* tpub = (int*)(smem + P.oTc) + ((j - 2 * r) & 7) * P.ncols;
+                for (int c = lane; c < P.ncolsP; c += 32) {
+                    const int a = (int)__ldg(ln + c), o2 = has_old ? (int)__ldg(lo + c) : 0;
+                    sLb[c] = (uint32_t)min(a, 2 * P.cap) * 0x01010101u;
+                    sLb[P.ncolsP + c] = (uint32_t)min(o2, 2 * P.cap) * 0x01010101u;
+                    if (c < P.ncols) {
+                        const int t = trun[c] + abs(a - P.cap) - (has_old ? abs(o2 - P.cap) : 0);
+                        trun[c] = t;
+                        if (publish) tpub[c] = t;     // texture column sums of output row j - 2r (ring of 8 rows)
+                    }
+                }
+            }
+            if (s >= 1 || P.nSw == 1) {   // right rows: the words are spread over the remaining stager warps
+                const uint32_t* rn = (const uint32_t*)(P.Rp + (size_t)yi * P.pitch + Xr0);
+                const uint32_t* ro = (const uint32_t*)(P.Rp + (size_t)max(yi - b, 0) * P.pitch + Xr0);
+                uint8_t* sRc = smem + P.oStage[sb] + 2 * P.ncolsP * 4;
+                const int nrw = P.nSw > 1 ? P.nSw - 1 : 1, rw = P.nSw > 1 ? s - 1 : 0;
+#pragma unroll 2
+                for (int wi = rw * 32 + lane; wi < P.RLW; wi += 32 * nrw) {
+                    const uint32_t vn = __vminu4(__ldg(rn + wi), clampw), vo = has_old ? __vminu4(__ldg(ro + wi), clampw) : 0u;
+                    uint8_t* cp = sRc + 4 * wi;
+                    // copy jj holds row[a + 4 jj] at byte a
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+                        if (wi >= jj) {
+                            *(uint32_t*)(cp + jj * P.CSB - 4 * jj) = vn;
+                            *(uint32_t*)(cp + (4 + jj) * P.CSB - 4 * jj) = vo;
+                        }
+                }
+            }
+            bar_arrive(B_FULL_STAGE + sb, NVt + NSt);
+        }
+    }
+}
+
+template <int R, int ND>
+static cudaError_t launch_vh2(const VhParams& P, dim3 grid, int nt, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(bm_vh_kernel<R, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    bm_vh_kernel<R, ND><<<grid, nt, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+template <int R>
+static cudaError_t launch_vh(const VhParams& P, dim3 grid, int nt, size_t smem, cudaStream_t st)
+{
+    if (P.nd == 256) return launch_vh2<R, 256>(P, grid, nt, smem, st);
+    if (P.nd == 128) return launch_vh2<R, 128>(P, grid, nt, smem, st);
+    if (P.nd == 64) return launch_vh2<R, 64>(P, grid, nt, smem, st);
+    return launch_vh2<R, 0>(P, grid, nt, smem, st);
+}
+
+// returns 1 when launched, 0 when this configuration is not handled (caller falls back), < 0 on CUDA errors
+int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg, int r, int lofs,
+                 int XA, int XB, int YA, int YB, int16_t* disp, int16_t* cost, cudaStream_t st)
+{
+    using vh::NC;
+    const int nd = cfg.nd;
+    if (cfg.cap > 31 || r < 2 || r > 10 || (nd & 15)) return 0;   // byte lanes of E need 2*cap <= 62; R is a template parameter
+    const int G4 = nd / 4;
+    static const int max_warps = getenv("B200S_VH_WARPS") ? atoi(getenv("B200S_VH_WARPS")) : 24;
+    static const int stagers_env = getenv("B200S_STAGERS") ? atoi(getenv("B200S_STAGERS")) : 4;
+    static const int n_sm = getenv("B200S_WS_BLOCKS") ? atoi(getenv("B200S_WS_BLOCKS")) : 148;
+    static const int ncb_env = getenv("B200S_VH_NCB") ? atoi(getenv("B200S_VH_NCB")) : 0;
+    const size_t smem_max = 227 * 1024 - 1024;
+    const int X0base = XA - ((XA - r - lofs) & 3);
+    const int need = XB - X0base;
+    const int rows = YB - YA;
+    VhParams P, best;
+    size_t smem = 0;
+    int nt = 0, best_bands = 1;
+    bool ok = false;
+    double best_cost = 1e300;
+    for (int NCB = std::min(32, (need + NC - 1) / NC); NCB >= 1; --NCB) {
+        if (ncb_env > 0 && NCB != ncb_env) continue;
+        const int TW = NC * NCB;
+        const int nVw = (NCB * G4 + 31) / 32, nWw = (TW + 31) / 32;
+        int nSw = std::max(1, std::min(stagers_env, max_warps - (nVw + nWw)));
+        if (nVw + nWw + nSw > max_warps) continue;
+        if ((NCB * G4) & 31) continue;                       // whole VH warps only
+        if (nSw < 2 && NCB > 1) continue;
+        const int ncols = TW + 2 * r;
+        P.ncolsP = ((ncols + 3) / 4) * 4 + 4;               // the VH threads read whole 16-byte groups of left words
+        P.SWb = nd * 2 + 16; P.NK16 = (G4 + 3) / 4; P.KWb = (P.NK16 * 4 + 4) * 4;
+        P.RLW = (std::max(ncols, TW + 12) + nd) / 4 + 4;    // right-row words: window bytes up to TW + nd + 4 * NRQ * 4
+        int units = (4 * P.RLW + 15) / 16;
+        while ((units & 3) != 2) ++units;
+        P.CSB = units * 16;
+        size_t o = 0;
+        for (int s2 = 0; s2 < 2; ++s2) { P.oStage[s2] = (int)o; o += 2 * (size_t)P.ncolsP * 4 + 8 * (size_t)P.CSB; o = (o + 15) & ~(size_t)15; }
+        P.oTc = (int)o; o += 9 * (size_t)ncols * 4; o = (o + 15) & ~(size_t)15;
+        for (int s2 = 0; s2 < 2; ++s2) { P.oK[s2] = (int)o; o += (size_t)TW * P.KWb; }
+        for (int s2 = 0; s2 < 2; ++s2) { P.oS[s2] = (int)o; o += (size_t)TW * P.SWb; }
+        if (o > smem_max) continue;
+        P.TW = TW; P.ncols = ncols; P.NCB = NCB; P.G4 = G4;
+        P.nVw = nVw; P.nWw = nWw; P.nSw = nSw;
+        const int tilesX = (need + TW - 1) / TW;
+        const int max_bands = std::max(1, rows / (2 * r + 4));
+        for (int bands = 1; bands <= max_bands; ++bands) {
+            const int BH = (rows + bands - 1) / bands;
+            if (128 * (BH + 2 * r + 1) + 2 * cfg.cap * (2 * r + 1) * (2 * r + 1) > 65535) continue;   // bias of the odd columns
+            const int nb = tilesX * ((rows + BH - 1) / BH);
+            const int waves = (nb + n_sm - 1) / n_sm;
+            // per-row time of a block ~ VH warps (all SMSPs share them) plus a fixed hand-over cost
+            const double cost = (double)waves * (BH + 2 * r + 6) * (nVw + 3.0);
+            if (cost < best_cost) {
+                best_cost = cost; best = P; best_bands = bands; smem = o;
+                nt = 32 * (nVw + nWw + nSw);
+                ok = true;
+            }
+        }
+    }
+    if (!ok || nt > 768) return 0;
+    P = best;
+    P.Lp = Lp; P.Rp = Rp; P.pitch = pitch; P.disp = disp; P.cost = cost;
+    P.W = W; P.H = H; P.nd = nd; P.minD = cfg.minD; P.r = r; P.cap = cfg.cap;
+    P.texThr = cfg.textureThreshold; P.uniq = cfg.uniquenessRatio; P.lofs = lofs;
+    P.X0base = X0base; P.XA = XA; P.XB = XB; P.YA = YA; P.YB = YB;
+    const int tilesX = (need + P.TW - 1) / P.TW;
+    P.BH = (rows + best_bands - 1) / best_bands;
+    dim3 grid(tilesX, (rows + P.BH - 1) / P.BH);
+    cudaError_t e;
+    switch (r) {
+    case 2: e = launch_vh<2>(P, grid, nt, smem, st); break;
+    case 3: e = launch_vh<3>(P, grid, nt, smem, st); break;
+    case 4: e = launch_vh<4>(P, grid, nt, smem, st); break;
+    case 5: e = launch_vh<5>(P, grid, nt, smem, st); break;
+    case 6: e = launch_vh<6>(P, grid, nt, smem, st); break;
+    case 7: e = launch_vh<7>(P, grid, nt, smem, st); break;
+    case 8: e = launch_vh<8>(P, grid, nt, smem, st); break;
+    case 9: e = launch_vh<9>(P, grid, nt, smem, st); break;
+    case 10: e = launch_vh<10>(P, grid, nt, smem, st); break;
+    default: return 0;
+    }
+    return e == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace b200s
