@@ -46,19 +46,36 @@ struct VhParams {
     int oStage[2];                   // per buffer: Lb [2][ncolsP] words, then Rc [2][4][CSB] bytes
     int oTc;                         // [8][ncols] words texture column sums (ring over output rows) + [ncols] running sums
     int oS[2], oK[2];
+    int oMbar;                       // 8 mbarriers
 };
 
 namespace vh {
 
-enum { B_FULL_STAGE = 1, B_EMPTY_STAGE = 3, B_FULL_S = 5, B_EMPTY_S = 7 };
+// Hand-over between the roles: shared-memory mbarriers, one full/empty pair per buffer.  Unlike a named barrier
+// (bar.sync makes every consumer wait for every other consumer), a consumer only waits for the producers, so the VH
+// warps drift apart by up to one row and their ALU-heavy and IMAD-heavy phases overlap on the two integer pipes.
+enum { MB_FULL_STAGE = 0, MB_EMPTY_STAGE = 2, MB_FULL_S = 4, MB_EMPTY_S = 6, MB_COUNT = 8 };
 
-__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id, int n)
+__device__ __forceinline__ void mbar_init(uint32_t a, int count)
 {
-    asm volatile("fence.acq_rel.cta;" ::: "memory");
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
 }
-__device__ __forceinline__ void bar_release(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t a)
+{
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MB_WAIT:\n"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MB_DONE;\n"
+        "bra MB_WAIT;\n"
+        "MB_DONE:\n"
+        "}" ::"r"(a), "r"(parity) : "memory");
+}
 
 constexpr int NC = 16;               // output columns per VH thread
 
@@ -96,6 +113,16 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
         ((uint32_t*)(smem + P.oK[0]))[i] = 0xFFFFFFFFu;
         ((uint32_t*)(smem + P.oK[1]))[i] = 0xFFFFFFFFu;
     }
+    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(smem + P.oMbar);
+    if (tid == 0) {
+        for (int s2 = 0; s2 < 2; ++s2) {
+            mbar_init(mb + 8 * (MB_FULL_STAGE + s2), NSt);
+            mbar_init(mb + 8 * (MB_EMPTY_STAGE + s2), NVt);
+            mbar_init(mb + 8 * (MB_FULL_S + s2), NVt);
+            mbar_init(mb + 8 * (MB_EMPTY_S + s2), NWt);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
     if (warp < P.nVw) {
@@ -113,7 +140,7 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
 
         for (int j = 0; j < nIn; ++j) {
             const int sb = j & 1;
-            bar_sync(B_FULL_STAGE + sb, NVt + NSt);
+            mbar_wait(mb + 8 * (MB_FULL_STAGE + sb), (j >> 1) & 1);
             uint32_t E[NE];
             {
                 const uint8_t* st = smem + P.oStage[sb];
@@ -142,7 +169,7 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
                     }
                 }
             }
-            bar_release(B_EMPTY_STAGE + sb, NVt + NSt);   // the staged rows are in registers now
+            mbar_arrive(mb + 8 * (MB_EMPTY_STAGE + sb));   // the staged rows are in registers now
 
             // horizontal window sum of the first pixel: byte-pair sums (<= 252), then widened
             uint32_t Re, Ro;
@@ -161,7 +188,7 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
             }
             const bool emit = j >= 2 * r;
             const int cbuf = (j - 2 * r) & 1;
-            if (emit && j - 2 * r >= 2) bar_sync(B_EMPTY_S + cbuf, NVt + NWt);
+            if (emit) mbar_wait(mb + 8 * (MB_EMPTY_S + cbuf), (((j - 2 * r) >> 1) & 1) ^ 1);
             uint8_t* ps = smem + P.oS[cbuf] + soffs;
             uint8_t* pk = smem + P.oK[cbuf] + koffs;
 #pragma unroll
@@ -188,7 +215,7 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
                     }
                 }
             }
-            if (emit) bar_arrive(B_FULL_S + cbuf, NVt + NWt);
+            if (emit) mbar_arrive(mb + 8 * (MB_FULL_S + cbuf));
         }
     } else if (warp < P.nVw + P.nWw) {
         // =============================== W role ===============================================================
@@ -199,7 +226,7 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
         const bool wout = wact && X >= P.XA && X < P.XB;
         for (int o = 0; o < nOut; ++o) {
             const int cb = o & 1;
-            bar_sync(B_FULL_S + cb, NVt + NWt);
+            mbar_wait(mb + 8 * (MB_FULL_S + cb), (o >> 1) & 1);
             if (wact) {
                 uint8_t* krow = smem + P.oK[cb] + px * KWb;
                 uint8_t* srow = smem + P.oS[cb] + px * SWb;
@@ -275,7 +302,7 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
                     if (P.cost) P.cost[(size_t)y * P.W + X] = (int16_t)minsad;
                 }
             }
-            bar_release(B_EMPTY_S + cb, NVt + NWt);
+            mbar_arrive(mb + 8 * (MB_EMPTY_S + cb));
         }
     } else {
         // =============================== stager role ===========================================================
@@ -292,7 +319,7 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
             const int sb = j & 1;
             const int yi = y_in0 + j;
             const bool has_old = j >= b;
-            if (j >= 2) bar_sync(B_EMPTY_STAGE + sb, NVt + NSt);
+            mbar_wait(mb + 8 * (MB_EMPTY_STAGE + sb), ((j >> 1) & 1) ^ 1);
             if (s == 0) {   // with a single stager warp it does both halves
                 const uint8_t* ln = P.Lp + (size_t)yi * P.pitch + Xl0;
                 const uint8_t* lo = P.Lp + (size_t)max(yi - b, 0) * P.pitch + Xl0;
@@ -328,7 +355,7 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
                         }
                 }
             }
-            bar_arrive(B_FULL_STAGE + sb, NVt + NSt);
+            mbar_arrive(mb + 8 * (MB_FULL_STAGE + sb));
         }
     }
 }
@@ -392,6 +419,7 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
         P.oTc = (int)o; o += 9 * (size_t)ncols * 4; o = (o + 15) & ~(size_t)15;
         for (int s2 = 0; s2 < 2; ++s2) { P.oK[s2] = (int)o; o += (size_t)TW * P.KWb; }
         for (int s2 = 0; s2 < 2; ++s2) { P.oS[s2] = (int)o; o += (size_t)TW * P.SWb; }
+        P.oMbar = (int)o; o += 8 * vh::MB_COUNT;
         if (o > smem_max) continue;
         P.TW = TW; P.ncols = ncols; P.NCB = NCB; P.G4 = G4;
         P.nVw = nVw; P.nWw = nWw; P.nSw = nSw;
