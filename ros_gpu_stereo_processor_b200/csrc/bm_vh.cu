@@ -306,56 +306,112 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
         }
     } else {
         // =============================== stager role ===========================================================
-        // stager 0: left rows (pre-broadcast, clamped) + running texture column sums; the others: right rows
+        // stager 0: left rows (pre-broadcast, clamped) + running texture column sums; the others: right rows.
+        // The global loads of row j + 1 are issued before the wait for the stage buffer of row j, so their latency
+        // never sits on the hand-over path (the planner keeps ncolsP <= 32 * MAXL and RLW <= 32 * MAXR * (nSw - 1)).
+        constexpr int MAXL = 6, MAXR = 4;
         const int s = warp - (P.nVw + P.nWw);
         const int lane = tid & 31;
         const int Xl0 = X0 - r;
         const int Xr0 = X0 - r - P.lofs;     // multiple of 4 by construction
-        const uint32_t clampw = (uint32_t)(2 * P.cap) * 0x01010101u;
-        int* trun = (int*)(smem + P.oTc) + 8 * P.ncols;    // [ncols] running sums, owned lane-wise by stager 0
-        if (s == 0)
+        if (s == 0) {
+            int* trun = (int*)(smem + P.oTc) + 8 * P.ncols;    // [ncols] running sums, owned lane-wise
             for (int c = lane; c < P.ncols; c += 32) trun[c] = 0;
-        for (int j = 0; j < nIn; ++j) {
-            const int sb = j & 1;
-            const int yi = y_in0 + j;
-            const bool has_old = j >= b;
-            mbar_wait(mb + 8 * (MB_EMPTY_STAGE + sb), ((j >> 1) & 1) ^ 1);
-            if (s == 0) {   // with a single stager warp it does both halves
-                const uint8_t* ln = P.Lp + (size_t)yi * P.pitch + Xl0;
-                const uint8_t* lo = P.Lp + (size_t)max(yi - b, 0) * P.pitch + Xl0;
-                uint32_t* sLb = (uint32_t*)(smem + P.oStage[sb]);
-                const bool publish = j >= 2 * r;
-                int* tpub = (int*)(smem + P.oTc) + ((j - 2 * r) & 7) * P.ncols;
-                for (int c = lane; c < P.ncolsP; c += 32) {
-                    const int a = (int)__ldg(ln + c), o2 = has_old ? (int)__ldg(lo + c) : 0;
-                    sLb[c] = (uint32_t)min(a, 2 * P.cap) * 0x01010101u;
-                    sLb[P.ncolsP + c] = (uint32_t)min(o2, 2 * P.cap) * 0x01010101u;
-                    if (c < P.ncols) {
-                        const int t = trun[c] + abs(a - P.cap) - (has_old ? abs(o2 - P.cap) : 0);
-                        trun[c] = t;
-                        if (publish) tpub[c] = t;     // texture column sums of output row j - 2r (ring of 8 rows)
+            int an[MAXL], ao[MAXL];
+#pragma unroll
+            for (int m = 0; m < MAXL; ++m) {
+                const int c = lane + 32 * m;
+                an[m] = c < P.ncolsP ? (int)__ldg(P.Lp + (size_t)y_in0 * P.pitch + Xl0 + c) : 0;
+                ao[m] = 0;
+            }
+            for (int j = 0; j < nIn; ++j) {
+                const int sb = j & 1;
+                int cn[MAXL], co[MAXL];
+#pragma unroll
+                for (int m = 0; m < MAXL; ++m) { cn[m] = an[m]; co[m] = ao[m]; }
+                if (j + 1 < nIn) {
+                    const int yi = y_in0 + j + 1;
+                    const bool has_old = j + 1 >= b;
+                    const uint8_t* ln = P.Lp + (size_t)yi * P.pitch + Xl0;
+                    const uint8_t* lo = P.Lp + (size_t)max(yi - b, 0) * P.pitch + Xl0;
+#pragma unroll
+                    for (int m = 0; m < MAXL; ++m) {
+                        const int c = lane + 32 * m;
+                        if (c < P.ncolsP) {
+                            an[m] = (int)__ldg(ln + c);
+                            ao[m] = has_old ? (int)__ldg(lo + c) : 0;
+                        }
                     }
                 }
-            }
-            if (s >= 1 || P.nSw == 1) {   // right rows: the words are spread over the remaining stager warps
-                const uint32_t* rn = (const uint32_t*)(P.Rp + (size_t)yi * P.pitch + Xr0);
-                const uint32_t* ro = (const uint32_t*)(P.Rp + (size_t)max(yi - b, 0) * P.pitch + Xr0);
-                uint8_t* sRc = smem + P.oStage[sb] + 2 * P.ncolsP * 4;
-                const int nrw = P.nSw > 1 ? P.nSw - 1 : 1, rw = P.nSw > 1 ? s - 1 : 0;
-#pragma unroll 2
-                for (int wi = rw * 32 + lane; wi < P.RLW; wi += 32 * nrw) {
-                    const uint32_t vn = __vminu4(__ldg(rn + wi), clampw), vo = has_old ? __vminu4(__ldg(ro + wi), clampw) : 0u;
-                    uint8_t* cp = sRc + 4 * wi;
-                    // copy jj holds row[a + 4 jj] at byte a
+                mbar_wait(mb + 8 * (MB_EMPTY_STAGE + sb), ((j >> 1) & 1) ^ 1);
+                uint32_t* sLb = (uint32_t*)(smem + P.oStage[sb]);
+                const bool publish = j >= 2 * r;
+                const bool has_old = j >= b;
+                int* tpub = (int*)(smem + P.oTc) + ((j - 2 * r) & 7) * P.ncols;
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj)
-                        if (wi >= jj) {
-                            *(uint32_t*)(cp + jj * P.CSB - 4 * jj) = vn;
-                            *(uint32_t*)(cp + (4 + jj) * P.CSB - 4 * jj) = vo;
+                for (int m = 0; m < MAXL; ++m) {
+                    const int c = lane + 32 * m;
+                    if (c < P.ncolsP) {
+                        sLb[c] = (uint32_t)min(cn[m], 2 * P.cap) * 0x01010101u;
+                        sLb[P.ncolsP + c] = (uint32_t)min(co[m], 2 * P.cap) * 0x01010101u;
+                        if (c < P.ncols) {
+                            const int t = trun[c] + abs(cn[m] - P.cap) - (has_old ? abs(co[m] - P.cap) : 0);
+                            trun[c] = t;
+                            if (publish) tpub[c] = t;     // texture column sums of output row j - 2r (ring of 8 rows)
                         }
+                    }
                 }
+                mbar_arrive(mb + 8 * (MB_FULL_STAGE + sb));
             }
-            mbar_arrive(mb + 8 * (MB_FULL_STAGE + sb));
+        } else {
+            const uint32_t clampw = (uint32_t)(2 * P.cap) * 0x01010101u;
+            const int nrw = P.nSw - 1, rw = s - 1;
+            const int w0 = rw * 32 + lane, wstep = 32 * nrw;
+            uint32_t vn[MAXR], vo[MAXR];
+#pragma unroll
+            for (int m = 0; m < MAXR; ++m) {
+                const int wi = w0 + wstep * m;
+                vn[m] = wi < P.RLW ? __ldg((const uint32_t*)(P.Rp + (size_t)y_in0 * P.pitch + Xr0) + wi) : 0u;
+                vo[m] = 0u;
+            }
+            for (int j = 0; j < nIn; ++j) {
+                const int sb = j & 1;
+                uint32_t cn[MAXR], co[MAXR];
+#pragma unroll
+                for (int m = 0; m < MAXR; ++m) { cn[m] = vn[m]; co[m] = vo[m]; }
+                if (j + 1 < nIn) {
+                    const int yi = y_in0 + j + 1;
+                    const bool has_old = j + 1 >= b;
+                    const uint32_t* rn = (const uint32_t*)(P.Rp + (size_t)yi * P.pitch + Xr0);
+                    const uint32_t* ro = (const uint32_t*)(P.Rp + (size_t)max(yi - b, 0) * P.pitch + Xr0);
+#pragma unroll
+                    for (int m = 0; m < MAXR; ++m) {
+                        const int wi = w0 + wstep * m;
+                        if (wi < P.RLW) {
+                            vn[m] = __ldg(rn + wi);
+                            vo[m] = has_old ? __ldg(ro + wi) : 0u;
+                        }
+                    }
+                }
+                mbar_wait(mb + 8 * (MB_EMPTY_STAGE + sb), ((j >> 1) & 1) ^ 1);
+                uint8_t* sRc = smem + P.oStage[sb] + 2 * P.ncolsP * 4;
+#pragma unroll
+                for (int m = 0; m < MAXR; ++m) {
+                    const int wi = w0 + wstep * m;
+                    if (wi < P.RLW) {
+                        const uint32_t a = __vminu4(cn[m], clampw), o2 = __vminu4(co[m], clampw);
+                        uint8_t* cp = sRc + 4 * wi;
+                        // copy jj holds row[a + 4 jj] at byte a
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (wi >= jj) {
+                                *(uint32_t*)(cp + jj * P.CSB - 4 * jj) = a;
+                                *(uint32_t*)(cp + (4 + jj) * P.CSB - 4 * jj) = o2;
+                            }
+                    }
+                }
+                mbar_arrive(mb + 8 * (MB_FULL_STAGE + sb));
+            }
         }
     }
 }
@@ -387,7 +443,7 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
     if (cfg.cap > 31 || r < 2 || r > 10 || (nd & 15)) return 0;   // byte lanes of E need 2*cap <= 62; R is a template parameter
     const int G4 = nd / 4;
     static const int max_warps = getenv("B200S_VH_WARPS") ? atoi(getenv("B200S_VH_WARPS")) : 24;
-    static const int stagers_env = getenv("B200S_STAGERS") ? atoi(getenv("B200S_STAGERS")) : 4;
+    static const int stagers_env = getenv("B200S_STAGERS") ? atoi(getenv("B200S_STAGERS")) : 2;
     static const int n_sm = getenv("B200S_WS_BLOCKS") ? atoi(getenv("B200S_WS_BLOCKS")) : 148;
     static const int ncb_env = getenv("B200S_VH_NCB") ? atoi(getenv("B200S_VH_NCB")) : 0;
     const size_t smem_max = 227 * 1024 - 1024;
@@ -403,14 +459,14 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
         if (ncb_env > 0 && NCB != ncb_env) continue;
         const int TW = NC * NCB;
         const int nVw = (NCB * G4 + 31) / 32, nWw = (TW + 31) / 32;
-        int nSw = std::max(1, std::min(stagers_env, max_warps - (nVw + nWw)));
-        if (nVw + nWw + nSw > max_warps) continue;
+        int nSw = std::min(stagers_env, max_warps - (nVw + nWw));
+        if (nSw < 2) continue;                               // one warp for the left rows, the others share the right rows
         if ((NCB * G4) & 31) continue;                       // whole VH warps only
-        if (nSw < 2 && NCB > 1) continue;
         const int ncols = TW + 2 * r;
         P.ncolsP = ((ncols + 3) / 4) * 4 + 4;               // the VH threads read whole 16-byte groups of left words
         P.SWb = nd * 2 + 16; P.NK16 = (G4 + 3) / 4; P.KWb = (P.NK16 * 4 + 4) * 4;
         P.RLW = (std::max(ncols, TW + 12) + nd) / 4 + 4;    // right-row words: window bytes up to TW + nd + 4 * NRQ * 4
+        if (P.ncolsP > 32 * 6 || P.RLW > 32 * 4 * (nSw - 1)) continue;   // register-prefetch limits of the stagers (MAXL, MAXR)
         int units = (4 * P.RLW + 15) / 16;
         while ((units & 3) != 2) ++units;
         P.CSB = units * 16;
