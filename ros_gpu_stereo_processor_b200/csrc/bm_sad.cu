@@ -596,7 +596,7 @@ int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W
         }
     }
     GenPlanes gp{Lp, Rp, pitch};
-    static const int kernel_sel = getenv("B200S_KERNEL") ? atoi(getenv("B200S_KERNEL")) : 4;
+    static const int kernel_sel = getenv("B200S_KERNEL") ? atoi(getenv("B200S_KERNEL")) : 7;
     bool ws_done = false;
     if (fast_ok_base && kernel_sel >= 7) {
         int rc = launch_bm_vh(Lp, Rp, pitch, W, H, cfg, g.r, g.lofs, XA, XB, g.roiY0, g.roiY1, disp, cost, st);

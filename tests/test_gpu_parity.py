@@ -359,10 +359,12 @@ def test_cpp_facade_chain(tmp_path):
 
 
 # ---- the fallback matcher kernels stay bit-exact too ------------------------------------------------------------
-@pytest.mark.parametrize("env", [{"B200S_KERNEL": "3"}, {"B200S_FORCE_GENERIC": "1"}, {"B200S_RING": "1"}])
+@pytest.mark.parametrize("env", [{"B200S_KERNEL": "3"}, {"B200S_KERNEL": "4"}, {"B200S_FORCE_GENERIC": "1"},
+                                 {"B200S_KERNEL": "4", "B200S_RING": "1"}, {"B200S_VH_NCB": "1"}, {"B200S_VH_NCB": "3", "B200S_STAGERS": "4"}])
 def test_fallback_matcher_kernels(env, tmp_path):
-    """bm_fast_kernel (non-specialised), the generic int32 path and the register-ring H variant are selected by
-    environment switches read once per process, so each runs in its own interpreter."""
+    """bm_fast_kernel (non-specialised), bm_ws_kernel (v4) with and without the register-ring H variant, the generic
+    int32 path and narrow bm_vh tiles are selected by environment switches read once per process, so each runs in
+    its own interpreter."""
     import os
     import subprocess
     import sys
@@ -409,6 +411,33 @@ def test_disparity_ragged_shapes(proc, case):
     W, H, kw = case
     p = O.BMParams(**kw)
     L, R = synth.synth_pair(W, H, max(p.numDisparities, 16), seed=W * 7 + H)
+    _set(proc, p)
+    got = proc.computeDisparityBare(L, R)
+    want = O.stereobm_compute(L, R, p)
+    assert np.array_equal(got, want), _describe(got, want)
+
+
+# ---- bm_vh_kernel: every window radius the kernel is instantiated for, several disparity counts and caps -----------
+VH_CASES = [(b, nd, cap) for b in (5, 7, 9, 11, 13, 15, 17, 19, 21) for nd, cap in ((64, 31), (256, 15))] + [
+    (11, 16, 31), (11, 48, 1), (15, 128, 31), (21, 96, 31), (9, 176, 20), (23, 64, 31), (11, 64, 32)]   # last two: v4 fallback
+
+
+@pytest.mark.parametrize("case", VH_CASES)
+def test_disparity_vh_kernel_instantiations(proc, case):
+    b, nd, cap = case
+    p = O.BMParams(numDisparities=nd, blockSize=b, preFilterCap=cap, textureThreshold=3)
+    W, H = nd + 420, 150 + 2 * b          # several tiles and bands, ragged right edge
+    L, R = synth.synth_pair(W, H, max(nd, 16), seed=b * 1000 + nd)
+    _set(proc, p)
+    got = proc.computeDisparityBare(L, R)
+    want = O.stereobm_compute(L, R, p)
+    assert np.array_equal(got, want), _describe(got, want)
+
+
+def test_disparity_tall_band_bias_limit(proc):
+    """bm_vh keeps 128 per accumulated row on the odd columns' sums: a tall, narrow image forces long bands."""
+    p = O.BMParams(numDisparities=16, blockSize=21, preFilterCap=31)
+    L, R = synth.synth_pair(120, 1500, 16, seed=99)
     _set(proc, p)
     got = proc.computeDisparityBare(L, R)
     want = O.stereobm_compute(L, R, p)
