@@ -5,7 +5,7 @@
 // Here one thread owns 16 adjacent output columns x 4 disparities and keeps the finished window sums S of those 64
 // (pixel, disparity) pairs in 32 registers for the whole band:
 //
-//   per input row   E[e]  = 64 + |L-R|(entering row) - |L-R|(leaving row)       packed bytes, 4 disparities per word,
+//   per input row   E[e]  = |L-R|(entering row) - |L-R|(leaving row)            packed bytes, 4 disparities per word,
 //                           for the 16 + 2r window columns of the thread (VABSDIFF4.U8; halo columns are recomputed
 //                           instead of exchanged)
 //                   R_0   = sum of the first 2r+1 E words (byte-pair sums, then widened to u16x2 lanes)
@@ -15,8 +15,8 @@
 // costing a subtraction per step: R (and with it S) of the odd columns carries a known bias of 128 per accumulated
 // row, which the W role removes from the handful of values it finally uses (a common offset does not move the argmin).
 //
-// Everything is exact integer arithmetic: the staged bytes are clamped to 2*cap <= 62, so no byte lane of E or of the
-// delta word can wrap, and the u16x2 registers are only ever combined linearly (a register is the integer
+// Everything is exact integer arithmetic: the staged bytes are clamped to 2*cap <= 62, so no byte lane of a biased
+// pair sum or delta word can wrap, and the u16x2 registers are only ever combined linearly (a register is the integer
 // lo + 65536 * hi, valid whenever the final lanes are inside [0, 65535], which 2*cap*block^2 < 65535 guarantees).
 //
 // Roles (one block per SM, warp-specialised, PTX named barriers, double-buffered shared memory):
@@ -164,7 +164,9 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
                         if (e < NE) {
                             const uint32_t rn = c ? __funnelshift_r(wn[q], wn[q + 1], 8 * c) : wn[q];
                             const uint32_t ro = c ? __funnelshift_r(wo[q], wo[q + 1], 8 * c) : wo[q];
-                            E[e] = __vabsdiffu4(ln[c], rn) + 0x40404040u - __vabsdiffu4(lo[c], ro);   // bytes in [2, 126]
+                            // E = |L-R|(entering) - |L-R|(leaving) as one 32-bit integer: byte lanes in [-62, 62] with
+                            // borrows between them; every use below adds a constant that makes all four lanes positive
+                            E[e] = __vabsdiffu4(ln[c], rn) - __vabsdiffu4(lo[c], ro);
                         }
                     }
                 }
@@ -177,14 +179,15 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
                 uint32_t se = 0, so = 0;
 #pragma unroll
                 for (int m = 0; m < R; ++m) {
-                    const uint32_t p = E[2 * m] + E[2 * m + 1];
+                    const uint32_t p = E[2 * m] + E[2 * m + 1] + 0x80808080u;     // bytes 128 + pair in [4, 252]
                     se += p & 0x00ff00ffu;
                     so += __byte_perm(p, 0, 0x4341);
                 }
-                se += E[2 * R] & 0x00ff00ffu;
-                so += __byte_perm(E[2 * R], 0, 0x4341);
-                Re = se - (uint32_t)(64 * B) * 0x00010001u;
-                Ro = so - (uint32_t)(64 * B) * 0x00010001u;
+                const uint32_t pl = E[2 * R] + 0x80808080u;
+                se += pl & 0x00ff00ffu;
+                so += __byte_perm(pl, 0, 0x4341);
+                Re = se - (uint32_t)(128 * (R + 1)) * 0x00010001u;
+                Ro = so - (uint32_t)(128 * (R + 1)) * 0x00010001u;
             }
             const bool emit = j >= 2 * r;
             const int cbuf = (j - 2 * r) & 1;
