@@ -27,6 +27,7 @@
 #include "bm_common.cuh"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 namespace b200s {
@@ -424,6 +425,9 @@ static cudaError_t launch_vh2(const VhParams& P, dim3 grid, int nt, size_t smem,
 {
     cudaError_t e = cudaFuncSetAttribute(bm_vh_kernel<R, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    // small tiles rely on several blocks per SM: ask for the whole shared-memory carve-out (no L1 use in this kernel)
+    e = cudaFuncSetAttribute(bm_vh_kernel<R, ND>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     bm_vh_kernel<R, ND><<<grid, nt, smem, st>>>(P);
     return cudaGetLastError();
 }
@@ -449,6 +453,8 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
     static const int stagers_env = getenv("B200S_STAGERS") ? atoi(getenv("B200S_STAGERS")) : 2;
     static const int n_sm = getenv("B200S_WS_BLOCKS") ? atoi(getenv("B200S_WS_BLOCKS")) : 148;
     static const int ncb_env = getenv("B200S_VH_NCB") ? atoi(getenv("B200S_VH_NCB")) : 0;
+    static const int bands_env = getenv("B200S_VH_BANDS") ? atoi(getenv("B200S_VH_BANDS")) : 0;
+    static const int verbose = getenv("B200S_VH_VERBOSE") ? atoi(getenv("B200S_VH_VERBOSE")) : 0;
     const size_t smem_max = 227 * 1024 - 1024;
     const int X0base = XA - ((XA - r - lofs) & 3);
     const int need = XB - X0base;
@@ -484,16 +490,25 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
         P.nVw = nVw; P.nWw = nWw; P.nSw = nSw;
         const int tilesX = (need + TW - 1) / TW;
         const int max_bands = std::max(1, rows / (2 * r + 4));
+        // Blocks that fit an SM together (80 registers per thread, shared memory incl. the 1 KiB system reservation).
+        const int nthr = 32 * (nVw + nWw + nSw);
+        const int occ = std::max(1, std::min(std::min(65536 / (80 * nthr), (int)((228 * 1024) / (o + 1024))), 2048 / nthr));
         for (int bands = 1; bands <= max_bands; ++bands) {
+            if (bands_env > 0 && bands != std::min(bands_env, max_bands)) continue;
             const int BH = (rows + bands - 1) / bands;
             if (128 * (BH + 2 * r + 1) + 2 * cfg.cap * (2 * r + 1) * (2 * r + 1) > 65535) continue;   // bias of the odd columns
             const int nb = tilesX * ((rows + BH - 1) / BH);
-            const int waves = (nb + n_sm - 1) / n_sm;
-            // per-row time of a block ~ VH warps (all SMSPs share them) plus a fixed hand-over cost
-            const double cost = (double)waves * (BH + 2 * r + 6) * (nVw + 3.0);
+            const int per_sm = (nb + n_sm - 1) / n_sm;
+            const int conc = std::min(occ, per_sm), waves = (per_sm + occ - 1) / occ;
+            // Measured on B200 (tools/sweep_vh.sh, profiles/r01_v7_planner_sweep.md): a block row costs about
+            // 0.35 + 0.33 * m us, m = VH warps per SM sub-partition (warps of co-resident blocks pile up on the same
+            // sub-partitions), plus a little for every further warp and for the W warps; ~2 rows of pipeline fill.
+            const int Veff = conc > 1 ? conc * 4 * ((nVw + 3) / 4) : nVw;
+            const double krow = 0.35 + 0.33 * ((Veff + 3) / 4) + 0.03 * ((Veff + 3) % 4);
+            const double cost = (double)waves * (BH + 2 * r + 2) * krow * (1.0 + 0.03 * conc * nWw) * (1.0 + 0.05 * (conc - 1));
             if (cost < best_cost) {
                 best_cost = cost; best = P; best_bands = bands; smem = o;
-                nt = 32 * (nVw + nWw + nSw);
+                nt = nthr;
                 ok = true;
             }
         }
@@ -507,6 +522,9 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
     const int tilesX = (need + P.TW - 1) / P.TW;
     P.BH = (rows + best_bands - 1) / best_bands;
     dim3 grid(tilesX, (rows + P.BH - 1) / P.BH);
+    if (verbose)
+        fprintf(stderr, "bm_vh plan: NCB=%d TW=%d BH=%d grid=%dx%d warps V/W/S=%d/%d/%d smem=%zu\n", P.NCB, P.TW, P.BH, grid.x, grid.y,
+                P.nVw, P.nWw, P.nSw, smem);
     cudaError_t e;
     switch (r) {
     case 2: e = launch_vh<2>(P, grid, nt, smem, st); break;
