@@ -110,6 +110,12 @@ class GpuStereoProcessor
         sync();
         ck(b200s_compute_disparity(h_, left, right, disparity));
     }
+    // cv::cuda::StereoBM compatibility mode: the CV_8UC1 plane the reference's GPU matcher writes (src/GPUStereoProcessor.cpp:283)
+    void computeDisparityCudaCompat(GpuMatSource left, GpuMatSource right, GpuMatSource disparity)
+    {
+        sync();
+        ck(b200s_compute_disparity_cuda_compat(h_, left, right, disparity));
+    }
     // computeDisparityBare: matcher only on host images -> CV_16SC1 x16 (src/GPUStereoProcessor.cpp:305-310)
     void computeDisparityBare(const Mat &left, const Mat &right, Mat &disparity)
     {

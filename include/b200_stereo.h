@@ -138,8 +138,15 @@ int b200s_rectify(b200s_handle* h, int src_id, int dst_id, int interpolation);
  * also fills the matching DISPARITY_32F buffer of the same side. Includes validate + ROI mask + speckle exactly
  * as cv::StereoBM::compute does. */
 int b200s_compute_disparity(b200s_handle* h, int left_id, int right_id, int disp_id);
-/* filterSpeckles(GpuMatSource) (src/GPUStereoProcessor.cpp:356-385) on a CV_16SC1 plane, in place:
- * newVal = FILTERED, maxSize = speckle_window_size, maxDiff = speckle_range (raw units). */
+/* "cuda-compat" mode: the bytes the reference's GPU matcher produces (block_matcher_gpu_->compute = cv::cuda::StereoBM,
+ * src/GPUStereoProcessor.cpp:283; known answer test_data/aloe-disp.png): SSD, integer disparity, CV_8UC1 in disp_id,
+ * 0 = invalid.  Uses num_disparities (multiple of 8, <= 256), block_size (3..51), pre_filter_type (1 = x-Sobel
+ * prefilter, else none), pre_filter_cap, texture_threshold (avergeTexThreshold).  minDisparity, uniqueness, disp12 and
+ * the speckle parameters have no effect there, exactly like the upstream setters. */
+int b200s_compute_disparity_cuda_compat(b200s_handle* h, int left_id, int right_id, int disp_id);
+/* filterSpeckles(GpuMatSource) (src/GPUStereoProcessor.cpp:356-385), in place.  CV_16SC1 plane: newVal = FILTERED,
+ * maxSize = speckle_window_size, maxDiff = speckle_range (raw x16 units, as cv::StereoBM).  CV_8UC1 plane (cuda-compat):
+ * the reference's own flow, newVal = 0 and maxDiff = speckle_range / 16 in integer disparities. */
 int b200s_filter_speckles(b200s_handle* h, int disp_id);
 /* stand-alone cv::filterSpeckles on a host CV_16SC1 plane (filterSpeckles(InputOutputArray), :367-385) */
 int b200s_filter_speckles_host(b200s_handle* h, int16_t* img, int rows, int cols, size_t step, int new_val,

@@ -256,3 +256,68 @@ def draw_color_disp(d16, nd):
         out[..., c] = (np.clip(v, 0, 1).astype(np.float32) * np.float32(255.0)).astype(np.uint32).astype(np.uint8)
     out[..., 3] = 255
     return out
+
+
+# ---- cv::cuda::StereoBM restated: what the reference's GPU path computes at
+# GPUStereoProcessor.cpp:283 (block_matcher_gpu_->compute).  Upstream: opencv_contrib cudastereo stereobm.cu. -----------
+def cuda_prefilter_xsobel(img, cap):
+    """prefilter_kernel_xsobel: full 3x3 Sobel-x on clamp-addressed pixels, min(clip(v, -cap, cap) + cap, 255)."""
+    p = np.pad(np.asarray(img, np.int32), 1, mode="edge")
+    conv = (-p[:-2, :-2] + p[:-2, 2:] - 2 * p[1:-1, :-2] + 2 * p[1:-1, 2:] - p[2:, :-2] + p[2:, 2:])
+    return np.minimum(np.clip(conv, -cap, cap) + cap, 255).astype(np.uint8)
+
+
+def _box_sum(a, r):
+    """exact integer box sum over (2r+1)^2, 'valid' region only: out[y, x] = sum a[y:y+2r+1, x:x+2r+1]"""
+    c = np.cumsum(np.cumsum(np.pad(a.astype(np.int64), ((1, 0), (1, 0))), axis=0), axis=1)
+    b = 2 * r + 1
+    return c[b:, b:] - c[:-b, b:] - c[b:, :-b] + c[:-b, :-b]
+
+
+def cuda_textureness_mask(img, wsz, avg_tex_threshold):
+    """postfilter_textureness: pixels whose window sum of |Sobel-x| (clamp-addressed, 3x3) is below
+    avergeTexThreshold * wsz * wsz.  Upstream sums normalised floats (value / 255) and scales by 255; this is the same
+    quantity in exact integer arithmetic (PARITY UNPINNED at the rounding boundary: no golden removes a pixel)."""
+    r = wsz // 2
+    H, W = img.shape
+    # the Sobel itself is evaluated at clamp-addressed coordinates: sobel(x, y) for x, y outside the image
+    # uses tex2D clamping of every tap, which equals evaluating on the edge-padded image
+    pp = np.pad(np.asarray(img, np.int32), r + 1, mode="edge")
+    s = np.abs(-pp[:-2, :-2] + pp[:-2, 2:] - 2 * pp[1:-1, :-2] + 2 * pp[1:-1, 2:] - pp[2:, :-2] + pp[2:, 2:])
+    win = _box_sum(s, r)                      # H x W
+    return win < int(avg_tex_threshold) * wsz * wsz
+
+
+def cuda_stereobm(L, R, nd, wsz, xsobel=False, cap=31, tex_threshold=3):
+    """u8 integer disparity, 0 = not computed / filtered.  SSD over wsz^2; candidates d = 0..nd-1 scanned ascending in
+    groups of 8: inside a group the HIGHEST index with the minimum wins, across groups strict '<' (earlier group wins).
+    Computed for x in [nd + r, W - r), y in [r, H - r)."""
+    L = np.ascontiguousarray(L, np.uint8)
+    R = np.ascontiguousarray(R, np.uint8)
+    if xsobel:
+        L, R = cuda_prefilter_xsobel(L, cap), cuda_prefilter_xsobel(R, cap)
+    H, W = L.shape
+    r = wsz // 2
+    out = np.zeros((H, W), np.uint8)
+    x0, x1, y0, y1 = nd + r, W - r, r, H - r
+    if x1 > x0 and y1 > y0:
+        Li, Ri = L.astype(np.int64), R.astype(np.int64)
+        best = np.full((y1 - y0, x1 - x0), np.iinfo(np.int64).max)
+        bd = np.zeros((y1 - y0, x1 - x0), np.int64)
+        for g in range(0, nd, 8):
+            ssd = []
+            for j in range(8):
+                d = g + j
+                sq = np.zeros((H, W), np.int64)
+                sq[:, d:] = (Li[:, d:] - Ri[:, :W - d]) ** 2
+                ssd.append(_box_sum(sq, r)[:, x0 - r:x1 - r])      # rows y0..y1, columns x0..x1
+            ssd = np.stack(ssd)
+            m = ssd.min(axis=0)
+            idx = 7 - np.argmin(ssd[::-1], axis=0)                 # last index that holds the minimum
+            upd = m < best
+            best = np.where(upd, m, best)
+            bd = np.where(upd, g + idx, bd)
+        out[y0:y1, x0:x1] = bd.astype(np.uint8)
+    if tex_threshold > 0:
+        out[cuda_textureness_mask(L, wsz, tex_threshold)] = 0
+    return out

@@ -75,6 +75,7 @@ SYMBOLS = {
     "b200s_convert_raw_to_color": (C.c_int, [H, C.c_int]),
     "b200s_rectify": (C.c_int, [H, C.c_int, C.c_int, C.c_int]),
     "b200s_compute_disparity": (C.c_int, [H, C.c_int, C.c_int, C.c_int]),
+    "b200s_compute_disparity_cuda_compat": (C.c_int, [H, C.c_int, C.c_int, C.c_int]),
     "b200s_filter_speckles": (C.c_int, [H, C.c_int]),
     "b200s_filter_speckles_host": (C.c_int, [H, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int]),
     "b200s_compute_disparity_image": (C.c_int, [H, C.c_int, C.c_int]),

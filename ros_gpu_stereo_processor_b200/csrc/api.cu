@@ -670,17 +670,63 @@ int b200s_compute_disparity(b200s_handle* h, int left_id, int right_id, int disp
     return check_kernels(h, "compute_disparity");
 }
 
+// cv::cuda::StereoBM compatibility mode: what block_matcher_gpu_->compute produces at src/GPUStereoProcessor.cpp:283
+int b200s_compute_disparity_cuda_compat(b200s_handle* h, int left_id, int right_id, int disp_id)
+{
+    if (!h) return B200S_EINVAL;
+    DeviceGuard g(h->device);
+    Mat* L = find_mat(h, left_id);
+    Mat* R = find_mat(h, right_id);
+    if (!L || !R) return fail(h, B200S_ENOBUF, "left/right buffer is empty");
+    if (L->type != B200S_8UC1 || R->type != B200S_8UC1 || L->rows != R->rows || L->cols != R->cols)
+        return fail(h, B200S_EINVAL, "both input images must have CV_8UC1 format and equal size");
+    const b200s_params& p = h->prm;
+    // cv::cuda::StereoBM limits (opencv_contrib cudastereo): ndisp a multiple of 8 up to 256, window radius 1..25
+    if (p.num_disparities <= 0 || p.num_disparities > 256 || (p.num_disparities & 7))
+        return fail(h, B200S_EINVAL, "cuda-compat: numDisparities must be a positive multiple of 8, at most 256");
+    if ((p.block_size >> 1) < 1 || (p.block_size >> 1) > 25) return fail(h, B200S_EINVAL, "cuda-compat: unsupported window size (3..51)");
+    if (p.pre_filter_cap < 1 || p.pre_filter_cap > 63 || p.texture_threshold < 0) return fail(h, B200S_EINVAL, "cuda-compat: bad prefilter cap / texture threshold");
+    const int rows = L->rows, cols = L->cols;
+    cudaStream_t st = h->l_strm;
+    CUDA_OK(h, cudaEventRecord(h->ev_r, h->r_strm));
+    CUDA_OK(h, cudaStreamWaitEvent(st, h->ev_r, 0));
+    Mat* D;
+    int rc = alloc_mat(h, disp_id, rows, cols, B200S_8UC1, "mono8", &D);
+    if (rc) return rc;
+    L = find_mat(h, left_id);
+    R = find_mat(h, right_id);
+    const size_t n = (size_t)rows * cols;
+    const bool xs = p.pre_filter_type == 1;
+    if (xs && (h->w0.preL.ensure(plane_bytes(cols, rows)) || h->w0.preR.ensure(plane_bytes(cols, rows))))
+        return fail(h, B200S_ENOMEM, "cudaMalloc failed (prefilter planes)");
+    h->launches += launch_cuda_compat_bm((const uint8_t*)L->buf.p, (const uint8_t*)R->buf.p, (uint8_t*)h->w0.preL.p, (uint8_t*)h->w0.preR.p,
+                                         cols, rows, p.num_disparities, p.block_size, xs, p.pre_filter_cap, p.texture_threshold,
+                                         (uint8_t*)D->buf.p, st);
+    (void)n;
+    return check_kernels(h, "compute_disparity_cuda_compat");
+}
+
 int b200s_filter_speckles(b200s_handle* h, int disp_id)
 {
     if (!h) return B200S_EINVAL;
     DeviceGuard g(h->device);
     Mat* D = find_mat(h, disp_id);
-    if (!D || D->type != B200S_16SC1) return fail(h, B200S_ENOBUF, "disparity buffer is empty or not CV_16SC1");
+    if (!D || (D->type != B200S_16SC1 && D->type != B200S_8UC1)) return fail(h, B200S_ENOBUF, "disparity buffer is empty or neither CV_16SC1 nor CV_8UC1");
     const b200s_params& p = h->prm;
     if (p.speckle_window_size <= 0 || p.speckle_range < 0) return B200S_OK;
     size_t n = (size_t)D->rows * D->cols;
     if (h->w0.ccl.ensure(3 * n * sizeof(int))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (speckle scratch)");
     cudaStream_t st = stream_of(h, disp_id);
+    if (D->type == B200S_8UC1) {
+        // the reference's own flow on the cuda matcher's u8 plane (src/GPUStereoProcessor.cpp:367-385):
+        // convertTo(CV_16S), cv::filterSpeckles(newVal 0, maxSpeckleSize, maxSpeckleDiff in integer disparities), convertTo(CV_8U)
+        if (h->w0.disp.ensure(n * sizeof(int16_t))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (speckle plane)");
+        h->launches += launch_u8_to_s16((const uint8_t*)D->buf.p, (int16_t*)h->w0.disp.p, n, st);
+        h->launches += launch_filter_speckles((int16_t*)h->w0.disp.p, D->cols, D->rows, 0, p.speckle_window_size,
+                                              (p.speckle_range + 8) / 16, (int*)h->w0.ccl.p, st);
+        h->launches += launch_s16_to_u8((const int16_t*)h->w0.disp.p, (uint8_t*)D->buf.p, n, st);
+        return check_kernels(h, "filter_speckles (u8)");
+    }
     h->launches += launch_filter_speckles((int16_t*)D->buf.p, D->cols, D->rows, (p.min_disparity - 1) * 16,
                                           p.speckle_window_size, p.speckle_range, (int*)h->w0.ccl.p, st);
     return check_kernels(h, "filter_speckles");

@@ -58,6 +58,13 @@ inline size_t plane_pitch(int W) { return ((size_t)W + 15) / 16 * 16; }
 inline size_t plane_bytes(int W, int H) { return PLANE_LEAD + plane_pitch(W) * H + PLANE_TAIL; }
 size_t bm_scratch_bytes(int W, int H, const BMConfig& cfg);
 
+// ---- bm_cuda_compat.cu ------------------------------------------------------------------------------
+// cv::cuda::StereoBM compatibility mode (SSD, CV_8UC1 integer disparity, 0 = invalid); tmpL/tmpR: W*H scratch (xsobel only)
+int launch_cuda_compat_bm(const uint8_t* L, const uint8_t* R, uint8_t* tmpL, uint8_t* tmpR, int W, int H, int nd, int wsz,
+                          bool xsobel, int cap, int tex_threshold, uint8_t* disp, cudaStream_t st);
+int launch_u8_to_s16(const uint8_t* a, int16_t* b, size_t n, cudaStream_t st);
+int launch_s16_to_u8(const int16_t* a, uint8_t* b, size_t n, cudaStream_t st);
+
 // ---- post.cu ----------------------------------------------------------------------------------------
 int launch_validate_disp12(int16_t* disp, const int16_t* cost, int W, int H, const BMConfig& cfg, cudaStream_t st);
 int launch_roi_mask(int16_t* disp, int W, int H, const BMConfig& cfg, cudaStream_t st);

@@ -178,6 +178,20 @@ class GpuStereoProcessor(object):
                                                    SRC_DISPARITY | SIDE_L))
         return self.downloadMat(SRC_DISPARITY | SIDE_L)
 
+    def computeDisparityCudaCompat(self, left, right, disparity=None):
+        """cv::cuda::StereoBM compatibility mode = the bytes of the reference's GPU matcher
+        (block_matcher_gpu_->compute, src/GPUStereoProcessor.cpp:283): CV_8UC1 integer disparity, 0 = invalid.
+        Ids like computeDisparity, or two host images -> host u8 plane."""
+        self._sync_params()
+        if isinstance(left, (int, np.integer)):
+            self._ck(self._lib.b200s_compute_disparity_cuda_compat(self._h, int(left), int(right), int(disparity)))
+            return None
+        self.uploadMat(SRC_RECT_MONO | SIDE_L, left)
+        self.uploadMat(SRC_RECT_MONO | SIDE_R, right)
+        self._ck(self._lib.b200s_compute_disparity_cuda_compat(self._h, SRC_RECT_MONO | SIDE_L, SRC_RECT_MONO | SIDE_R,
+                                                               SRC_DISPARITY | SIDE_L))
+        return self.downloadMat(SRC_DISPARITY | SIDE_L)
+
     def computeDisparityImage(self, disparity_src, disp_image_dest):
         self._sync_params()
         self._ck(self._lib.b200s_compute_disparity_image(self._h, int(disparity_src), int(disp_image_dest)))

@@ -444,6 +444,42 @@ def test_disparity_tall_band_bias_limit(proc):
     assert np.array_equal(got, want), _describe(got, want)
 
 
+# ---- cuda-compat mode: the bytes of the reference's GPU matcher (cv::cuda::StereoBM) ----------------------------------
+def test_cuda_compat_matches_reference_aloe_golden(proc, fixtures):
+    """Known answer shipped with the reference: test_data/aloe-disp.png = cuda::createStereoBM(128, 19) on the aloe pair
+    (upstream's last r computed columns read uninitialised shared memory, SURVEY.md C.6: outside the parity domain)."""
+    L, R, G = fixtures["aloe_L"], fixtures["aloe_R"], fixtures["aloe_cuda_disp"]
+    _set(proc, O.BMParams(numDisparities=128, blockSize=19, preFilterType=0, textureThreshold=3))
+    got = proc.computeDisparityCudaCompat(L, R)
+    W, r = L.shape[1], 9
+    assert got.dtype == np.uint8
+    assert np.array_equal(got[:, :W - 2 * r], G[:, :W - 2 * r]), _describe(got[:, :W - 2 * r], G[:, :W - 2 * r])
+    assert np.array_equal(got, O.cuda_stereobm(L, R, 128, 19, False, 31, 3))
+
+
+@pytest.mark.parametrize("case", [(64, 9, True, 31, 3), (32, 5, False, 31, 0), (256, 11, True, 15, 10), (48, 51, False, 31, 4), (16, 21, True, 63, 1)])
+def test_cuda_compat_matches_oracle(proc, case):
+    nd, b, xs, cap, tex = case
+    W, H = nd + 333, 141 if b < 40 else 230
+    L, R = synth.synth_pair(W, H, max(nd, 16), seed=nd + b)
+    L[20:60, nd + 60:nd + 160] = 90                       # a textureless patch for the textureness filter
+    _set(proc, O.BMParams(numDisparities=nd, blockSize=b, preFilterType=1 if xs else 0, preFilterCap=cap, textureThreshold=tex))
+    got = proc.computeDisparityCudaCompat(L, R)
+    want = O.cuda_stereobm(L, R, nd, b, xs, cap, tex)
+    assert np.array_equal(got, want), _describe(got, want)
+    if tex > 0 and b <= 11:
+        assert (want[28:52, nd + 75:nd + 145] == 0).all()      # prefilter + Sobel + window margins inside the flat patch
+    # the reference's u8 speckle flow (GPUStereoProcessor.cpp:367-385): convertTo 16S, filterSpeckles(newVal 0), convertTo 8U
+    m = _gpu()
+    proc.setMaxSpeckleSize(60)
+    proc.setMaxSpeckleDiff(2)
+    proc.filterSpeckles(m.SRC_DISPARITY | m.SIDE_L)
+    got2 = proc.downloadMat(m.SRC_DISPARITY | m.SIDE_L)
+    want2 = O.filter_speckles(want.astype(np.int16), 0, 60, 2).astype(np.uint8)
+    assert np.array_equal(got2, want2), _describe(got2, want2)
+    proc.setMaxSpeckleSize(0)
+
+
 def test_block_not_smaller_than_image_is_rejected(proc):
     m = _gpu()
     L, R = synth.synth_pair(64, 21, 16, seed=3)
