@@ -195,6 +195,11 @@ int b200s_wait_slot(b200s_handle* h, int slot);
 int b200s_slot_device_ptr(b200s_handle* h, int slot, uint32_t which /* one B200S_OUT_* */, void** dptr, size_t* bytes);
 /* synchronous convenience: slot 0, process + wait */
 int b200s_process_pair(b200s_handle* h, const void* left, const void* right, const b200s_frame_io* io);
+/* The frame chain of a slot is captured into a CUDA graph the second time it runs with the same parameters, products
+ * and output addresses, and replayed with one cudaGraphLaunch afterwards (inputs are copied into the slot first).
+ * on = 0 launches every kernel individually (also: environment B200S_GRAPH=0).  Results are identical. */
+int b200s_set_graph_mode(b200s_handle* h, int on);
+uint64_t b200s_graph_replays(const b200s_handle* h);
 
 /* Device-side timing of a batch of frames spread over the slots (CUDA events on the slot streams): begin() syncs
  * the device, records a start event and makes every slot stream wait on it; end() records one event per slot

@@ -96,6 +96,8 @@ SYMBOLS = {
     "b200s_enable_timing": (C.c_int, [H, C.c_int]),
     "b200s_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "b200s_host_free": (C.c_int, [C.c_void_p]),
+    "b200s_set_graph_mode": (C.c_int, [H, C.c_int]),
+    "b200s_graph_replays": (C.c_uint64, [H]),
     "b200s_int_peak": (C.c_int, [H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

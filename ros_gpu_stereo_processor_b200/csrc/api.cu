@@ -69,8 +69,22 @@ struct Work {
     cudaEvent_t ev_bm0 = nullptr, ev_bm1 = nullptr, ev_done = nullptr;
     double last_evals = 0;
     bool timed = false;
+    // CUDA graph of the frame chain of this slot: the first frame with a given key runs eagerly (allocations, map
+    // build), the second is captured, the following ones are replayed with one cudaGraphLaunch
+    std::string gkey, warm_key;
+    cudaGraphExec_t gexec = nullptr;
+    uint64_t glaunches = 0;
+    double gevals = 0;
+    void drop_graph()
+    {
+        if (gexec) cudaGraphExecDestroy(gexec);
+        gexec = nullptr;
+        gkey.clear();
+        warm_key.clear();
+    }
     void release()
     {
+        drop_graph();
         DevBuf* all[] = {&rawL, &rawR, &rectL, &rectR, &preL, &preR, &disp, &cost, &df, &xyz, &pc2, &vol, &ccl, &normtmp, &misc};
         for (DevBuf* b : all) b->release();
         if (ev_bm0) cudaEventDestroy(ev_bm0);
@@ -112,6 +126,9 @@ struct b200s_handle {
     cudaEvent_t batch_start = nullptr;
     int slot_rows = 0, slot_cols = 0;
     uint64_t launches = 0;
+    uint64_t model_version = 0;   // bumped by every calibration change (part of the graph key)
+    int use_graphs = 1;           // B200S_GRAPH=0 or b200s_set_graph_mode(h, 0) turns the replay off
+    uint64_t graph_replays = 0;
 };
 
 namespace {
@@ -391,6 +408,7 @@ int b200s_create(int device, b200s_handle** out)
     h->device = device;
     // state of the reference's CPU matcher after its constructor (src/GPUStereoProcessor.cpp:18-38):
     // createStereoBM(48, 19) mirrored into cv::StereoBM, preFilterSize 5
+    if (const char* e = getenv("B200S_GRAPH")) h->use_graphs = atoi(e) != 0;
     b200s_default_params(&h->prm);
     h->prm.pre_filter_type = 0; h->prm.pre_filter_size = 5; h->prm.num_disparities = 48; h->prm.block_size = 19;
     h->prm.texture_threshold = 3; h->prm.uniqueness_ratio = 0; h->prm.disp12_max_diff = 0;
@@ -458,6 +476,7 @@ int b200s_set_calibration(b200s_handle* h, const b200s_caminfo* left, const b200
     if (h->Qdev.ensure(sizeof(h->Q))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (Q)");
     CUDA_OK(h, cudaMemcpy(h->Qdev.p, h->Q, sizeof(h->Q), cudaMemcpyHostToDevice));
     h->model_ok = true;
+    ++h->model_version;
     return B200S_OK;
 }
 
@@ -505,6 +524,7 @@ int b200s_set_rectify_mode(b200s_handle* h, int on_the_fly)
 {
     if (!h) return B200S_EINVAL;
     h->rect_fly = on_the_fly != 0;
+    ++h->model_version;
     return B200S_OK;
 }
 
@@ -905,28 +925,13 @@ int b200s_configure_slots(b200s_handle* h, int n_slots, int rows, int cols)
     return B200S_OK;
 }
 
-int b200s_process_pair_async(b200s_handle* h, int slot, const void* left, const void* right, const b200s_frame_io* io)
+namespace {
+
+// everything of a frame after the inputs are on the device: rectify -> disparity -> float / reproject+pack -> outputs
+int run_frame_chain(b200s_handle* h, Work& w, const b200s_frame_io* io, const uint8_t* L, const uint8_t* R, cudaStream_t st)
 {
-    if (!h || !left || !right || !io) return B200S_EINVAL;
-    DeviceGuard g(h->device);
-    if (slot < 0 || slot >= (int)h->slots.size()) return fail(h, B200S_EINVAL, "slot out of range (call b200s_configure_slots)");
-    Work& w = h->slots[slot];
     const int rows = h->slot_rows, cols = h->slot_cols;
     const size_t n = (size_t)rows * cols;
-    cudaStream_t st = w.st;
-    const bool need_model = io->rectify || (io->want & (B200S_OUT_POINTCLOUD2 | B200S_OUT_POINTS_XYZ));
-    if (need_model && !h->model_ok) return fail(h, B200S_ENOTINIT, "stereo model not initialised");
-    if (io->rectify && (h->cam[0].info.width != cols || h->cam[0].info.height != rows))
-        return fail(h, B200S_EINVAL, "slot size differs from the calibration size");
-    // inputs
-    const uint8_t *L = (const uint8_t*)left, *R = (const uint8_t*)right;
-    if (!io->inputs_on_device) {
-        if (w.rawL.ensure(n + 64) || w.rawR.ensure(n + 64)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (input planes)");
-        CUDA_OK(h, cudaMemcpyAsync(w.rawL.p, left, n, cudaMemcpyHostToDevice, st));
-        CUDA_OK(h, cudaMemcpyAsync(w.rawR.p, right, n, cudaMemcpyHostToDevice, st));
-        L = (const uint8_t*)w.rawL.p;
-        R = (const uint8_t*)w.rawR.p;
-    }
     bool prefiltered = false;
     const uint8_t *rl = L, *rr = R;
     if (io->rectify) {
@@ -985,9 +990,104 @@ int b200s_process_pair_async(b200s_handle* h, int slot, const void* left, const 
     if (want_df && (rc = copy_out(h, io->disparity32f, w.df.p, n * 4, od, st))) return rc;
     if (want_pc && (rc = copy_out(h, io->pointcloud2, w.pc2.p, n * 32, od, st))) return rc;
     if (want_xyz && (rc = copy_out(h, io->points_xyz, w.xyz.p, n * 12, od, st))) return rc;
+    return B200S_OK;
+}
+
+// everything a captured chain depends on besides the (fixed) slot buffers
+std::string frame_graph_key(const b200s_handle* h, const b200s_frame_io* io)
+{
+    std::string k;
+    auto add = [&k](const void* p, size_t n) { k.append((const char*)p, n); };
+    add(&h->prm, sizeof h->prm);
+    add(io, sizeof *io);
+    add(&h->model_version, sizeof h->model_version);
+    add(&h->slot_rows, sizeof h->slot_rows);
+    add(&h->slot_cols, sizeof h->slot_cols);
+    return k;
+}
+
+}  // namespace
+
+int b200s_process_pair_async(b200s_handle* h, int slot, const void* left, const void* right, const b200s_frame_io* io)
+{
+    if (!h || !left || !right || !io) return B200S_EINVAL;
+    DeviceGuard g(h->device);
+    if (slot < 0 || slot >= (int)h->slots.size()) return fail(h, B200S_EINVAL, "slot out of range (call b200s_configure_slots)");
+    Work& w = h->slots[slot];
+    const int rows = h->slot_rows, cols = h->slot_cols;
+    const size_t n = (size_t)rows * cols;
+    cudaStream_t st = w.st;
+    const bool need_model = io->rectify || (io->want & (B200S_OUT_POINTCLOUD2 | B200S_OUT_POINTS_XYZ));
+    if (need_model && !h->model_ok) return fail(h, B200S_ENOTINIT, "stereo model not initialised");
+    if (io->rectify && (h->cam[0].info.width != cols || h->cam[0].info.height != rows))
+        return fail(h, B200S_EINVAL, "slot size differs from the calibration size");
+    const bool graphs = h->use_graphs && !h->timing;
+    // inputs: host frames always go through the slot's raw planes; with graph replay device frames do too, so that
+    // the captured kernels see fixed addresses
+    const uint8_t *L = (const uint8_t*)left, *R = (const uint8_t*)right;
+    if (!io->inputs_on_device || graphs) {
+        if (w.rawL.ensure(n + 64) || w.rawR.ensure(n + 64)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (input planes)");
+        const cudaMemcpyKind kind = io->inputs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        CUDA_OK(h, cudaMemcpyAsync(w.rawL.p, left, n, kind, st));
+        CUDA_OK(h, cudaMemcpyAsync(w.rawR.p, right, n, kind, st));
+        L = (const uint8_t*)w.rawL.p;
+        R = (const uint8_t*)w.rawR.p;
+    }
+    int rc = B200S_OK;
+    if (!graphs) {
+        rc = run_frame_chain(h, w, io, L, R, st);
+    } else {
+        const std::string key = frame_graph_key(h, io);
+        if (w.gexec && key == w.gkey) {
+            CUDA_OK(h, cudaGraphLaunch(w.gexec, st));
+            h->launches += w.glaunches;
+            w.last_evals = w.gevals;
+            ++h->graph_replays;
+        } else if (key == w.warm_key) {
+            // second frame with this key: every buffer exists, the maps are built -> capture, instantiate, launch
+            if (w.gexec) { cudaGraphExecDestroy(w.gexec); w.gexec = nullptr; w.gkey.clear(); }
+            const uint64_t l0 = h->launches;
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+            if (e == cudaSuccess) {
+                rc = run_frame_chain(h, w, io, L, R, st);
+                e = cudaStreamEndCapture(st, &graph);
+                if (rc == B200S_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&w.gexec, graph, 0);
+                if (graph) cudaGraphDestroy(graph);
+            }
+            if (rc != B200S_OK || e != cudaSuccess || !w.gexec) {
+                // capture is an optimisation only: fall back to eager launches for this handle
+                cudaGetLastError();
+                w.drop_graph();
+                h->use_graphs = 0;
+                h->launches = l0;
+                rc = run_frame_chain(h, w, io, L, R, st);
+            } else {
+                w.glaunches = h->launches - l0;
+                w.gevals = w.last_evals;
+                w.gkey = key;
+                h->launches = l0 + w.glaunches;
+                CUDA_OK(h, cudaGraphLaunch(w.gexec, st));
+            }
+        } else {
+            rc = run_frame_chain(h, w, io, L, R, st);
+            w.warm_key = rc == B200S_OK ? key : std::string();
+        }
+    }
+    if (rc) return rc;
     CUDA_OK(h, cudaEventRecord(w.ev_done, st));
     return B200S_OK;
 }
+
+int b200s_set_graph_mode(b200s_handle* h, int on)
+{
+    if (!h) return B200S_EINVAL;
+    h->use_graphs = on ? 1 : 0;
+    for (Work& w : h->slots) w.drop_graph();
+    return B200S_OK;
+}
+
+uint64_t b200s_graph_replays(const b200s_handle* h) { return h ? h->graph_replays : 0; }
 
 int b200s_wait_slot(b200s_handle* h, int slot)
 {

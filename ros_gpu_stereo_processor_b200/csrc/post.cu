@@ -116,13 +116,16 @@ __device__ __forceinline__ void sm_union(int* L, int a, int b)
 
 // Stage 1.  Rows first: a warp scans two rows and labels every pixel with the first pixel of its horizontal run
 // (inclusive max-scan of run starts with shuffles), so only run pairs -- not pixels -- need a union in the vertical pass.
-// Writes L[i] = global index of the tile-local root (or -1 for newVal pixels) and clears sz.
+// Every run end then adds its run length to the tile-local root's pixel count (one shared-memory atomic per run, not per
+// pixel).  Writes L[i] = global index of the tile-local root (or -1 for newVal pixels) and sz[i] = pixel count of the
+// tile-local component at its root, 0 everywhere else.
 __global__ void __launch_bounds__(256) ccl_local_kernel(const int16_t* __restrict__ img, int* __restrict__ L,
                                                         int* __restrict__ sz, int W, int H, int newVal, int maxDiff)
 {
     __shared__ int16_t v[CTY * CTX];
     __shared__ int16_t rs[CTY * CTX];     // immutable run start (tile index) of every pixel, -1 for newVal
     __shared__ int lab[CTY * CTX];        // union-find parents over tile indices (only run starts ever get hooked)
+    __shared__ int cnt[CTY * CTX];        // pixels per tile-local root
     const int x0 = blockIdx.x * CTX, y0 = blockIdx.y * CTY;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -130,11 +133,9 @@ __global__ void __launch_bounds__(256) ccl_local_kernel(const int16_t* __restric
         const int tx = idx & (CTX - 1), ty = idx >> 6;
         const int x = x0 + tx, y = y0 + ty;
         int val = newVal;
-        if (x < W && y < H) {
-            val = img[(size_t)y * W + x];
-            sz[(size_t)y * W + x] = 0;
-        }
+        if (x < W && y < H) val = img[(size_t)y * W + x];
         v[idx] = (int16_t)val;
+        cnt[idx] = 0;
     }
     __syncthreads();
     {
@@ -180,18 +181,28 @@ __global__ void __launch_bounds__(256) ccl_local_kernel(const int16_t* __restric
         if (first) sm_union(lab, rs[idx], rs[idx + CTX]);
     }
     __syncthreads();
+    int lroot[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = threadIdx.x + 256 * k;
+        const int tx = idx & (CTX - 1);
+        lroot[k] = -1;
+        if (rs[idx] >= 0) {
+            lroot[k] = sm_find(lab, rs[idx]);
+            if (tx == CTX - 1 || rs[idx + 1] != rs[idx]) atomicAdd(&cnt[lroot[k]], idx - rs[idx] + 1);   // run end
+        }
+    }
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int idx = threadIdx.x + 256 * k;
         const int tx = idx & (CTX - 1), ty = idx >> 6;
         const int x = x0 + tx, y = y0 + ty;
         if (x >= W || y >= H) continue;
-        int g = -1;
-        if (rs[idx] >= 0) {
-            const int r = sm_find(lab, rs[idx]);
-            g = (y0 + (r >> 6)) * W + x0 + (r & (CTX - 1));   // raster order is preserved: root index <= own index
-        }
-        L[(size_t)y * W + x] = g;
+        const int r = lroot[k];
+        // raster order is preserved: root index <= own index
+        L[(size_t)y * W + x] = r >= 0 ? (y0 + (r >> 6)) * W + x0 + (r & (CTX - 1)) : -1;
+        sz[(size_t)y * W + x] = r == idx ? cnt[idx] : 0;
     }
 }
 
@@ -204,21 +215,30 @@ __global__ void __launch_bounds__(256) ccl_border_kernel(const int16_t* __restri
     const long long nR = (long long)ncx * H, total = nR + (long long)ncy * W;
     long long t = (long long)blockIdx.x * 256 + threadIdx.x;
     if (t >= total) return;
-    int x, y, j;
+    int x, y, j, back;       // back: offset to the previous pixel pair along the border, 0 at the start of a tile
     if (t < nR) {
         y = (int)(t / ncx);
         x = ((int)(t - (long long)y * ncx) + 1) * CTX - 1;
         j = y * W + x + 1;
+        back = (y % CTY) ? W : 0;
     } else {
         t -= nR;
         const int ry = (int)(t / W);
         x = (int)(t - (long long)ry * W);
         y = (ry + 1) * CTY - 1;
         j = (y + 1) * W + x;
+        back = (x % CTX) ? 1 : 0;
     }
     const int i = y * W + x;
     const int a = img[i], u = img[j];
-    if (a != newVal && u != newVal && abs(u - a) <= maxDiff) uf_union(L, i, j);
+    if (a == newVal || u == newVal || abs(u - a) > maxDiff) return;
+    if (back) {
+        // the previous pair is joined by its own thread and both pixels are joined to their predecessors inside their
+        // tiles (never across a tile corner, so there is no cycle of skipped edges): this union would be redundant
+        const int ap = img[i - back], up = img[j - back];
+        if (ap != newVal && up != newVal && abs(ap - a) <= maxDiff && abs(up - u) <= maxDiff && abs(up - ap) <= maxDiff) return;
+    }
+    uf_union(L, i, j);
 }
 
 // read-only root lookup: the forest is final here, and no thread may write L while others still walk it
@@ -230,63 +250,31 @@ __device__ __forceinline__ int uf_root(const int* __restrict__ L, int i)
     return i;
 }
 
-// ---- stage 3: per tile, count pixels per tile-local root in shared memory, resolve each local root's global root
-// once, add the counts to the global histogram and record the global root of every pixel --------------------------
-__global__ void __launch_bounds__(256) ccl_finalize_kernel(const int* __restrict__ L, int* __restrict__ root,
-                                                           int* __restrict__ sz, int W, int H)
+// ---- stage 3: every tile-local root (sz > 0) that was hooked under another root adds its count to the global root
+// and is pointed straight at it, so that afterwards L[L[i]] is the global root of any pixel i ----------------------
+__global__ void __launch_bounds__(256) ccl_merge_counts_kernel(int* __restrict__ L, int* __restrict__ sz, int n)
 {
-    __shared__ int cnt[CTY * CTX];
-    __shared__ int groot[CTY * CTX];
-    const int x0 = blockIdx.x * CTX, y0 = blockIdx.y * CTY;
-    int bucket[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) cnt[threadIdx.x + 256 * k] = 0;
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int idx = threadIdx.x + 256 * k;
-        const int tx = idx & (CTX - 1), ty = idx >> 6;
-        const int x = x0 + tx, y = y0 + ty;
-        bucket[k] = -1;
-        if (x < W && y < H) {
-            const int p = L[(size_t)y * W + x];
-            if (p >= 0) {
-                // parent inside this tile (the tile-local root) -> its bucket; otherwise (own root, or a border pixel whose
-                // parent was shortened to another tile by path halving) the pixel is its own bucket
-                const int px = p % W - x0, py = p / W - y0;
-                bucket[k] = ((unsigned)px < (unsigned)CTX && (unsigned)py < (unsigned)CTY) ? py * CTX + px : idx;
-                atomicAdd(&cnt[bucket[k]], 1);
-            }
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int idx = threadIdx.x + 256 * k;
-        const int c = cnt[idx];
-        if (c > 0) {
-            const int g = uf_root(L, (y0 + (idx >> 6)) * W + x0 + (idx & (CTX - 1)));
-            groot[idx] = g;
-            atomicAdd(&sz[g], c);
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int idx = threadIdx.x + 256 * k;
-        const int tx = idx & (CTX - 1), ty = idx >> 6;
-        const int x = x0 + tx, y = y0 + ty;
-        if (x < W && y < H) root[(size_t)y * W + x] = bucket[k] >= 0 ? groot[bucket[k]] : -1;
-    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = sz[i];
+    if (c <= 0) return;
+    int p = L[i];
+    if (p == i) return;                       // a global root keeps its own count
+    int g = p;
+    for (int q = L[g]; q != g; q = L[g]) g = q;
+    atomicAdd(&sz[g], c);                     // only global roots ever receive additions
+    L[i] = g;                                 // concurrent walkers see the old parent or the root: both are ancestors
 }
 
-__global__ void __launch_bounds__(256) ccl_apply_kernel(int16_t* __restrict__ img, const int* __restrict__ root,
+__global__ void __launch_bounds__(256) ccl_apply_kernel(int16_t* __restrict__ img, const int* __restrict__ L,
                                                         const int* __restrict__ sz, int n, int newVal, int maxSize)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int r = root[i];
-    if (r >= 0 && sz[r] <= maxSize) img[i] = (int16_t)newVal;
+    const int p = L[i];                        // a tile-local root (parents are always tile-local roots)
+    if (p < 0) return;
+    const int g = L[p];                        // its global root after stage 3
+    if (sz[g] <= maxSize) img[i] = (int16_t)newVal;
 }
 
 static inline dim3 grid2d(int W, int H) { return dim3((W + 31) / 32, (H + 7) / 8); }
@@ -315,15 +303,14 @@ int launch_filter_speckles(int16_t* img, int W, int H, int newVal, int maxSize, 
     int n = W * H;
     int* L = scratch;
     int* sz = scratch + n;
-    int* root = scratch + 2 * (size_t)n;
     int nb = (n + 255) / 256;
     ccl_local_kernel<<<dim3((W + CTX - 1) / CTX, (H + CTY - 1) / CTY), 256, 0, st>>>(img, L, sz, W, H, newVal, maxDiff);
     {
         const long long nbp = (long long)((W - 1) / CTX) * H + (long long)((H - 1) / CTY) * W;
         if (nbp > 0) ccl_border_kernel<<<(unsigned)((nbp + 255) / 256), 256, 0, st>>>(img, L, W, H, newVal, maxDiff);
     }
-    ccl_finalize_kernel<<<dim3((W + CTX - 1) / CTX, (H + CTY - 1) / CTY), 256, 0, st>>>(L, root, sz, W, H);
-    ccl_apply_kernel<<<nb, 256, 0, st>>>(img, root, sz, n, newVal, maxSize);
+    ccl_merge_counts_kernel<<<nb, 256, 0, st>>>(L, sz, n);
+    ccl_apply_kernel<<<nb, 256, 0, st>>>(img, L, sz, n, newVal, maxSize);
     return 4;
 }
 

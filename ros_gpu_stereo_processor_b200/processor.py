@@ -386,6 +386,13 @@ class GpuStereoProcessor(object):
         self._ck(self._lib.b200s_last_bm_time(self._h, int(slot), C.byref(ms), C.byref(ev)))
         return ms.value, ev.value
 
+    def setGraphMode(self, on):
+        """CUDA-graph replay of the per-slot frame chain (default on); results are identical either way."""
+        self._ck(self._lib.b200s_set_graph_mode(self._h, int(bool(on))))
+
+    def graphReplays(self):
+        return int(self._lib.b200s_graph_replays(self._h))
+
     def intPeak(self, which):
         ops, mhz = C.c_double(), C.c_double()
         self._ck(self._lib.b200s_int_peak(self._h, int(which), C.byref(ops), C.byref(mhz)))

@@ -285,6 +285,59 @@ def test_fused_chain_matches_oracle_chain(cfg):
     proc.close()
 
 
+def test_graph_replay_gives_identical_frames():
+    """The slot chain is captured into a CUDA graph on its second run and replayed afterwards; every replayed frame must
+    equal the oracle chain, also after a parameter change (re-capture) and with graphs switched off."""
+    m = _gpu()
+    cap = m._capi
+    W, H, nd, b = 640, 360, 64, 9
+    proc = m.GpuStereoProcessor(0)
+    frames = [synth.synth_raw_pair(W, H, nd, seed=4000 + i) for i in range(4)]
+    cal = frames[0][2]
+    proc.initStereoModel(_caminfo(cal["left"], W, H), _caminfo(cal["right"], W, H))
+    proc.configureSlots(2, H, W)
+    n = W * H
+    outs = []
+    for s in range(2):
+        io = cap.FrameIO()
+        io.want, io.rectify = cap.OUT_DISPARITY16 | cap.OUT_POINTCLOUD2, 1
+        d16, io.disparity16 = proc.hostAlloc(n * 2)
+        pc, io.pointcloud2 = proc.hostAlloc(n * 32)
+        outs.append((io, d16, pc))
+    cxd = cal["left"]["P"][2] - cal["right"]["P"][2]
+    Q = O.stereo_Q(cal["left"]["P"], cal["right"]["P"])
+
+    def check(p, rounds):
+        want = []
+        for (Lr, Rr, _) in frames:
+            rl, rr = O.rectify(Lr, **cal["left"]), O.rectify(Rr, **cal["right"])
+            d = O.stereobm_compute(rl, rr, p)
+            want.append((d, O.pack_pointcloud2(O.reproject(O.disparity_to_float(d, cxd), Q), rl)))
+        for it in range(rounds):
+            for i, (Lr, Rr, _) in enumerate(frames):
+                io, d16, pc = outs[i % 2]
+                proc.processPairAsync(i % 2, np.ascontiguousarray(Lr).ctypes.data, np.ascontiguousarray(Rr).ctypes.data, io)
+                proc.waitSlot(i % 2)
+                assert np.array_equal(d16.view(np.int16).reshape(H, W), want[i][0]), (it, i)
+                assert np.array_equal(pc.reshape(H, W, 32), want[i][1]), (it, i)
+
+    p1 = O.BMParams(numDisparities=nd, blockSize=b)
+    _set(proc, p1)
+    r0 = proc.graphReplays()
+    check(p1, 3)                      # eager, capture, then replays
+    assert proc.graphReplays() - r0 >= 8
+    p2 = O.BMParams(numDisparities=nd, blockSize=15, speckleWindowSize=50, speckleRange=2, disp12MaxDiff=1)
+    _set(proc, p2)
+    check(p2, 3)                      # new key: re-capture
+    proc.setGraphMode(False)
+    r1 = proc.graphReplays()
+    check(p2, 1)
+    assert proc.graphReplays() == r1
+    for io, d16, pc in outs:
+        proc.hostFree(io.disparity16); proc.hostFree(io.pointcloud2)
+    proc.close()
+
+
 # ---- error behaviour ----------------------------------------------------------------------------------------
 def test_errors():
     m = _gpu()
