@@ -45,7 +45,7 @@ struct VhParams {
     int SWb, KWb, NK16, CSB, RLW;    // Sbuf / Kbuf row strides, LDS.128 per key row
     int nVw, nWw, nSw;
     int oStage[2];                   // per buffer: Lb [2][ncolsP] words, then Rc [2][4][CSB] bytes
-    int oTc;                         // [8][ncols] words texture column sums (ring over output rows) + [ncols] running sums
+    int oTc;                         // [8][ncols] words: texture column sums (ring over output rows)
     int oS[2], oK[2];
     int oMbar;                       // 8 mbarriers
 };
@@ -250,28 +250,32 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
                     }
                 }
                 const int minsad_b = (int)(best >> 16), gs = (int)(best & 0xffffu);
-                int mind;
-                {
-                    const uint2 u = *(const uint2*)(srow + 8 * gs);          // u16 order: k, k+2, k+1, k+3
-                    int loc = 3;
-                    if ((int)(u.x >> 16) == minsad_b) loc = 2;
-                    if ((int)(u.y & 0xffffu) == minsad_b) loc = 1;
-                    if ((int)(u.x & 0xffffu) == minsad_b) loc = 0;
-                    mind = 4 * gs + loc;
-                }
-                uint16_t* s16 = (uint16_t*)srow;
+                // the winner's group and its two neighbours (4 disparities each, u16 order k, k+2, k+1, k+3) give the exact
+                // index, the sub-pixel neighbours and -- with mind-1, mind, mind+1 masked in registers -- their share of the
+                // uniqueness test; Sbuf is never written by this role
+                const int g0 = max(gs - 1, 0), g2 = min(gs + 1, G4 - 1);
+                uint2 e0 = *(const uint2*)(srow + 8 * g0);
+                uint2 e1 = *(const uint2*)(srow + 8 * gs);
+                uint2 e2 = *(const uint2*)(srow + 8 * g2);
+                const int v1[4] = {(int)(e1.x & 0xffffu), (int)(e1.y & 0xffffu), (int)(e1.x >> 16), (int)(e1.y >> 16)};
+                int loc = 3;
+                if (v1[2] == minsad_b) loc = 2;
+                if (v1[1] == minsad_b) loc = 1;
+                if (v1[0] == minsad_b) loc = 0;
+                const int mind = 4 * gs + loc;
                 const int minsad = minsad_b - bias;
-                const int pv = (int)s16[kpos(mind + 1 < nd ? mind + 1 : nd - 2)] - bias;
-                const int nv = (int)s16[kpos(mind > 0 ? mind - 1 : 1)] - bias;
+                // S[mind + 1] (S[nd - 2] at the upper end) and S[mind - 1] (S[1] at the lower end)
+                int pv = loc == 0 ? v1[1] : (loc == 1 ? v1[2] : v1[3]);
+                if (loc == 3) pv = gs < G4 - 1 ? (int)(e2.x & 0xffffu) : v1[2];
+                int nv = loc == 3 ? v1[2] : (loc == 2 ? v1[1] : v1[0]);
+                if (loc == 0) nv = gs > 0 ? (int)(e0.y >> 16) : v1[1];
+                pv -= bias;
+                nv -= bias;
                 bool filtered = false;
                 if (P.uniq > 0) {
-                    const int g0 = max(gs - 1, 0), g2 = min(gs + 1, G4 - 1);
                     ((uint32_t*)krow)[g0] = 0xFFFFFFFFu;
                     ((uint32_t*)krow)[gs] = 0xFFFFFFFFu;
                     ((uint32_t*)krow)[g2] = 0xFFFFFFFFu;
-                    s16[kpos(mind)] = 0xFFFFu;
-                    if (mind > 0) s16[kpos(mind - 1)] = 0xFFFFu;
-                    if (mind + 1 < nd) s16[kpos(mind + 1)] = 0xFFFFu;
                     uint32_t m2k = 0xFFFFFFFFu;
                     if (ND > 0) {
 #pragma unroll
@@ -285,9 +289,12 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
                             m2k = min(min(m2k, k4.x), min(k4.y, min(k4.z, k4.w)));
                         }
                     }
-                    const uint2 e0 = *(const uint2*)(srow + 8 * g0);
-                    const uint2 e1 = *(const uint2*)(srow + 8 * gs);
-                    const uint2 e2 = *(const uint2*)(srow + 8 * g2);
+                    e1.x |= (loc <= 1 ? 0x0000FFFFu : 0u) | (loc >= 1 ? 0xFFFF0000u : 0u);    // k, k+2
+                    e1.y |= (loc <= 2 ? 0x0000FFFFu : 0u) | (loc >= 2 ? 0xFFFF0000u : 0u);    // k+1, k+3
+                    if (gs == 0) e0 = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);                    // clamped: the same group again
+                    else if (loc == 0) e0.y |= 0xFFFF0000u;
+                    if (gs == G4 - 1) e2 = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+                    else if (loc == 3) e2.x |= 0x0000FFFFu;
                     uint32_t acc = __vimin3_u16x2(e0.x, e0.y, e1.x);
                     acc = __vimin3_u16x2(acc, e1.y, e2.x);
                     acc = __vminu2(acc, e2.y);
@@ -298,9 +305,22 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
                 if (wout) {
                     const int* tc = (const int*)(smem + P.oTc) + (o & 7) * P.ncols + px;
                     int tsum = 0;
-                    for (int c = 0; c < b; ++c) tsum += tc[c];
+#pragma unroll
+                    for (int c = 0; c < B; ++c) tsum += tc[c];
                     int16_t out = FILTERED;
-                    if (tsum >= P.texThr && !filtered) out = subpixel_disp(minsad, mind, pv, nv, nd, P.minD);
+                    if (tsum >= P.texThr && !filtered) {
+                        // cv::StereoBM's sub-pixel fit (bm_common.cuh subpixel_disp) with the truncating division done in fp32:
+                        // |p - n| <= d, so the quotient is at most 256 and one correction step makes it exact
+                        const int dd = pv + nv - 2 * minsad + abs(pv - nv);
+                        const int num = (pv - nv) * 256, an = abs(num);
+                        int q = 0;
+                        if (dd != 0) {
+                            q = (int)__fdividef((float)an, (float)dd);
+                            const int rem = an - q * dd;
+                            q += rem < 0 ? -1 : (rem >= dd ? 1 : 0);
+                        }
+                        out = (int16_t)(((nd - mind - 1 + P.minD) * 256 + (num < 0 ? -q : q) + 15) >> 4);
+                    }
                     const int y = yb0 + o;
                     P.disp[(size_t)y * P.W + X] = out;
                     if (P.cost) P.cost[(size_t)y * P.W + X] = (int16_t)minsad;
@@ -319,14 +339,13 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
         const int Xl0 = X0 - r;
         const int Xr0 = X0 - r - P.lofs;     // multiple of 4 by construction
         if (s == 0) {
-            int* trun = (int*)(smem + P.oTc) + 8 * P.ncols;    // [ncols] running sums, owned lane-wise
-            for (int c = lane; c < P.ncols; c += 32) trun[c] = 0;
-            int an[MAXL], ao[MAXL];
+            int an[MAXL], ao[MAXL], trun[MAXL];      // trun: running texture column sums of the lane's columns
 #pragma unroll
             for (int m = 0; m < MAXL; ++m) {
                 const int c = lane + 32 * m;
                 an[m] = c < P.ncolsP ? (int)__ldg(P.Lp + (size_t)y_in0 * P.pitch + Xl0 + c) : 0;
                 ao[m] = 0;
+                trun[m] = 0;
             }
             for (int j = 0; j < nIn; ++j) {
                 const int sb = j & 1;
@@ -359,9 +378,8 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
                         sLb[c] = (uint32_t)min(cn[m], 2 * P.cap) * 0x01010101u;
                         sLb[P.ncolsP + c] = (uint32_t)min(co[m], 2 * P.cap) * 0x01010101u;
                         if (c < P.ncols) {
-                            const int t = trun[c] + abs(cn[m] - P.cap) - (has_old ? abs(co[m] - P.cap) : 0);
-                            trun[c] = t;
-                            if (publish) tpub[c] = t;     // texture column sums of output row j - 2r (ring of 8 rows)
+                            trun[m] += abs(cn[m] - P.cap) - (has_old ? abs(co[m] - P.cap) : 0);
+                            if (publish) tpub[c] = trun[m];   // texture column sums of output row j - 2r (ring of 8 rows)
                         }
                     }
                 }
@@ -481,7 +499,7 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
         P.CSB = units * 16;
         size_t o = 0;
         for (int s2 = 0; s2 < 2; ++s2) { P.oStage[s2] = (int)o; o += 2 * (size_t)P.ncolsP * 4 + 8 * (size_t)P.CSB; o = (o + 15) & ~(size_t)15; }
-        P.oTc = (int)o; o += 9 * (size_t)ncols * 4; o = (o + 15) & ~(size_t)15;
+        P.oTc = (int)o; o += 8 * (size_t)ncols * 4; o = (o + 15) & ~(size_t)15;
         for (int s2 = 0; s2 < 2; ++s2) { P.oK[s2] = (int)o; o += (size_t)TW * P.KWb; }
         for (int s2 = 0; s2 < 2; ++s2) { P.oS[s2] = (int)o; o += (size_t)TW * P.SWb; }
         P.oMbar = (int)o; o += 8 * vh::MB_COUNT;
