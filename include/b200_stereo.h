@@ -201,6 +201,25 @@ int b200s_process_pair(b200s_handle* h, const void* left, const void* right, con
 int b200s_set_graph_mode(b200s_handle* h, int on);
 uint64_t b200s_graph_replays(const b200s_handle* h);
 
+/* ---- several GPUs inside one process (the nodelet case): one handle per GPU, frames sharded round-robin ------------ */
+/* Independent stereo frames need no exchange between GPUs: frame k runs on GPU k mod N in slot
+ * (k div N) mod slots_per_gpu.  Every call only enqueues work, so a single host thread (the reference's one callback
+ * thread, src/StereoProcessor.h:92) keeps all GPUs busy.  devices = NULL selects ordinals 0..n_gpus-1. */
+typedef struct b200s_pool b200s_pool;
+int b200s_pool_create(int n_gpus, const int* devices, int slots_per_gpu, int rows, int cols, b200s_pool** out);
+int b200s_pool_destroy(b200s_pool* p);
+int b200s_pool_size(const b200s_pool* p);
+b200s_handle* b200s_pool_handle(b200s_pool* p, int gpu);                       /* for per-GPU calls of the API above */
+const char* b200s_pool_last_error_string(const b200s_pool* p);
+int b200s_pool_set_calibration(b200s_pool* p, const b200s_caminfo* left, const b200s_caminfo* right);   /* all GPUs */
+int b200s_pool_set_params(b200s_pool* p, const b200s_params* prm);                                      /* all GPUs */
+/* waits for the previous frame of the chosen slot, then enqueues this one; *gpu / *slot (optional) tell where it went.
+ * left/right/io follow b200s_process_pair_async; device pointers must belong to that GPU. */
+int b200s_pool_submit(b200s_pool* p, uint64_t frame_index, const void* left, const void* right, const b200s_frame_io* io,
+                      int* gpu, int* slot);
+int b200s_pool_wait(b200s_pool* p, int gpu, int slot);
+int b200s_pool_wait_all(b200s_pool* p);
+
 /* Device-side timing of a batch of frames spread over the slots (CUDA events on the slot streams): begin() syncs
  * the device, records a start event and makes every slot stream wait on it; end() records one event per slot
  * stream, waits for all of them and returns the longest start->end span in ms. */

@@ -5,4 +5,4 @@ Python host-side mirror of gpuimageproc::GpuStereoProcessor.  There is no CPU fa
 """
 from . import _capi  # noqa: F401
 from .processor import *  # noqa: F401,F403
-from .processor import GpuStereoProcessor  # noqa: F401
+from .processor import GpuStereoProcessor, GpuStereoPool  # noqa: F401

@@ -96,6 +96,16 @@ SYMBOLS = {
     "b200s_enable_timing": (C.c_int, [H, C.c_int]),
     "b200s_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "b200s_host_free": (C.c_int, [C.c_void_p]),
+    "b200s_pool_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "b200s_pool_destroy": (C.c_int, [C.c_void_p]),
+    "b200s_pool_size": (C.c_int, [C.c_void_p]),
+    "b200s_pool_handle": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "b200s_pool_last_error_string": (C.c_char_p, [C.c_void_p]),
+    "b200s_pool_set_calibration": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200s_pool_set_params": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200s_pool_submit": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "b200s_pool_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "b200s_pool_wait_all": (C.c_int, [C.c_void_p]),
     "b200s_set_graph_mode": (C.c_int, [H, C.c_int]),
     "b200s_graph_replays": (C.c_uint64, [H]),
     "b200s_int_peak": (C.c_int, [H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -1130,6 +1130,110 @@ int b200s_process_pair(b200s_handle* h, const void* left, const void* right, con
     return b200s_wait_slot(h, 0);
 }
 
+// ---- multi-GPU pool: one handle (stream set, slots, calibration, parameters) per GPU inside one process ----------
+// Independent stereo frames shard over the GPUs with no exchange step: frame k -> GPU k mod N, slot
+// (k div N) mod S.  All calls only enqueue work, so one host thread drives every GPU; with graph replay a submit is
+// two copies and one graph launch.
+struct b200s_pool {
+    std::vector<b200s_handle*> h;
+    int slots = 0;
+    std::string err;
+};
+
+int b200s_pool_create(int n_gpus, const int* devices, int slots_per_gpu, int rows, int cols, b200s_pool** out)
+{
+    if (!out || n_gpus < 1 || n_gpus > 64 || slots_per_gpu < 1) return B200S_EINVAL;
+    b200s_pool* p = new b200s_pool;
+    p->slots = slots_per_gpu;
+    for (int i = 0; i < n_gpus; ++i) {
+        b200s_handle* h = nullptr;
+        int rc = b200s_create(devices ? devices[i] : i, &h);
+        if (rc == B200S_OK) {
+            p->h.push_back(h);
+            rc = b200s_configure_slots(h, slots_per_gpu, rows, cols);
+        }
+        if (rc != B200S_OK) {
+            for (b200s_handle* q : p->h) b200s_destroy(q);
+            delete p;
+            return rc;
+        }
+    }
+    *out = p;
+    return B200S_OK;
+}
+
+int b200s_pool_destroy(b200s_pool* p)
+{
+    if (!p) return B200S_OK;
+    for (b200s_handle* h : p->h) b200s_destroy(h);
+    delete p;
+    return B200S_OK;
+}
+
+int b200s_pool_size(const b200s_pool* p) { return p ? (int)p->h.size() : 0; }
+b200s_handle* b200s_pool_handle(b200s_pool* p, int gpu) { return (p && gpu >= 0 && gpu < (int)p->h.size()) ? p->h[gpu] : nullptr; }
+const char* b200s_pool_last_error_string(const b200s_pool* p) { return p ? p->err.c_str() : "null pool"; }
+
+extern "C++" {
+namespace {
+template <class F>
+int pool_each(b200s_pool* p, F f)
+{
+    if (!p) return B200S_EINVAL;
+    for (b200s_handle* h : p->h) {
+        int rc = f(h);
+        if (rc != B200S_OK) { p->err = h->err; return rc; }
+    }
+    return B200S_OK;
+}
+}  // namespace
+}
+
+int b200s_pool_set_calibration(b200s_pool* p, const b200s_caminfo* l, const b200s_caminfo* r)
+{
+    return pool_each(p, [&](b200s_handle* h) { return b200s_set_calibration(h, l, r); });
+}
+
+int b200s_pool_set_params(b200s_pool* p, const b200s_params* prm)
+{
+    return pool_each(p, [&](b200s_handle* h) { return b200s_set_params(h, prm); });
+}
+
+int b200s_pool_submit(b200s_pool* p, uint64_t frame_index, const void* left, const void* right, const b200s_frame_io* io, int* gpu, int* slot)
+{
+    if (!p || p->h.empty()) return B200S_EINVAL;
+    const int n = (int)p->h.size();
+    const int g = (int)(frame_index % (uint64_t)n), s = (int)((frame_index / (uint64_t)n) % (uint64_t)p->slots);
+    if (gpu) *gpu = g;
+    if (slot) *slot = s;
+    b200s_handle* h = p->h[g];
+    // the slot's previous frame (and the caller's output buffers for it) must be complete before it is reused
+    int rc = b200s_wait_slot(h, s);
+    if (rc == B200S_OK) rc = b200s_process_pair_async(h, s, left, right, io);
+    if (rc != B200S_OK) p->err = h->err;
+    return rc;
+}
+
+int b200s_pool_wait(b200s_pool* p, int gpu, int slot)
+{
+    b200s_handle* h = b200s_pool_handle(p, gpu);
+    if (!h) return B200S_EINVAL;
+    int rc = b200s_wait_slot(h, slot);
+    if (rc != B200S_OK) p->err = h->err;
+    return rc;
+}
+
+int b200s_pool_wait_all(b200s_pool* p)
+{
+    return pool_each(p, [&](b200s_handle* h) {
+        for (int s = 0; s < (int)h->slots.size(); ++s) {
+            int rc = b200s_wait_slot(h, s);
+            if (rc != B200S_OK) return rc;
+        }
+        return (int)B200S_OK;
+    });
+}
+
 // ---- batch timing: one start event all slot streams wait on, one end event per slot stream ----------------
 int b200s_batch_begin(b200s_handle* h)
 {

@@ -294,14 +294,15 @@ class GpuStereoProcessor(object):
     def getMaxSpeckleDiff(self): return self._p.speckle_range / 16.0
     def setMaxSpeckleDiff(self, maxSpeckleDiff): self._p.speckle_range = int(round(float(maxSpeckleDiff) * 16))  # integer-disparity units
 
+    _PARAM_NAMES = dict(minDisparity="min_disparity", numDisparities="num_disparities", blockSize="block_size",
+                        preFilterType="pre_filter_type", preFilterSize="pre_filter_size", preFilterCap="pre_filter_cap",
+                        textureThreshold="texture_threshold", uniquenessRatio="uniqueness_ratio",
+                        speckleWindowSize="speckle_window_size", speckleRange="speckle_range", disp12MaxDiff="disp12_max_diff")
+
     def setParams(self, **kw):
         """Bulk setter with cv::StereoBM names: numDisparities, blockSize, minDisparity, preFilterType, ..."""
-        m = dict(minDisparity="min_disparity", numDisparities="num_disparities", blockSize="block_size",
-                 preFilterType="pre_filter_type", preFilterSize="pre_filter_size", preFilterCap="pre_filter_cap",
-                 textureThreshold="texture_threshold", uniquenessRatio="uniqueness_ratio",
-                 speckleWindowSize="speckle_window_size", speckleRange="speckle_range", disp12MaxDiff="disp12_max_diff")
         for k, v in kw.items():
-            setattr(self._p, m[k], int(v))
+            setattr(self._p, self._PARAM_NAMES[k], int(v))
 
     def getParams(self):
         return {n: getattr(self._p, n) for n, _ in self._p._fields_}
@@ -397,3 +398,54 @@ class GpuStereoProcessor(object):
         ops, mhz = C.c_double(), C.c_double()
         self._ck(self._lib.b200s_int_peak(self._h, int(which), C.byref(ops), C.byref(mhz)))
         return ops.value, mhz.value
+
+
+class GpuStereoPool(object):
+    """Several GPUs inside one process (b200s_pool_*): one GpuStereoProcessor-equivalent handle per GPU, independent
+    frames sharded round-robin (frame k -> GPU k mod N, slot (k // N) mod slots), no exchange between GPUs."""
+
+    def __init__(self, n_gpus, rows, cols, slots_per_gpu=2, devices=None):
+        self._lib = capi.load()
+        self._p = C.c_void_p()
+        dev = (C.c_int * n_gpus)(*devices) if devices is not None else None
+        rc = self._lib.b200s_pool_create(int(n_gpus), dev, int(slots_per_gpu), int(rows), int(cols), C.byref(self._p))
+        if rc != 0:
+            raise capi.B200StereoError(rc, "b200s_pool_create failed")
+        self.n_gpus, self.slots = int(n_gpus), int(slots_per_gpu)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise capi.B200StereoError(rc, self._lib.b200s_pool_last_error_string(self._p).decode())
+
+    def initStereoModel(self, left, right):
+        l, r = _caminfo(left), _caminfo(right)
+        self._ck(self._lib.b200s_pool_set_calibration(self._p, C.byref(l), C.byref(r)))
+
+    def setParams(self, **kw):
+        prm = capi.Params()
+        self._lib.b200s_default_params(C.byref(prm))
+        for k, v in kw.items():
+            setattr(prm, GpuStereoProcessor._PARAM_NAMES[k], int(v))
+        self._ck(self._lib.b200s_pool_set_params(self._p, C.byref(prm)))
+
+    def submit(self, frame_index, left_ptr, right_ptr, io):
+        g, s = C.c_int(), C.c_int()
+        self._ck(self._lib.b200s_pool_submit(self._p, int(frame_index), left_ptr, right_ptr, C.byref(io), C.byref(g), C.byref(s)))
+        return g.value, s.value
+
+    def wait(self, gpu, slot):
+        self._ck(self._lib.b200s_pool_wait(self._p, int(gpu), int(slot)))
+
+    def waitAll(self):
+        self._ck(self._lib.b200s_pool_wait_all(self._p))
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self._lib.b200s_pool_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -338,6 +338,62 @@ def test_graph_replay_gives_identical_frames():
     proc.close()
 
 
+def test_multi_gpu_pool_shards_frames():
+    """b200s_pool_*: frames round-robin over every visible GPU (1 on the test box, N with gpurun --gpus N), each result
+    equal to the oracle chain of its own frame."""
+    import torch
+    m = _gpu()
+    cap = m._capi
+    n_gpus = max(1, min(torch.cuda.device_count(), 8))
+    W, H, nd, b = 640, 360, 64, 11
+    slots = 2
+    pool = m.GpuStereoPool(n_gpus, H, W, slots_per_gpu=slots)
+    frames = [synth.synth_raw_pair(W, H, nd, seed=6000 + i) for i in range(3 * n_gpus * slots)]
+    cal = frames[0][2]
+    pool.initStereoModel(_caminfo(cal["left"], W, H), _caminfo(cal["right"], W, H))
+    p = O.BMParams(numDisparities=nd, blockSize=b)
+    pool.setParams(**p.as_dict())
+    helper = m.GpuStereoProcessor(0)          # only for pinned allocations
+    n = W * H
+    bufs = {}
+    for g in range(n_gpus):
+        for s in range(slots):
+            io = cap.FrameIO()
+            io.want, io.rectify = cap.OUT_DISPARITY16, 1
+            d16, io.disparity16 = helper.hostAlloc(n * 2)
+            bufs[(g, s)] = (io, d16)
+    pending = {}
+    seen_gpus = set()
+
+    def check(key):
+        k = pending.pop(key)
+        Lr, Rr, _ = frames[k]
+        rl, rr = O.rectify(Lr, **cal["left"]), O.rectify(Rr, **cal["right"])
+        want = O.stereobm_compute(rl, rr, p)
+        got = bufs[key][1].view(np.int16).reshape(H, W)
+        assert np.array_equal(got, want), (k, key)
+
+    for k, (Lr, Rr, _) in enumerate(frames):
+        g, s = k % n_gpus, (k // n_gpus) % slots
+        if (g, s) in pending:
+            pool.wait(g, s)
+            check((g, s))
+        L8, R8 = np.ascontiguousarray(Lr), np.ascontiguousarray(Rr)
+        got_g, got_s = pool.submit(k, L8.ctypes.data, R8.ctypes.data, bufs[(g, s)][0])
+        assert (got_g, got_s) == (g, s)
+        pool.wait(g, s)                        # pageable host inputs: keep them alive until the copy is done
+        pending[(g, s)] = k
+        seen_gpus.add(got_g)
+    pool.waitAll()
+    for key in list(pending):
+        check(key)
+    assert seen_gpus == set(range(n_gpus))
+    for io, d16 in bufs.values():
+        helper.hostFree(io.disparity16)
+    helper.close()
+    pool.close()
+
+
 # ---- error behaviour ----------------------------------------------------------------------------------------
 def test_errors():
     m = _gpu()
