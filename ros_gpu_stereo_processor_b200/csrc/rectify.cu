@@ -112,7 +112,7 @@ template <bool FLY>
 __global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSide sr, int sW, int sH, size_t ppitch,
                                                              int W, int H, int cap)
 {
-    __shared__ uint8_t tile[FTY + 2][FTX + 2 + 2];
+    __shared__ __align__(16) uint8_t tile[FTY + 2][FTX + 2 + 2];
     const RectSide& S = blockIdx.z ? sr : sl;
     const uint8_t* __restrict__ src = S.src;
     const int x0 = blockIdx.x * FTX, y0 = blockIdx.y * FTY;
@@ -133,44 +133,64 @@ __global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSi
 #pragma unroll
     for (int k = 0; k < FT_PER; ++k) {
         const int X0 = sat16(m[k].x >> 5), Y0 = sat16(m[k].y >> 5);
-        s00[k] = ok[k] ? fetch1(src, sW, sH, X0, Y0, 1, 0) : 0;
-        s01[k] = ok[k] ? fetch1(src, sW, sH, X0 + 1, Y0, 1, 0) : 0;
-        s10[k] = ok[k] ? fetch1(src, sW, sH, X0, Y0 + 1, 1, 0) : 0;
-        s11[k] = ok[k] ? fetch1(src, sW, sH, X0 + 1, Y0 + 1, 1, 0) : 0;
+        s00[k] = s01[k] = s10[k] = s11[k] = 0;
+        if (ok[k]) {
+            if ((unsigned)X0 < (unsigned)(sW - 1) && (unsigned)Y0 < (unsigned)(sH - 1)) {
+                // the whole 2x2 footprint is inside the source image (the common case): no per-tap border test
+                const uint8_t* p = src + (size_t)Y0 * sW + X0;
+                s00[k] = __ldg(p); s01[k] = __ldg(p + 1); s10[k] = __ldg(p + sW); s11[k] = __ldg(p + sW + 1);
+            } else {
+                s00[k] = fetch1(src, sW, sH, X0, Y0, 1, 0);
+                s01[k] = fetch1(src, sW, sH, X0 + 1, Y0, 1, 0);
+                s10[k] = fetch1(src, sW, sH, X0, Y0 + 1, 1, 0);
+                s11[k] = fetch1(src, sW, sH, X0 + 1, Y0 + 1, 1, 0);
+            }
+        }
     }
 #pragma unroll
     for (int k = 0; k < FT_PER; ++k) {
         const int i = threadIdx.x + 256 * k;
         if (i >= FT_N) continue;
         const int ty = i / (FTX + 2), tx = i - ty * (FTX + 2);
-        const int x = x0 + tx - 1, y = y0 + ty - 1;
         const int a = m[k].x & 31, b = m[k].y & 31;
-        const int acc = (32 - a) * (32 - b) * s00[k] + a * (32 - b) * s01[k] + (32 - a) * b * s10[k] + a * b * s11[k];
-        const int v = ok[k] ? (acc + 512) >> 10 : 0;
-        tile[ty][tx] = (uint8_t)v;
+        // (32-a)(32-b) s00 + a(32-b) s01 + (32-a) b s10 + a b s11, factored (exact in integers)
+        const int top = 32 * s00[k] + a * (s01[k] - s00[k]), bot = 32 * s10[k] + a * (s11[k] - s10[k]);
+        const int acc = 32 * top + b * (bot - top);
+        tile[ty][tx] = (uint8_t)(ok[k] ? (acc + 512) >> 10 : 0);
     }
     __syncthreads();
-    // each thread finishes 4 adjacent pixels: one 32-bit store to the (pitched) prefiltered plane, and one to the
-    // rectified plane when its rows are word aligned
+    // each thread finishes 4 adjacent pixels with packed 16-bit arithmetic: per tile row two aligned words give the six
+    // bytes x-1 .. x+4; one 32-bit store to the (pitched) prefiltered plane and one to the rectified plane
     {
         const int ty = threadIdx.x >> 4, tx = (threadIdx.x & 15) * 4;
         const int x = x0 + tx, y = y0 + ty;
         if (x < W && y < H) {
             const bool last_odd = (H & 1) && (y == H - 1);
-            uint32_t pre4 = 0, rect4 = 0;
+            uint32_t de = 0, dO = 0, rect4 = 0;     // Sobel sums of pixels (0, 2) and (1, 3) as s16x2
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int xi = x + i;
-                int out = cap;
-                if (xi > 0 && xi < W - 1 && !last_odd && H > 1) {
-                    int d0 = (int)tile[ty][tx + i + 2] - (int)tile[ty][tx + i];
-                    int d1 = (int)tile[ty + 1][tx + i + 2] - (int)tile[ty + 1][tx + i];
-                    int d2 = (int)tile[ty + 2][tx + i + 2] - (int)tile[ty + 2][tx + i];
-                    int v = d0 + 2 * d1 + d2;
-                    out = min(max(v, -cap), cap) + cap;
+            for (int rr = 0; rr < 3; ++rr) {
+                const uint32_t w0 = *(const uint32_t*)&tile[ty + rr][tx], w1 = *(const uint32_t*)&tile[ty + rr][tx + 4];
+                const uint32_t hi = __funnelshift_r(w0, w1, 16);                      // bytes x+1 .. x+4
+                const uint32_t le = w0 & 0x00ff00ffu, lo = (w0 >> 8) & 0x00ff00ffu;    // x-1, x+1 | x, x+2
+                const uint32_t he = hi & 0x00ff00ffu, ho = (hi >> 8) & 0x00ff00ffu;    // x+1, x+3 | x+2, x+4
+                uint32_t d_e = __vsub2(he, le), d_o = __vsub2(ho, lo);                 // pixels 0, 2 | pixels 1, 3
+                if (rr == 1) {
+                    d_e = __vadd2(d_e, d_e);
+                    d_o = __vadd2(d_o, d_o);
+                    rect4 = __funnelshift_r(w0, w1, 8);                                // bytes x .. x+3 of the centre row
                 }
-                pre4 |= (uint32_t)out << (8 * i);
-                rect4 |= (uint32_t)tile[ty + 1][tx + i + 1] << (8 * i);
+                de = __vadd2(de, d_e);
+                dO = __vadd2(dO, d_o);
+            }
+            const uint32_t capw = (uint32_t)cap * 0x00010001u, ncapw = (uint32_t)(-cap & 0xffff) * 0x00010001u;
+            de = __vadd2(__vmins2(__vmaxs2(de, ncapw), capw), capw);
+            dO = __vadd2(__vmins2(__vmaxs2(dO, ncapw), capw), capw);
+            uint32_t pre4 = __byte_perm(de, dO, 0x6240);                               // p0 p1 p2 p3
+            if (last_odd || H <= 1) pre4 = (uint32_t)cap * 0x01010101u;
+            else if (x == 0 || x + 3 >= W - 1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (x + i == 0 || x + i >= W - 1) pre4 = (pre4 & ~(0xffu << (8 * i))) | ((uint32_t)cap << (8 * i));
             }
             uint8_t* pp = S.pre + (size_t)y * ppitch + x;
             uint8_t* rp = S.rect + (size_t)y * W + x;
