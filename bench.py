@@ -40,6 +40,9 @@ CONFIGS = {
     "C3": dict(W=1280, H=720, nd=128, block=15, rectify=True, speckle=(0, 0), idx=3),
     "C4": dict(W=1920, H=1080, nd=256, block=11, rectify=True, speckle=(0, 0), idx=4),
     "C5": dict(W=3840, H=2160, nd=256, block=11, rectify=True, speckle=(0, 0), idx=5),
+    # not a BASELINE config: C4 with the reference's default speckle filter on (GPU.cfg max_speckle_size 800,
+    # max_speckle_diff 5 disparities = 80 raw units), i.e. what StereoProcessor::imageCb runs out of the box
+    "C4s": dict(W=1920, H=1080, nd=256, block=11, rectify=True, speckle=(800, 80), idx=4),
 }
 FRAMES_PER_STEP = 16
 N_SLOTS = 4

@@ -241,40 +241,51 @@ __global__ void __launch_bounds__(256) ccl_border_kernel(const int16_t* __restri
     uf_union(L, i, j);
 }
 
-// read-only root lookup: the forest is final here, and no thread may write L while others still walk it
-// (a stale path-halving store could otherwise replace an already flattened label by a non-root ancestor)
-__device__ __forceinline__ int uf_root(const int* __restrict__ L, int i)
-{
-    int p = L[i];
-    while (p != i) { i = p; p = L[i]; }
-    return i;
-}
-
 // ---- stage 3: every tile-local root (sz > 0) that was hooked under another root adds its count to the global root
 // and is pointed straight at it, so that afterwards L[L[i]] is the global root of any pixel i ----------------------
 __global__ void __launch_bounds__(256) ccl_merge_counts_kernel(int* __restrict__ L, int* __restrict__ sz, int n)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int c = sz[i];
-    if (c <= 0) return;
-    int p = L[i];
-    if (p == i) return;                       // a global root keeps its own count
-    int g = p;
-    for (int q = L[g]; q != g; q = L[g]) g = q;
-    atomicAdd(&sz[g], c);                     // only global roots ever receive additions
-    L[i] = g;                                 // concurrent walkers see the old parent or the root: both are ancestors
+    // four pixels per thread (one 16-byte load of the counts): roots are sparse, most threads stop here
+    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= n) return;
+    int c4[4] = {0, 0, 0, 0};
+    if (i0 + 4 <= n) {
+        const int4 q = *(const int4*)(sz + i0);
+        c4[0] = q.x; c4[1] = q.y; c4[2] = q.z; c4[3] = q.w;
+    } else {
+        for (int k = 0; i0 + k < n; ++k) c4[k] = sz[i0 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c4[k], i = i0 + k;
+        if (c <= 0) continue;
+        const int p = L[i];
+        if (p == i) continue;                     // a global root keeps its own count
+        int g = p;
+        for (int q = L[g]; q != g; q = L[g]) g = q;
+        atomicAdd(&sz[g], c);                     // only global roots ever receive additions
+        L[i] = g;                                 // concurrent walkers see the old parent or the root: both are ancestors
+    }
 }
 
 __global__ void __launch_bounds__(256) ccl_apply_kernel(int16_t* __restrict__ img, const int* __restrict__ L,
                                                         const int* __restrict__ sz, int n, int newVal, int maxSize)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int p = L[i];                        // a tile-local root (parents are always tile-local roots)
-    if (p < 0) return;
-    const int g = L[p];                        // its global root after stage 3
-    if (sz[g] <= maxSize) img[i] = (int16_t)newVal;
+    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= n) return;
+    int p4[4] = {-1, -1, -1, -1};
+    if (i0 + 4 <= n) {
+        const int4 q = *(const int4*)(L + i0);    // tile-local roots (parents are always tile-local roots)
+        p4[0] = q.x; p4[1] = q.y; p4[2] = q.z; p4[3] = q.w;
+    } else {
+        for (int k = 0; i0 + k < n; ++k) p4[k] = L[i0 + k];
+    }
+    int g4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g4[k] = p4[k] >= 0 ? L[p4[k]] : -1;          // global roots after stage 3
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (g4[k] >= 0 && sz[g4[k]] <= maxSize) img[i0 + k] = (int16_t)newVal;
 }
 
 static inline dim3 grid2d(int W, int H) { return dim3((W + 31) / 32, (H + 7) / 8); }
@@ -302,15 +313,15 @@ int launch_filter_speckles(int16_t* img, int W, int H, int newVal, int maxSize, 
 {
     int n = W * H;
     int* L = scratch;
-    int* sz = scratch + n;
-    int nb = (n + 255) / 256;
+    int* sz = scratch + (((size_t)n + 3) & ~(size_t)3);   // 16-byte aligned like L (the scratch holds 3n ints)
     ccl_local_kernel<<<dim3((W + CTX - 1) / CTX, (H + CTY - 1) / CTY), 256, 0, st>>>(img, L, sz, W, H, newVal, maxDiff);
     {
         const long long nbp = (long long)((W - 1) / CTX) * H + (long long)((H - 1) / CTY) * W;
         if (nbp > 0) ccl_border_kernel<<<(unsigned)((nbp + 255) / 256), 256, 0, st>>>(img, L, W, H, newVal, maxDiff);
     }
-    ccl_merge_counts_kernel<<<nb, 256, 0, st>>>(L, sz, n);
-    ccl_apply_kernel<<<nb, 256, 0, st>>>(img, L, sz, n, newVal, maxSize);
+    const int nb4 = (n + 1023) / 1024;
+    ccl_merge_counts_kernel<<<nb4, 256, 0, st>>>(L, sz, n);
+    ccl_apply_kernel<<<nb4, 256, 0, st>>>(img, L, sz, n, newVal, maxSize);
     return 4;
 }
 
