@@ -333,6 +333,21 @@ def test_graph_replay_gives_identical_frames():
     r1 = proc.graphReplays()
     check(p2, 1)
     assert proc.graphReplays() == r1
+    # pageable destination buffers reused across frames: whether or not the driver lets such copies into a capture, the
+    # results must stay correct (the library falls back to plain launches when the capture is refused)
+    proc.setGraphMode(True)
+    io2 = cap.FrameIO()
+    io2.want, io2.rectify = cap.OUT_DISPARITY16, 1
+    dpage = np.empty((H, W), np.int16)
+    io2.disparity16 = dpage.ctypes.data
+    Lr, Rr, _ = frames[1]
+    rl, rr = O.rectify(Lr, **cal["left"]), O.rectify(Rr, **cal["right"])
+    want1 = O.stereobm_compute(rl, rr, p2)
+    for it in range(4):
+        dpage[:] = 0
+        proc.processPairAsync(0, np.ascontiguousarray(Lr).ctypes.data, np.ascontiguousarray(Rr).ctypes.data, io2)
+        proc.waitSlot(0)
+        assert np.array_equal(dpage, want1), it
     for io, d16, pc in outs:
         proc.hostFree(io.disparity16); proc.hostFree(io.pointcloud2)
     proc.close()
