@@ -192,6 +192,9 @@ typedef struct {
 int b200s_configure_slots(b200s_handle* h, int n_slots, int rows, int cols);
 int b200s_process_pair_async(b200s_handle* h, int slot, const void* left, const void* right, const b200s_frame_io* io);
 int b200s_wait_slot(b200s_handle* h, int slot);
+/* non-blocking: *done = 1 when the slot's last frame (outputs included) is complete; the polled counterpart of the
+ * reference's stream callback that publishes a message (src/GpuSenderIfc.cpp:13-26) */
+int b200s_poll_slot(b200s_handle* h, int slot, int* done);
 int b200s_slot_device_ptr(b200s_handle* h, int slot, uint32_t which /* one B200S_OUT_* */, void** dptr, size_t* bytes);
 /* synchronous convenience: slot 0, process + wait */
 int b200s_process_pair(b200s_handle* h, const void* left, const void* right, const b200s_frame_io* io);

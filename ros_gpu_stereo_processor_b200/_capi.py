@@ -106,6 +106,7 @@ SYMBOLS = {
     "b200s_pool_submit": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b200s_pool_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "b200s_pool_wait_all": (C.c_int, [C.c_void_p]),
+    "b200s_poll_slot": (C.c_int, [H, C.c_int, C.POINTER(C.c_int)]),
     "b200s_set_graph_mode": (C.c_int, [H, C.c_int]),
     "b200s_graph_replays": (C.c_uint64, [H]),
     "b200s_int_peak": (C.c_int, [H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

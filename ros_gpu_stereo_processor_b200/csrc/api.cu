@@ -1098,6 +1098,18 @@ int b200s_wait_slot(b200s_handle* h, int slot)
     return B200S_OK;
 }
 
+// non-blocking completion test of a slot's last frame (the reference publishes from a stream callback, GpuSenderIfc.cpp:13-26)
+int b200s_poll_slot(b200s_handle* h, int slot, int* done)
+{
+    if (!h || !done) return B200S_EINVAL;
+    if (slot < 0 || slot >= (int)h->slots.size()) return fail(h, B200S_EINVAL, "slot out of range");
+    DeviceGuard g(h->device);
+    cudaError_t e = cudaEventQuery(h->slots[slot].ev_done);
+    if (e != cudaSuccess && e != cudaErrorNotReady) return fail(h, B200S_ECUDA, cudaGetErrorString(e));
+    *done = e == cudaSuccess;
+    return B200S_OK;
+}
+
 int b200s_slot_device_ptr(b200s_handle* h, int slot, uint32_t which, void** dptr, size_t* bytes)
 {
     if (!h || !dptr) return B200S_EINVAL;

@@ -323,6 +323,12 @@ class GpuStereoProcessor(object):
     def waitSlot(self, slot):
         self._ck(self._lib.b200s_wait_slot(self._h, int(slot)))
 
+    def slotDone(self, slot):
+        """Non-blocking completion test of the slot's last frame."""
+        d = C.c_int()
+        self._ck(self._lib.b200s_poll_slot(self._h, int(slot), C.byref(d)))
+        return bool(d.value)
+
     def processPair(self, left, right, rectify=True, want=("disparity16",)):
         """Synchronous convenience on slot 0 with host arrays; returns a dict of numpy outputs."""
         L = np.ascontiguousarray(left, np.uint8)
