@@ -609,6 +609,16 @@ def test_cuda_compat_matches_oracle(proc, case):
     proc.setMaxSpeckleSize(0)
 
 
+def test_matcher_random_parameter_sweep():
+    """tools/fuzz_parity.py: random sizes and cv::StereoBM parameter sets (every matcher path) against the oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "30", "2024"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "0 bad" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_block_not_smaller_than_image_is_rejected(proc):
     m = _gpu()
     L, R = synth.synth_pair(64, 21, 16, seed=3)
