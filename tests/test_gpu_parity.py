@@ -619,6 +619,16 @@ def test_matcher_random_parameter_sweep():
     assert out.returncode == 0 and "0 bad" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+def test_speckle_random_pattern_sweep():
+    """tools/fuzz_speckle.py: noise, ramps with holes, one-pixel stripes, rectangles, snakes across many tiles, rings."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_speckle.py"), "40", "11"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "0 bad" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_block_not_smaller_than_image_is_rejected(proc):
     m = _gpu()
     L, R = synth.synth_pair(64, 21, 16, seed=3)
