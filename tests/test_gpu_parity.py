@@ -629,6 +629,16 @@ def test_speckle_random_pattern_sweep():
     assert out.returncode == 0 and "0 bad" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+def test_chain_random_calibration_sweep():
+    """tools/fuzz_chain.py: random plumb_bob / rational calibrations, cached and on-the-fly maps, whole chain vs the oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_chain.py"), "16", "21"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "0 bad" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_block_not_smaller_than_image_is_rejected(proc):
     m = _gpu()
     L, R = synth.synth_pair(64, 21, 16, seed=3)

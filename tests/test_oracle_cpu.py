@@ -169,3 +169,29 @@ def test_cuda_textureness_is_a_window_sum_of_abs_sobel():
     p = np.pad(img.astype(np.int64), 1, mode="edge")
     s = np.abs(-p[:-2, :-2] + p[:-2, 2:] - 2 * p[1:-1, :-2] + 2 * p[1:-1, 2:] - p[2:, :-2] + p[2:, 2:])
     assert m[20, 25] == (s[16:25, 21:30].sum() < 3 * 81)
+
+
+def test_rectify_matches_cv2_random_calibrations():
+    """Random plumb_bob / rational_polynomial calibrations (the sweep tools/fuzz_chain.py feeds to the GPU): the C
+    restatement must equal cv2.initUndistortRectifyMap + cv2.remap bit for bit."""
+    import cv2
+    from oracle import cv2_ref as CV
+    rng = np.random.default_rng(5)
+    for case in range(12):
+        W, H = int(rng.integers(160, 700)), int(rng.integers(120, 480))
+        f = float(rng.uniform(0.6, 1.4) * W)
+        K = [f, 0, W / 2 + float(rng.uniform(-15, 15)), 0, f * 1.01, H / 2 + float(rng.uniform(-15, 15)), 0, 0, 1]
+        D = [float(rng.uniform(-0.3, 0.2)), float(rng.uniform(-0.1, 0.15)), float(rng.uniform(-2e-3, 2e-3)),
+             float(rng.uniform(-2e-3, 2e-3)), float(rng.uniform(-0.05, 0.05))]
+        if case % 2:
+            D += [float(rng.uniform(-0.05, 0.05)), float(rng.uniform(-0.02, 0.02)), float(rng.uniform(-0.01, 0.01))]
+        a, b, c = rng.uniform(-0.02, 0.02, 3)
+        Rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+        Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+        Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+        R = (Rz @ Ry @ Rx).ravel().tolist()
+        fp = f * 1.05
+        P = [fp, 0, W / 2 + 3, 0, 0, fp, H / 2 - 2, 0, 0, 0, 1, 0]
+        img = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        m1, m2 = CV.rect_maps(K, D, R, P, W, H)
+        assert np.array_equal(O.rectify(img, K=K, D=D, R=R, P=P), cv2.remap(img, m1, m2, cv2.INTER_LINEAR)), case
