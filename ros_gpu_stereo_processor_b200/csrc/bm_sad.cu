@@ -380,6 +380,55 @@ __global__ void __launch_bounds__(128) bm_generic_cost_kernel(const GenParams P)
     }
 }
 
+// Narrow bands (at most GEN_STRIP_MAXC columns, e.g. the r-wide strips next to the fast rectangle): one thread per
+// (disparity, row march) walks the columns itself, so the horizontal window sum slides (2 terms per further column
+// instead of 2r+1) and the vertical sums of all strip columns stay in registers.
+constexpr int GEN_STRIP_MAXC = 16;
+
+__device__ __forceinline__ int gen_term(const GenParams& P, const uint8_t* __restrict__ lr, const uint8_t* __restrict__ rr, int xp, int k)
+{
+    const int lc = min(max(xp, -P.lofs), P.W - 1 - P.lofs) + P.lofs;
+    const int rc = min(max(xp, -P.rofs), P.W - P.nd - P.rofs) + P.rofs + k;
+    return abs((int)__ldg(lr + lc) - (int)__ldg(rr + rc));
+}
+
+// adds sign * (window sums of row y for the strip columns) to V
+__device__ __forceinline__ void gen_strip_row(const GenParams& P, int y, int k, int ncx, int sign, int (&V)[GEN_STRIP_MAXC])
+{
+    const uint8_t* lr = P.Lp + (size_t)y * P.pitch;
+    const uint8_t* rr = P.Rp + (size_t)y * P.pitch;
+    int s = 0;
+    for (int dx = -P.r; dx <= P.r; ++dx) s += gen_term(P, lr, rr, P.xa + dx, k);
+#pragma unroll
+    for (int c = 0; c < GEN_STRIP_MAXC; ++c) {
+        if (c < ncx) {
+            V[c] += sign * s;
+            if (c + 1 < ncx) s += gen_term(P, lr, rr, P.xa + c + 1 + P.r, k) - gen_term(P, lr, rr, P.xa + c - P.r, k);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) bm_generic_strip_cost_kernel(const GenParams P)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = P.ya + blockIdx.y * P.RCH, y1 = min(y0 + P.RCH, P.yb);
+    if (k >= P.nd || y0 >= y1) return;
+    const int ncx = P.xb - P.xa;
+    int V[GEN_STRIP_MAXC];
+#pragma unroll
+    for (int c = 0; c < GEN_STRIP_MAXC; ++c) V[c] = 0;
+    for (int yy = y0 - P.r; yy <= y0 + P.r; ++yy) gen_strip_row(P, yy, k, ncx, 1, V);
+    for (int y = y0; y < y1; ++y) {
+#pragma unroll
+        for (int c = 0; c < GEN_STRIP_MAXC; ++c)
+            if (c < ncx) P.vol[((size_t)(y - P.ya) * ncx + c) * P.nd + k] = V[c];
+        if (y + 1 < y1) {
+            gen_strip_row(P, y + 1 + P.r, k, ncx, 1, V);
+            gen_strip_row(P, y - P.r, k, ncx, -1, V);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128) bm_generic_winner_kernel(const GenParams P)
 {
     const int ncx = P.xb - P.xa;
@@ -418,6 +467,59 @@ __global__ void __launch_bounds__(128) bm_generic_winner_kernel(const GenParams 
         if (P.cost) P.cost[(size_t)y * P.W + X] = (int16_t)minsad;
     }
     P.disp[(size_t)y * P.W + X] = out;
+}
+
+// Same selection with one warp per pixel (lanes stride over the disparities): the border bands that disp12MaxDiff >= 0
+// needs are only r columns wide, far too few pixels to fill the GPU with one thread each.
+__global__ void __launch_bounds__(256) bm_generic_winner_warp_kernel(const GenParams P)
+{
+    const int ncx = P.xb - P.xa;
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int npx = ncx * (P.yb - P.ya);
+    if (idx >= npx) return;
+    const int y = P.ya + idx / ncx, x = P.xa + idx % ncx;
+    const int* S = P.vol + (size_t)idx * P.nd;
+    const int nd = P.nd;
+    // argmin with the lowest index on ties: key = (sad << 9 | k) would overflow for big windows, so compare pairs
+    int best = INT_MAX, bk = nd;
+    for (int k = lane; k < nd; k += 32) {
+        const int v = S[k];
+        if (v < best) { best = v; bk = k; }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const int ov = __shfl_xor_sync(0xffffffffu, best, d), ok = __shfl_xor_sync(0xffffffffu, bk, d);
+        if (ov < best || (ov == best && ok < bk)) { best = ov; bk = ok; }
+    }
+    const int minsad = best, mind = bk;
+    const int X = x + P.lofs;
+    const int16_t FILTERED = (int16_t)((P.minD - 1) * 16);
+    if (X < 0 || X >= P.W) return;
+    const int b = 2 * P.r + 1;
+    int tsum = 0;
+    for (int t = lane; t < b * b; t += 32) {
+        const int dy = t / b - P.r, dx = t % b - P.r;
+        const int lc = min(max(x + dx, -P.lofs), P.W - 1 - P.lofs) + P.lofs;
+        tsum += abs((int)__ldg(P.Lp + (size_t)(y + dy) * P.pitch + lc) - P.cap);
+    }
+    tsum = __reduce_add_sync(0xffffffffu, tsum);
+    bool ok = tsum >= P.texThr;
+    if (ok && P.uniq > 0) {
+        const int thr = minsad + (minsad * P.uniq / 100);
+        bool hit = false;
+        for (int k = lane; k < nd; k += 32)
+            if ((k < mind - 1 || k > mind + 1) && S[k] <= thr) hit = true;
+        if (__any_sync(0xffffffffu, hit)) ok = false;
+    }
+    if (lane == 0) {
+        int16_t out = FILTERED;
+        if (ok) {
+            const int p = S[mind + 1 < nd ? mind + 1 : nd - 2], n = S[mind > 0 ? mind - 1 : 1];
+            out = subpixel_disp(minsad, mind, p, n, nd, P.minD);
+            if (P.cost) P.cost[(size_t)y * P.W + X] = (int16_t)minsad;
+        }
+        P.disp[(size_t)y * P.W + X] = out;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -467,16 +569,21 @@ static int run_generic(const GenPlanes& pl, int W, int H, const BMConfig& cfg, c
     P.Lp = pl.Lp; P.Rp = pl.Rp; P.pitch = pl.pitch; P.W = W; P.H = H; P.nd = cfg.nd; P.minD = cfg.minD; P.r = g.r; P.cap = cfg.cap;
     P.texThr = cfg.textureThreshold; P.uniq = cfg.uniquenessRatio; P.lofs = g.lofs; P.rofs = g.rofs;
     P.xa = xa; P.xb = xb; P.vol = sc->vol; P.disp = disp; P.cost = cost;
-    P.RCH = 32;
+    // rows per thread-march: narrow bands (the r-wide strips next to the fast rectangle) would leave most SMs idle with
+    // long marches, so they get short ones (more threads, a few more warm-up rows each)
+    const long long warps_at_32 = (long long)((cfg.nd + 31) / 32) * ncx * ((g.roiY1 - g.roiY0 + 31) / 32);
+    P.RCH = warps_at_32 >= 8192 ? 32 : (warps_at_32 >= 4096 ? 16 : 8);
     for (int ya = g.roiY0; ya < g.roiY1; ya += rows_per_chunk) {
         P.ya = ya;
         P.yb = std::min(g.roiY1, ya + rows_per_chunk);
         int kt = std::min(128, cfg.nd);
         dim3 grid((cfg.nd + kt - 1) / kt, ncx, (P.yb - P.ya + P.RCH - 1) / P.RCH);
         // gridDim.y/z limits (65535) are far above any supported image size
-        bm_generic_cost_kernel<<<grid, kt, 0, st>>>(P);
+        if (ncx <= GEN_STRIP_MAXC) bm_generic_strip_cost_kernel<<<dim3(grid.x, grid.z), kt, 0, st>>>(P);
+        else bm_generic_cost_kernel<<<grid, kt, 0, st>>>(P);
         int npx = ncx * (P.yb - P.ya);
-        bm_generic_winner_kernel<<<(npx + 127) / 128, 128, 0, st>>>(P);
+        if (npx < 262144) bm_generic_winner_warp_kernel<<<(npx + 7) / 8, 256, 0, st>>>(P);
+        else bm_generic_winner_kernel<<<(npx + 127) / 128, 128, 0, st>>>(P);
         launches += 2;
     }
     return launches;
