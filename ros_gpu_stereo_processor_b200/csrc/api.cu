@@ -328,9 +328,14 @@ int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, 
             h->launches += launch_prefilter_xsobel(L, pl, pitch, cols, rows, p.pre_filter_cap, st);
             h->launches += launch_prefilter_xsobel(R, pr, pitch, cols, rows, p.pre_filter_cap, st);
         } else {
-            if (w.normtmp.ensure(n * sizeof(int))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (prefilter scratch)");
-            h->launches += launch_prefilter_norm(L, pl, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, (int*)w.normtmp.p, st);
-            h->launches += launch_prefilter_norm(R, pr, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, (int*)w.normtmp.p, st);
+            const int one = launch_norm_prefilter_pair(L, R, cols, rows, false, nullptr, nullptr, h->cam[0].cm, h->cam[1].cm, nullptr, nullptr,
+                                                       pl, pr, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, st);
+            h->launches += one;
+            if (!one) {     // preFilterSize > 21: two passes through a scratch plane
+                if (w.normtmp.ensure(n * sizeof(int))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (prefilter scratch)");
+                h->launches += launch_prefilter_norm(L, pl, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, (int*)w.normtmp.p, st);
+                h->launches += launch_prefilter_norm(R, pr, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, (int*)w.normtmp.p, st);
+            }
         }
     }
     // the matcher always reads the pitched, slack-padded prefiltered planes of this Work
@@ -954,8 +959,21 @@ int run_frame_chain(b200s_handle* h, Work& w, const b200s_frame_io* io, const ui
                                                       (uint8_t*)w.preR.p + PLANE_LEAD, pitch, cols, rows, h->prm.pre_filter_cap, st);
             prefiltered = true;
         } else {
-            h->launches += launch_remap(L, cols, rows, 1, mapL, h->cam[0].cm, (uint8_t*)w.rectL.p, cols, rows, st);
-            h->launches += launch_remap(R, cols, rows, 1, mapR, h->cam[1].cm, (uint8_t*)w.rectR.p, cols, rows, st);
+            int one = 0;
+            if (h->prm.pre_filter_size <= 21) {
+                int rc2 = ensure_pre_planes(h, w, rows, cols);
+                if (rc2) return rc2;
+                one = launch_norm_prefilter_pair(L, R, cols, rows, true, mapL, mapR, h->cam[0].cm, h->cam[1].cm, (uint8_t*)w.rectL.p,
+                                                 (uint8_t*)w.rectR.p, (uint8_t*)w.preL.p + PLANE_LEAD, (uint8_t*)w.preR.p + PLANE_LEAD,
+                                                 plane_pitch(cols), cols, rows, h->prm.pre_filter_size, h->prm.pre_filter_cap, st);
+            }
+            if (one) {
+                h->launches += one;
+                prefiltered = true;
+            } else {
+                h->launches += launch_remap(L, cols, rows, 1, mapL, h->cam[0].cm, (uint8_t*)w.rectL.p, cols, rows, st);
+                h->launches += launch_remap(R, cols, rows, 1, mapR, h->cam[1].cm, (uint8_t*)w.rectR.p, cols, rows, st);
+            }
         }
         rl = (const uint8_t*)w.rectL.p;
         rr = (const uint8_t*)w.rectR.p;

@@ -28,6 +28,11 @@ int launch_remap(const uint8_t* src, int sW, int sH, int ch, const int2* map, co
 int launch_rectify_xsobel_pair(const uint8_t* srcL, const uint8_t* srcR, int sW, int sH, const int2* mapL, const int2* mapR,
                                const CamModel& cmL, const CamModel& cmR, uint8_t* rectL, uint8_t* rectR, uint8_t* preL,
                                uint8_t* preR, size_t pre_pitch, int W, int H, int cap, cudaStream_t st);
+// (rectify +) normalised-response prefilter of both sides in one tiled kernel (preFilterSize <= 21; returns 0 otherwise).
+// rectify = false: srcL/srcR are already rectified W x H planes (rect outputs unused)
+int launch_norm_prefilter_pair(const uint8_t* srcL, const uint8_t* srcR, int sW, int sH, bool rectify, const int2* mapL,
+                               const int2* mapR, const CamModel& cmL, const CamModel& cmR, uint8_t* rectL, uint8_t* rectR,
+                               uint8_t* preL, uint8_t* preR, size_t pre_pitch, int W, int H, int ps, int cap, cudaStream_t st);
 int launch_remap_nearest(const uint8_t* src, int sW, int sH, int ch, const int2* map, const CamModel& cm,
                          uint8_t* dst, int W, int H, cudaStream_t st);
 

@@ -205,7 +205,114 @@ __global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSi
     }
 }
 
+// ---- fused (rectify +) normalised-response prefilter -------------------------------------------------------
+// cv::StereoBM's NORMALIZED_RESPONSE prefilter: out = clip((c * scale_g - boxsum * scale_s) >> 10) + cap
+// with c = 4 I(x,y) + its 4 neighbours and boxsum over preFilterSize^2, replicate borders.  One block rectifies (or just
+// loads) a 64x16 tile plus a halo of preFilterSize/2 at clamped coordinates into shared memory, forms the vertical box
+// sums of every tile column with a sliding sum, then every thread finishes 4 adjacent pixels with a sliding horizontal
+// sum.  Replaces remap x2 + two prefilter passes through a global scratch plane; both sides in one launch.
+constexpr int NTX = 64, NTY = 16, NP2MAX = 10;                 // preFilterSize <= 21
+constexpr int NTW = NTX + 2 * NP2MAX + 4;                      // tile row stride (bytes / u16 entries)
+
+template <int MODE>     // 0: source is already rectified, 1: cached rectification map, 2: map evaluated on the fly
+__global__ void __launch_bounds__(256) norm_prefilter_kernel(RectSide sl, RectSide sr, int sW, int sH, size_t ppitch, int W,
+                                                             int H, int p2, int scale_g, int scale_s, int cap)
+{
+    __shared__ __align__(16) uint8_t tile[NTY + 2 * NP2MAX][NTW];
+    __shared__ __align__(16) uint16_t vs[NTY][NTW];
+    const RectSide& S = blockIdx.z ? sr : sl;
+    const uint8_t* __restrict__ src = S.src;
+    const int x0 = blockIdx.x * NTX, y0 = blockIdx.y * NTY;
+    const int tw = NTX + 2 * p2, th = NTY + 2 * p2, tn = tw * th;
+    for (int i0 = threadIdx.x; i0 < tn; i0 += 4 * 256) {
+        int2 m[4];
+        int xs[4], ys[4];
+        bool in[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = i0 + 256 * k;
+            in[k] = i < tn;
+            const int ty = i / tw, tx = i - ty * tw;
+            xs[k] = min(max(x0 + tx - p2, 0), W - 1);           // replicate border of the (rectified) image
+            ys[k] = min(max(y0 + ty - p2, 0), H - 1);
+            m[k] = make_int2(0, 0);
+            if (MODE != 0 && in[k]) m[k] = MODE == 2 ? map_point(S.cm, xs[k], ys[k]) : __ldg(S.map + (size_t)ys[k] * W + xs[k]);
+        }
+        int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = 0;
+            if (!in[k]) continue;
+            if (MODE == 0) v[k] = __ldg(src + (size_t)ys[k] * sW + xs[k]);
+            else v[k] = sample_linear(src, sW, sH, 1, 0, m[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = i0 + 256 * k;
+            if (!in[k]) continue;
+            const int ty = i / tw, tx = i - ty * tw;
+            tile[ty][tx] = (uint8_t)v[k];
+        }
+    }
+    __syncthreads();
+    // vertical box sums: thread = tile column, sliding down the 16 output rows (255 * 21 fits 16 bits)
+    if (threadIdx.x < tw) {
+        const int c = threadIdx.x;
+        int s = 0;
+        for (int j = 0; j <= 2 * p2; ++j) s += tile[j][c];
+        vs[0][c] = (uint16_t)s;
+        for (int y = 1; y < NTY; ++y) {
+            s += (int)tile[y + 2 * p2][c] - (int)tile[y - 1][c];
+            vs[y][c] = (uint16_t)s;
+        }
+    }
+    __syncthreads();
+    {
+        const int ty = threadIdx.x >> 4, tx = (threadIdx.x & 15) * 4;
+        const int x = x0 + tx, y = y0 + ty;
+        if (x < W && y < H) {
+            int sum = 0;
+            for (int j = 0; j <= 2 * p2; ++j) sum += vs[ty][tx + j];
+            uint32_t pre4 = 0, rect4 = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint8_t* cr = &tile[ty + p2][tx + i + p2];
+                const int c = 4 * (int)cr[0] + (int)cr[-1] + (int)cr[1] + (int)cr[-NTW] + (int)cr[NTW];
+                const int val = (c * scale_g - sum * scale_s) >> 10;
+                pre4 |= (uint32_t)(min(max(val, -cap), cap) + cap) << (8 * i);
+                rect4 |= (uint32_t)cr[0] << (8 * i);
+                if (i < 3) sum += (int)vs[ty][tx + i + 2 * p2 + 1] - (int)vs[ty][tx + i];
+            }
+            uint8_t* pp = S.pre + (size_t)y * ppitch + x;
+            if (x + 3 < W) *(uint32_t*)pp = pre4;                // ppitch % 16 == 0 and x % 4 == 0
+            else for (int i = 0; i < 4 && x + i < W; ++i) pp[i] = (uint8_t)(pre4 >> (8 * i));
+            if (MODE != 0 && S.rect) {
+                uint8_t* rp = S.rect + (size_t)y * W + x;
+                if (x + 3 < W && (W & 3) == 0) *(uint32_t*)rp = rect4;
+                else for (int i = 0; i < 4 && x + i < W; ++i) rp[i] = (uint8_t)(rect4 >> (8 * i));
+            }
+        }
+    }
+}
+
 static inline dim3 grid2d(int W, int H) { return dim3((W + 31) / 32, (H + 7) / 8); }
+
+// returns 0 when preFilterSize is too large for the tile kernel (the caller uses the two-pass kernels then)
+int launch_norm_prefilter_pair(const uint8_t* srcL, const uint8_t* srcR, int sW, int sH, bool rectify, const int2* mapL,
+                               const int2* mapR, const CamModel& cmL, const CamModel& cmR, uint8_t* rectL, uint8_t* rectR,
+                               uint8_t* preL, uint8_t* preR, size_t pre_pitch, int W, int H, int ps, int cap, cudaStream_t st)
+{
+    const int p2 = ps / 2;
+    if (p2 > NP2MAX) return 0;
+    int scale_g = ps * ps / 8, scale_s = (1024 + scale_g) / (scale_g * 2);
+    scale_g *= scale_s;
+    dim3 g((W + NTX - 1) / NTX, (H + NTY - 1) / NTY, 2);
+    RectSide l{srcL, mapL, rectL, preL, cmL}, r{srcR, mapR, rectR, preR, cmR};
+    if (!rectify) norm_prefilter_kernel<0><<<g, 256, 0, st>>>(l, r, sW, sH, pre_pitch, W, H, p2, scale_g, scale_s, cap);
+    else if (mapL && mapR) norm_prefilter_kernel<1><<<g, 256, 0, st>>>(l, r, sW, sH, pre_pitch, W, H, p2, scale_g, scale_s, cap);
+    else norm_prefilter_kernel<2><<<g, 256, 0, st>>>(l, r, sW, sH, pre_pitch, W, H, p2, scale_g, scale_s, cap);
+    return 1;
+}
 
 int launch_build_map(const CamModel& cm, int W, int H, int2* map, cudaStream_t st)
 {

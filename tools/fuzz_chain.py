@@ -44,7 +44,8 @@ for case in range(n_cases):
     Lraw = rng.integers(0, 256, (H, W), dtype=np.uint8)
     Lraw = np.ascontiguousarray(np.clip(Lraw.astype(np.int32) // 2 + np.roll(Lraw, 3, axis=1) // 2, 0, 255).astype(np.uint8))
     Rraw = np.ascontiguousarray(np.roll(Lraw, -int(rng.integers(2, max(3, nd // 2))), axis=1))
-    p = O.BMParams(numDisparities=nd, blockSize=b, textureThreshold=0, uniquenessRatio=int(rng.choice([0, 10])))
+    p = O.BMParams(numDisparities=nd, blockSize=b, textureThreshold=0, uniquenessRatio=int(rng.choice([0, 10])),
+                   preFilterType=int(rng.integers(0, 2)), preFilterSize=int(rng.choice([5, 9, 21, 31])))
     proc = m.GpuStereoProcessor(0)
     info = lambda c: dict(width=W, height=H, K=c["K"], D=c["D"], R=c["R"], P=c["P"])
     proc.initStereoModel(info(cal["left"]), info(cal["right"]))
