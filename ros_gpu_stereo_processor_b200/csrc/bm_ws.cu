@@ -312,53 +312,105 @@ __global__ void __launch_bounds__(WsBounds<RB>::threads, 1) bm_ws_kernel(const W
         }
     } else {
         // =============================== stager role ===========================================================
-        // stager 0: left rows (pre-broadcast) + running texture column sums; stager 1: right rows (4 shifted copies)
+        // stager 0: left rows (pre-broadcast) + running texture column sums; the others: right rows (4 shifted copies).
+        // The global loads of row j + 1 are issued into registers before the wait for the stage buffer of row j, so
+        // their latency is off the hand-over path (the planner keeps ncols <= 32 * MAXL, RLW <= 32 * MAXR * (nSw - 1)).
+        constexpr int MAXL = 5, MAXR = 4;
         const int s = warp - (P.nVw + P.nHw + P.nWw);
         const int lane = tid & 31;
         const int Xl0 = X0 - r;
         const int Xr0 = X0 - r - P.lofs;     // multiple of 4 by construction
-        int* trun = (int*)(smem + P.oTc) + 8 * P.ncols;    // [ncols] running sums, owned lane-wise by stager 0
-        if (s == 0)
-            for (int c = lane; c < P.ncols; c += 32) trun[c] = 0;
-        for (int j = 0; j < nIn; ++j) {
-            const int sb = j & 1;
-            const int yi = y_in0 + j;
-            const bool has_old = j >= b;
-            if (j >= 2) bar_sync(B_EMPTY_STAGE + sb, NVt + NSt);
-            if (s == 0) {   // with a single stager warp it does both halves
-                const uint8_t* ln = P.Lp + (size_t)yi * P.pitch + Xl0;
-                const uint8_t* lo = P.Lp + (size_t)max(yi - b, 0) * P.pitch + Xl0;
-                uint32_t* sLb = (uint32_t*)(smem + P.oStage[sb]);
-                const bool publish = j >= 2 * r;
-                int* tpub = (int*)(smem + P.oTc) + ((j - 2 * r) & 7) * P.ncols;
-                for (int c = lane; c < P.ncols; c += 32) {
-                    const int a = (int)__ldg(ln + c), o2 = has_old ? (int)__ldg(lo + c) : 0;
-                    sLb[c] = (uint32_t)a * 0x01010101u;
-                    sLb[P.ncols + c] = (uint32_t)o2 * 0x01010101u;
-                    const int t = trun[c] + abs(a - P.cap) - (has_old ? abs(o2 - P.cap) : 0);
-                    trun[c] = t;
-                    if (publish) tpub[c] = t;     // texture column sums of output row j - 2r (ring of 8 rows)
-                }
-            }
-            if (s >= 1 || P.nSw == 1) {   // right rows: the words are spread over the remaining stager warps
-                const uint32_t* rn = (const uint32_t*)(P.Rp + (size_t)yi * P.pitch + Xr0);
-                const uint32_t* ro = (const uint32_t*)(P.Rp + (size_t)max(yi - b, 0) * P.pitch + Xr0);
-                uint8_t* sRc = smem + P.oStage[sb] + 2 * P.ncols * 4;
-                const int nrw = P.nSw > 1 ? P.nSw - 1 : 1, rw = P.nSw > 1 ? s - 1 : 0;
-#pragma unroll 2
-                for (int wi = rw * 32 + lane; wi < P.RLW; wi += 32 * nrw) {
-                    const uint32_t vn = __ldg(rn + wi), vo = has_old ? __ldg(ro + wi) : 0u;
-                    uint8_t* cp = sRc + 4 * wi;
-                    // copy jj holds row[a + 4 jj] at byte a
+        if (s == 0) {
+            int an[MAXL], ao[MAXL], trun[MAXL];
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj)
-                        if (wi >= jj) {
-                            *(uint32_t*)(cp + jj * P.CSB - 4 * jj) = vn;
-                            *(uint32_t*)(cp + (4 + jj) * P.CSB - 4 * jj) = vo;
-                        }
-                }
+            for (int m = 0; m < MAXL; ++m) {
+                const int c = lane + 32 * m;
+                an[m] = c < P.ncols ? (int)__ldg(P.Lp + (size_t)y_in0 * P.pitch + Xl0 + c) : 0;
+                ao[m] = 0;
+                trun[m] = 0;
             }
-            bar_arrive(B_FULL_STAGE + sb, NVt + NSt);
+            for (int j = 0; j < nIn; ++j) {
+                const int sb = j & 1;
+                int cn[MAXL], co[MAXL];
+#pragma unroll
+                for (int m = 0; m < MAXL; ++m) { cn[m] = an[m]; co[m] = ao[m]; }
+                if (j + 1 < nIn) {
+                    const int yi = y_in0 + j + 1;
+                    const bool has_old = j + 1 >= b;
+                    const uint8_t* ln = P.Lp + (size_t)yi * P.pitch + Xl0;
+                    const uint8_t* lo = P.Lp + (size_t)max(yi - b, 0) * P.pitch + Xl0;
+#pragma unroll
+                    for (int m = 0; m < MAXL; ++m) {
+                        const int c = lane + 32 * m;
+                        if (c < P.ncols) {
+                            an[m] = (int)__ldg(ln + c);
+                            ao[m] = has_old ? (int)__ldg(lo + c) : 0;
+                        }
+                    }
+                }
+                if (j >= 2) bar_sync(B_EMPTY_STAGE + sb, NVt + NSt);
+                uint32_t* sLb = (uint32_t*)(smem + P.oStage[sb]);
+                const bool publish = j >= 2 * r, has_old = j >= b;
+                int* tpub = (int*)(smem + P.oTc) + ((j - 2 * r) & 7) * P.ncols;
+#pragma unroll
+                for (int m = 0; m < MAXL; ++m) {
+                    const int c = lane + 32 * m;
+                    if (c < P.ncols) {
+                        sLb[c] = (uint32_t)cn[m] * 0x01010101u;
+                        sLb[P.ncols + c] = (uint32_t)co[m] * 0x01010101u;
+                        trun[m] += abs(cn[m] - P.cap) - (has_old ? abs(co[m] - P.cap) : 0);
+                        if (publish) tpub[c] = trun[m];   // texture column sums of output row j - 2r (ring of 8 rows)
+                    }
+                }
+                bar_arrive(B_FULL_STAGE + sb, NVt + NSt);
+            }
+        } else {
+            const int nrw = P.nSw - 1, rw = s - 1;
+            const int w0 = rw * 32 + lane, wstep = 32 * nrw;
+            uint32_t vn[MAXR], vo[MAXR];
+#pragma unroll
+            for (int m = 0; m < MAXR; ++m) {
+                const int wi = w0 + wstep * m;
+                vn[m] = wi < P.RLW ? __ldg((const uint32_t*)(P.Rp + (size_t)y_in0 * P.pitch + Xr0) + wi) : 0u;
+                vo[m] = 0u;
+            }
+            for (int j = 0; j < nIn; ++j) {
+                const int sb = j & 1;
+                uint32_t cn[MAXR], co[MAXR];
+#pragma unroll
+                for (int m = 0; m < MAXR; ++m) { cn[m] = vn[m]; co[m] = vo[m]; }
+                if (j + 1 < nIn) {
+                    const int yi = y_in0 + j + 1;
+                    const bool has_old = j + 1 >= b;
+                    const uint32_t* rn = (const uint32_t*)(P.Rp + (size_t)yi * P.pitch + Xr0);
+                    const uint32_t* ro = (const uint32_t*)(P.Rp + (size_t)max(yi - b, 0) * P.pitch + Xr0);
+#pragma unroll
+                    for (int m = 0; m < MAXR; ++m) {
+                        const int wi = w0 + wstep * m;
+                        if (wi < P.RLW) {
+                            vn[m] = __ldg(rn + wi);
+                            vo[m] = has_old ? __ldg(ro + wi) : 0u;
+                        }
+                    }
+                }
+                if (j >= 2) bar_sync(B_EMPTY_STAGE + sb, NVt + NSt);
+                uint8_t* sRc = smem + P.oStage[sb] + 2 * P.ncols * 4;
+#pragma unroll
+                for (int m = 0; m < MAXR; ++m) {
+                    const int wi = w0 + wstep * m;
+                    if (wi < P.RLW) {
+                        uint8_t* cp = sRc + 4 * wi;
+                        // copy jj holds row[a + 4 jj] at byte a
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (wi >= jj) {
+                                *(uint32_t*)(cp + jj * P.CSB - 4 * jj) = cn[m];
+                                *(uint32_t*)(cp + (4 + jj) * P.CSB - 4 * jj) = co[m];
+                            }
+                    }
+                }
+                bar_arrive(B_FULL_STAGE + sb, NVt + NSt);
+            }
         }
     }
 }
@@ -429,7 +481,9 @@ int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
         static const int min_stagers = getenv("B200S_MIN_STAGERS") ? atoi(getenv("B200S_MIN_STAGERS")) : 2;
         if (nSw < min_stagers && NCQ > 8) continue;   // a single stager warp costs ~15 % (measured); prefer a narrower tile
         if (nVw + nHw + nWw + nSw > warp_cap) continue;
+        if (nSw < 2) continue;                               // one warp for the left rows, the others share the right rows
         const int ncols = 4 * NCQ;
+        if (ncols > 32 * 5 || (ncols + nd) / 4 + 1 > 32 * 4 * (nSw - 1)) continue;   // register-prefetch limits of the stagers
         const int rowsS = NS * SWD, rowsC = std::max(ncols, rowsS + 2 * r + 4);
         P.CWb = nd * 2; P.SWb = nd * 2 + 16; P.NK4 = (NGH + 3) / 4; P.KWb = (P.NK4 * 4 + 4) * 4;
         P.RLW = (ncols + nd) / 4 + 1;
