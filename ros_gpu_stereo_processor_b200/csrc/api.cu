@@ -126,6 +126,8 @@ struct b200s_handle {
     cudaEvent_t batch_start = nullptr;
     int slot_rows = 0, slot_cols = 0;
     uint64_t launches = 0;
+    void* stage_host[2] = {nullptr, nullptr};   // pinned staging for device->host copies into pageable user memory
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     uint64_t model_version = 0;   // bumped by every calibration change (part of the graph key)
     int use_graphs = 1;           // B200S_GRAPH=0 or b200s_set_graph_mode(h, 0) turns the replay off
     uint64_t graph_replays = 0;
@@ -154,6 +156,42 @@ int check_kernels(b200s_handle* h, const char* what)
 {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, B200S_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return B200S_OK;
+}
+
+// Device -> host copy of a packed payload followed by a stream sync.  Pinned (or registered) destinations take one DMA.
+// Pageable destinations -- a freshly allocated message buffer, the usual case with the reference-shaped calls -- go
+// through two pinned staging chunks so that the DMA of chunk k+1 overlaps the host memcpy of chunk k, instead of the
+// driver's slow pageable path.
+constexpr size_t STAGE_CHUNK = 8u << 20;
+
+int d2h_sync(b200s_handle* h, void* dst, const void* src, size_t bytes, cudaStream_t st)
+{
+    cudaPointerAttributes at;
+    const bool pageable = cudaPointerGetAttributes(&at, dst) != cudaSuccess || at.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    if (!pageable || bytes < (1u << 20)) {
+        CUDA_OK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(h, cudaStreamSynchronize(st));
+        return B200S_OK;
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (!h->stage_host[i]) CUDA_OK(h, cudaHostAlloc(&h->stage_host[i], STAGE_CHUNK, cudaHostAllocDefault));
+        if (!h->stage_ev[i]) CUDA_OK(h, cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming));
+    }
+    const size_t nchunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+    auto issue = [&](size_t k) -> cudaError_t {
+        const size_t off = k * STAGE_CHUNK, len = std::min(STAGE_CHUNK, bytes - off);
+        cudaError_t e = cudaMemcpyAsync(h->stage_host[k & 1], (const char*)src + off, len, cudaMemcpyDeviceToHost, st);
+        return e != cudaSuccess ? e : cudaEventRecord(h->stage_ev[k & 1], st);
+    };
+    CUDA_OK(h, issue(0));
+    for (size_t k = 0; k < nchunks; ++k) {
+        if (k + 1 < nchunks) CUDA_OK(h, issue(k + 1));          // its staging chunk was drained in iteration k - 1
+        CUDA_OK(h, cudaEventSynchronize(h->stage_ev[k & 1]));
+        const size_t off = k * STAGE_CHUNK, len = std::min(STAGE_CHUNK, bytes - off);
+        memcpy((char*)dst + off, h->stage_host[k & 1], len);
+    }
     return B200S_OK;
 }
 
@@ -439,6 +477,10 @@ int b200s_destroy(b200s_handle* h)
     for (int s = 0; s < 2; ++s) h->cam[s].map.release();
     h->Qdev.release();
     if (h->ev_r) cudaEventDestroy(h->ev_r);
+    for (int i = 0; i < 2; ++i) {
+        if (h->stage_host[i]) cudaFreeHost(h->stage_host[i]);
+        if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
+    }
     if (h->batch_start) cudaEventDestroy(h->batch_start);
     for (cudaEvent_t e : h->batch_end) cudaEventDestroy(e);
     if (h->l_strm) cudaStreamDestroy(h->l_strm);
@@ -566,6 +608,7 @@ int b200s_download(b200s_handle* h, int mat_id, void* dst, size_t dst_step)
     int es = elem_size(m->type);
     if (dst_step == 0) dst_step = (size_t)m->cols * es;
     cudaStream_t st = stream_of(h, mat_id);
+    if (dst_step == (size_t)m->cols * es) return d2h_sync(h, dst, m->buf.p, m->bytes(), st);
     CUDA_OK(h, cudaMemcpy2DAsync(dst, dst_step, m->buf.p, (size_t)m->cols * es, (size_t)m->cols * es, m->rows, cudaMemcpyDeviceToHost, st));
     CUDA_OK(h, cudaStreamSynchronize(st));
     return B200S_OK;
@@ -831,8 +874,7 @@ int b200s_pack_image(b200s_handle* h, int mat_id, void* dst, size_t cap_bytes, i
     if (!m) return fail(h, B200S_ENOBUF, "named buffer is empty");
     if (cap_bytes < m->bytes()) return fail(h, B200S_EINVAL, "destination too small");
     cudaStream_t st = stream_of(h, mat_id);
-    CUDA_OK(h, cudaMemcpyAsync(dst, m->buf.p, m->bytes(), cudaMemcpyDeviceToHost, st));
-    CUDA_OK(h, cudaStreamSynchronize(st));
+    { int rcd = d2h_sync(h, dst, m->buf.p, m->bytes(), st); if (rcd) return rcd; }
     if (rows) *rows = m->rows;
     if (cols) *cols = m->cols;
     if (step) *step = m->cols * elem_size(m->type);   // GpuSenderImage.cpp:20: width * bitdepth * channels / 8
@@ -868,8 +910,7 @@ int b200s_pack_disparity(b200s_handle* h, int disp_id, void* dst, size_t cap_byt
     if (h->w0.df.ensure(n * 4)) return fail(h, B200S_ENOMEM, "cudaMalloc failed");
     cudaStream_t st = stream_of(h, disp_id);
     h->launches += launch_disparity_to_float((const int16_t*)D->buf.p, (float*)h->w0.df.p, (int)n, h->model_ok ? h->cxd : 0.0, (int*)h->w0.misc.p, st);
-    CUDA_OK(h, cudaMemcpyAsync(dst, h->w0.df.p, n * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(h, cudaStreamSynchronize(st));
+    { int rcd = d2h_sync(h, dst, h->w0.df.p, n * 4, st); if (rcd) return rcd; }
     if (meta) fill_disparity_meta(h, D->rows, D->cols, meta);
     return check_kernels(h, "pack_disparity");
 }
@@ -903,8 +944,7 @@ int b200s_pack_pointcloud2(b200s_handle* h, int disp_id, int color_id, void* dst
     h->launches += launch_reproject_pack((const int16_t*)D->buf.p, D->cols, D->rows, h->cxd, (const double*)h->Qdev.p, h->qmask,
                                          (const int*)h->w0.misc.p, (const uint8_t*)Cc->buf.p, Cc->type == B200S_8UC3 ? 3 : 1,
                                          nullptr, (uint8_t*)h->w0.pc2.p, st);
-    CUDA_OK(h, cudaMemcpyAsync(dst, h->w0.pc2.p, n * 32, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(h, cudaStreamSynchronize(st));
+    { int rcd = d2h_sync(h, dst, h->w0.pc2.p, n * 32, st); if (rcd) return rcd; }
     if (meta) fill_pc2_meta(D->rows, D->cols, meta);
     return check_kernels(h, "pack_pointcloud2");
 }
