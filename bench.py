@@ -45,7 +45,7 @@ CONFIGS = {
     "C4s": dict(W=1920, H=1080, nd=256, block=11, rectify=True, speckle=(800, 80), idx=4),
 }
 FRAMES_PER_STEP = 16
-N_SLOTS = 4
+N_SLOTS = int(os.environ.get("B200S_BENCH_SLOTS", "4"))
 
 
 def workload_name(c, name):
