@@ -17,10 +17,12 @@
 //
 // Everything is exact integer arithmetic: the staged bytes are clamped to 2*cap <= 62, so no byte lane of a biased
 // pair sum or delta word can wrap, and the u16x2 registers are only ever combined linearly (a register is the integer
-// lo + 65536 * hi, valid whenever the final lanes are inside [0, 65535], which 2*cap*block^2 < 65535 guarantees).
+// lo + 65536 * hi, valid whenever the final lanes are inside [0, 65535]: the planner keeps
+// 2*cap*block^2 + 128 * (band rows + 2r + 1) <= 65535).
 //
-// Roles (one block per SM, warp-specialised, PTX named barriers, double-buffered shared memory):
-//   stager warps   global rows -> stage[j & 1]  (left bytes pre-broadcast, right row as 4 word-shifted copies)
+// Roles (usually one block per SM, warp-specialised, mbarrier full/empty pairs, double-buffered shared memory):
+//   stager warps   global rows -> stage[j & 1]  (left bytes pre-broadcast, right row as 4 word-shifted copies; the loads
+//                  of row j + 1 are in flight while the buffer of row j is awaited)
 //   VH warps       stage -> S registers -> Sbuf[o & 1] (all window sums of the row) + Kbuf[o & 1] (min per 4 disparities)
 //   W warps        Sbuf/Kbuf -> disparity (argmin, uniqueness, texture, sub-pixel), one thread per pixel
 #include "kernels.h"
