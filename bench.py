@@ -227,7 +227,7 @@ def run_ours(args, c, name, rank, world, local_rank):
     proc.initStereoModel(info(cal["left"]), info(cal["right"]))
     proc.setParams(numDisparities=nd, blockSize=c["block"], minDisparity=0, preFilterType=1, preFilterSize=9, preFilterCap=31,
                    textureThreshold=10, uniquenessRatio=15, speckleWindowSize=c["speckle"][0], speckleRange=c["speckle"][1],
-                   disp12MaxDiff=-1)
+                   disp12MaxDiff=int(os.environ.get("B200S_BENCH_DISP12", "-1")))   # -1 = BASELINE configs; override for experiments
     proc.configureSlots(N_SLOTS, H, W)
     want = capi.OUT_DISPARITY32F | capi.OUT_POINTCLOUD2 | (capi.OUT_RECT_L | capi.OUT_RECT_R if c["rectify"] else 0)
 

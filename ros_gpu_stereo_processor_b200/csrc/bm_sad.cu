@@ -408,7 +408,22 @@ __device__ __forceinline__ void gen_strip_row(const GenParams& P, int y, int k, 
     }
 }
 
-__global__ void __launch_bounds__(128) bm_generic_strip_cost_kernel(const GenParams P)
+__device__ __forceinline__ void gen_strip_cost_body(const GenParams& P);
+__device__ __forceinline__ void gen_winner_warp_body(const GenParams& P);
+
+// both border strips of a frame in one launch each (blockIdx.z selects the strip): one strip alone leaves most SMs idle
+__global__ void __launch_bounds__(128) bm_generic_strip_cost_pair_kernel(const GenParams P0, const GenParams P1)
+{
+    gen_strip_cost_body(blockIdx.z ? P1 : P0);
+}
+__global__ void __launch_bounds__(256) bm_generic_winner_warp_pair_kernel(const GenParams P0, const GenParams P1)
+{
+    gen_winner_warp_body(blockIdx.y ? P1 : P0);
+}
+
+__global__ void __launch_bounds__(128) bm_generic_strip_cost_kernel(const GenParams P) { gen_strip_cost_body(P); }
+
+__device__ __forceinline__ void gen_strip_cost_body(const GenParams& P)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int y0 = P.ya + blockIdx.y * P.RCH, y1 = min(y0 + P.RCH, P.yb);
@@ -471,7 +486,9 @@ __global__ void __launch_bounds__(128) bm_generic_winner_kernel(const GenParams 
 
 // Same selection with one warp per pixel (lanes stride over the disparities): the border bands that disp12MaxDiff >= 0
 // needs are only r columns wide, far too few pixels to fill the GPU with one thread each.
-__global__ void __launch_bounds__(256) bm_generic_winner_warp_kernel(const GenParams P)
+__global__ void __launch_bounds__(256) bm_generic_winner_warp_kernel(const GenParams P) { gen_winner_warp_body(P); }
+
+__device__ __forceinline__ void gen_winner_warp_body(const GenParams& P)
 {
     const int ncx = P.xb - P.xa;
     const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -587,6 +604,33 @@ static int run_generic(const GenPlanes& pl, int W, int H, const BMConfig& cfg, c
         launches += 2;
     }
     return launches;
+}
+
+// the two r-wide strips left and right of the fast rectangle, one cost launch and one winner launch for both
+static int run_generic_pair(const GenPlanes& pl, int W, int H, const BMConfig& cfg, const Geom& g, int xa0, int xb0, int xa1,
+                            int xb1, int16_t* disp, int16_t* cost, BMScratch* sc, cudaStream_t st)
+{
+    const int n0 = xb0 - xa0, n1 = xb1 - xa1, rows = g.roiY1 - g.roiY0;
+    const size_t need = (size_t)(n0 + n1) * cfg.nd * sizeof(int) * (size_t)rows;
+    if (n0 <= 0 || n1 <= 0 || n0 > GEN_STRIP_MAXC || n1 > GEN_STRIP_MAXC || !sc || !sc->vol || need > sc->vol_bytes || rows <= 0) {
+        int l0 = run_generic(pl, W, H, cfg, g, xa0, xb0, disp, cost, sc, st);
+        if (l0 < 0) return l0;
+        int l1 = run_generic(pl, W, H, cfg, g, xa1, xb1, disp, cost, sc, st);
+        return l1 < 0 ? l1 : l0 + l1;
+    }
+    GenParams P[2];
+    for (int i = 0; i < 2; ++i) {
+        GenParams& Q = P[i];
+        Q.Lp = pl.Lp; Q.Rp = pl.Rp; Q.pitch = pl.pitch; Q.W = W; Q.H = H; Q.nd = cfg.nd; Q.minD = cfg.minD; Q.r = g.r; Q.cap = cfg.cap;
+        Q.texThr = cfg.textureThreshold; Q.uniq = cfg.uniquenessRatio; Q.lofs = g.lofs; Q.rofs = g.rofs;
+        Q.xa = i ? xa1 : xa0; Q.xb = i ? xb1 : xb0; Q.ya = g.roiY0; Q.yb = g.roiY1; Q.RCH = 8;
+        Q.vol = sc->vol + (i ? (size_t)n0 * cfg.nd * rows : 0); Q.disp = disp; Q.cost = cost;
+    }
+    const int kt = std::min(128, cfg.nd);
+    bm_generic_strip_cost_pair_kernel<<<dim3((cfg.nd + kt - 1) / kt, (rows + 7) / 8, 2), kt, 0, st>>>(P[0], P[1]);
+    const int npx = std::max(n0, n1) * rows;
+    bm_generic_winner_warp_pair_kernel<<<dim3((npx + 7) / 8, 2), 256, 0, st>>>(P[0], P[1]);
+    return 2;
 }
 
 template <int ND>
@@ -717,10 +761,7 @@ int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W
     }
     if (ws_done) {
         ++launches;
-        int l = run_generic(gp, W, H, cfg, g, outX0 - g.lofs, XA - g.lofs, disp, cost, sc, st);
-        if (l < 0) return l;
-        launches += l;
-        l = run_generic(gp, W, H, cfg, g, XB - g.lofs, outX1 - g.lofs, disp, cost, sc, st);
+        int l = run_generic_pair(gp, W, H, cfg, g, outX0 - g.lofs, XA - g.lofs, XB - g.lofs, outX1 - g.lofs, disp, cost, sc, st);
         if (l < 0) return l;
         launches += l;
     } else if (fast_ok) {
