@@ -392,37 +392,47 @@ __device__ __forceinline__ int gen_term(const GenParams& P, const uint8_t* __res
     return abs((int)__ldg(lr + lc) - (int)__ldg(rr + rc));
 }
 
-// adds sign * (window sums of row y for the strip columns) to V
+// adds sign * (window sums of row y for the strip columns) to V.  RT > 0: compile-time radius, so that the 2r+1 terms of
+// the first window are unrolled and their loads overlap (the kernel is latency-bound otherwise).
+template <int RT>
 __device__ __forceinline__ void gen_strip_row(const GenParams& P, int y, int k, int ncx, int sign, int (&V)[GEN_STRIP_MAXC])
 {
     const uint8_t* lr = P.Lp + (size_t)y * P.pitch;
     const uint8_t* rr = P.Rp + (size_t)y * P.pitch;
+    const int r = RT > 0 ? RT : P.r;
     int s = 0;
-    for (int dx = -P.r; dx <= P.r; ++dx) s += gen_term(P, lr, rr, P.xa + dx, k);
+    if (RT > 0) {
+#pragma unroll
+        for (int dx = -RT; dx <= RT; ++dx) s += gen_term(P, lr, rr, P.xa + dx, k);
+    } else {
+        for (int dx = -r; dx <= r; ++dx) s += gen_term(P, lr, rr, P.xa + dx, k);
+    }
 #pragma unroll
     for (int c = 0; c < GEN_STRIP_MAXC; ++c) {
         if (c < ncx) {
             V[c] += sign * s;
-            if (c + 1 < ncx) s += gen_term(P, lr, rr, P.xa + c + 1 + P.r, k) - gen_term(P, lr, rr, P.xa + c - P.r, k);
+            if (c + 1 < ncx) s += gen_term(P, lr, rr, P.xa + c + 1 + r, k) - gen_term(P, lr, rr, P.xa + c - r, k);
         }
     }
 }
 
-__device__ __forceinline__ void gen_strip_cost_body(const GenParams& P);
+template <int RT> __device__ __forceinline__ void gen_strip_cost_body(const GenParams& P);
 __device__ __forceinline__ void gen_winner_warp_body(const GenParams& P);
 
 // both border strips of a frame in one launch each (blockIdx.z selects the strip): one strip alone leaves most SMs idle
+template <int RT>
 __global__ void __launch_bounds__(128) bm_generic_strip_cost_pair_kernel(const GenParams P0, const GenParams P1)
 {
-    gen_strip_cost_body(blockIdx.z ? P1 : P0);
+    gen_strip_cost_body<RT>(blockIdx.z ? P1 : P0);
 }
 __global__ void __launch_bounds__(256) bm_generic_winner_warp_pair_kernel(const GenParams P0, const GenParams P1)
 {
     gen_winner_warp_body(blockIdx.y ? P1 : P0);
 }
 
-__global__ void __launch_bounds__(128) bm_generic_strip_cost_kernel(const GenParams P) { gen_strip_cost_body(P); }
+__global__ void __launch_bounds__(128) bm_generic_strip_cost_kernel(const GenParams P) { gen_strip_cost_body<0>(P); }
 
+template <int RT>
 __device__ __forceinline__ void gen_strip_cost_body(const GenParams& P)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -432,14 +442,14 @@ __device__ __forceinline__ void gen_strip_cost_body(const GenParams& P)
     int V[GEN_STRIP_MAXC];
 #pragma unroll
     for (int c = 0; c < GEN_STRIP_MAXC; ++c) V[c] = 0;
-    for (int yy = y0 - P.r; yy <= y0 + P.r; ++yy) gen_strip_row(P, yy, k, ncx, 1, V);
+    for (int yy = y0 - P.r; yy <= y0 + P.r; ++yy) gen_strip_row<RT>(P, yy, k, ncx, 1, V);
     for (int y = y0; y < y1; ++y) {
 #pragma unroll
         for (int c = 0; c < GEN_STRIP_MAXC; ++c)
             if (c < ncx) P.vol[((size_t)(y - P.ya) * ncx + c) * P.nd + k] = V[c];
         if (y + 1 < y1) {
-            gen_strip_row(P, y + 1 + P.r, k, ncx, 1, V);
-            gen_strip_row(P, y - P.r, k, ncx, -1, V);
+            gen_strip_row<RT>(P, y + 1 + P.r, k, ncx, 1, V);
+            gen_strip_row<RT>(P, y - P.r, k, ncx, -1, V);
         }
     }
 }
@@ -627,7 +637,19 @@ static int run_generic_pair(const GenPlanes& pl, int W, int H, const BMConfig& c
         Q.vol = sc->vol + (i ? (size_t)n0 * cfg.nd * rows : 0); Q.disp = disp; Q.cost = cost;
     }
     const int kt = std::min(128, cfg.nd);
-    bm_generic_strip_cost_pair_kernel<<<dim3((cfg.nd + kt - 1) / kt, (rows + 7) / 8, 2), kt, 0, st>>>(P[0], P[1]);
+    const dim3 gc((cfg.nd + kt - 1) / kt, (rows + 7) / 8, 2);
+    switch (g.r) {
+    case 2: bm_generic_strip_cost_pair_kernel<2><<<gc, kt, 0, st>>>(P[0], P[1]); break;
+    case 3: bm_generic_strip_cost_pair_kernel<3><<<gc, kt, 0, st>>>(P[0], P[1]); break;
+    case 4: bm_generic_strip_cost_pair_kernel<4><<<gc, kt, 0, st>>>(P[0], P[1]); break;
+    case 5: bm_generic_strip_cost_pair_kernel<5><<<gc, kt, 0, st>>>(P[0], P[1]); break;
+    case 6: bm_generic_strip_cost_pair_kernel<6><<<gc, kt, 0, st>>>(P[0], P[1]); break;
+    case 7: bm_generic_strip_cost_pair_kernel<7><<<gc, kt, 0, st>>>(P[0], P[1]); break;
+    case 8: bm_generic_strip_cost_pair_kernel<8><<<gc, kt, 0, st>>>(P[0], P[1]); break;
+    case 9: bm_generic_strip_cost_pair_kernel<9><<<gc, kt, 0, st>>>(P[0], P[1]); break;
+    case 10: bm_generic_strip_cost_pair_kernel<10><<<gc, kt, 0, st>>>(P[0], P[1]); break;
+    default: bm_generic_strip_cost_pair_kernel<0><<<gc, kt, 0, st>>>(P[0], P[1]); break;
+    }
     const int npx = std::max(n0, n1) * rows;
     bm_generic_winner_warp_pair_kernel<<<dim3((npx + 7) / 8, 2), 256, 0, st>>>(P[0], P[1]);
     return 2;
