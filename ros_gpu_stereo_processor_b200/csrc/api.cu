@@ -398,8 +398,7 @@ int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, 
     if (cfg.disp12MaxDiff >= 0) {
         int v = launch_validate_disp12(disp, cost, cols, rows, cfg, st);
         if (v < 0) return fail(h, B200S_EUNSUPPORTED, "disp12MaxDiff needs image width <= 65535");
-        h->launches += v;
-        h->launches += launch_roi_mask(disp, cols, rows, cfg, st);
+        h->launches += v;     // the valid-ROI mask of the rows is applied by the same kernel
     }
     if (p.speckle_window_size > 0 && p.speckle_range >= 0) {
         if (w.ccl.ensure(3 * n * sizeof(int))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (speckle scratch)");

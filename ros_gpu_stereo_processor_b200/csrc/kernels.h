@@ -71,6 +71,7 @@ int launch_u8_to_s16(const uint8_t* a, int16_t* b, size_t n, cudaStream_t st);
 int launch_s16_to_u8(const int16_t* a, uint8_t* b, size_t n, cudaStream_t st);
 
 // ---- post.cu ----------------------------------------------------------------------------------------
+// cv::validateDisparity on the ROI rows followed by the valid-ROI column mask of those rows
 int launch_validate_disp12(int16_t* disp, const int16_t* cost, int W, int H, const BMConfig& cfg, cudaStream_t st);
 int launch_roi_mask(int16_t* disp, int W, int H, const BMConfig& cfg, cudaStream_t st);
 // scratch: 3 * W*H int32 (parents, sizes, roots)

@@ -12,7 +12,7 @@ namespace b200s {
 // pass 1 is a scatter-min: the sequential rule "c2[x2] > c (strict), x ascending" keeps the smallest cost and,
 // among equal costs, the smallest x  ==  atomicMin over the key (cost + 32768) << 16 | x.
 __global__ void __launch_bounds__(256) validate_kernel(int16_t* __restrict__ disp, const int16_t* __restrict__ cost,
-                                                       int W, int minD, int nd, int maxdiff16, int ya)
+                                                       int W, int minD, int nd, int maxdiff16, int ya, int roiX0, int roiX1)
 {
     extern __shared__ uint32_t vsm[];
     uint32_t* key = vsm;                 // [W]
@@ -48,6 +48,10 @@ __global__ void __launch_bounds__(256) validate_kernel(int16_t* __restrict__ dis
         bool b1 = (unsigned)x1 < (unsigned)W && d2[x1] > INV && abs((int)d2[x1] - d) > maxdiff16;
         if (b0 && b1) dp[x] = (int16_t)INV;
     }
+    // valid-ROI mask of the row (cv::StereoBM applies it after the L/R check): the columns outside [roiX0, roiX1) were
+    // only computed to feed the check; nobody reads another thread's dp[] any more at this point
+    for (int x = threadIdx.x; x < W; x += blockDim.x)
+        if (x < roiX0 || x >= roiX1) dp[x] = (int16_t)INV;
 }
 
 __global__ void __launch_bounds__(256) roi_mask_kernel(int16_t* __restrict__ disp, int W, int H, int x0, int x1, int y0,
@@ -297,7 +301,8 @@ int launch_validate_disp12(int16_t* disp, const int16_t* cost, int W, int H, con
     if (y1 <= y0 || W > 65535) return y1 <= y0 ? 0 : -1;
     size_t smem = (size_t)W * 4 + (size_t)W * 2 + 16;
     if (smem > 48 * 1024) cudaFuncSetAttribute(validate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    validate_kernel<<<y1 - y0, 256, smem, st>>>(disp, cost, W, cfg.minD, cfg.nd, cfg.disp12MaxDiff * 16, y0);
+    const int x0 = std::max(cfg.minD + cfg.nd - 1, 0) + r, x1 = W - r;
+    validate_kernel<<<y1 - y0, 256, smem, st>>>(disp, cost, W, cfg.minD, cfg.nd, cfg.disp12MaxDiff * 16, y0, x0, x1);
     return 1;
 }
 
