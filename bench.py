@@ -43,14 +43,20 @@ CONFIGS = {
     # not a BASELINE config: C4 with the reference's default speckle filter on (GPU.cfg max_speckle_size 800,
     # max_speckle_diff 5 disparities = 80 raw units), i.e. what StereoProcessor::imageCb runs out of the box
     "C4s": dict(W=1920, H=1080, nd=256, block=11, rectify=True, speckle=(800, 80), idx=4),
+    # not a BASELINE config either: C4 shape in the state the reference's matcher is in out of the box (GPU.cfg defaults
+    # xsobel=False -> NORMALIZED_RESPONSE with the constructor's preFilterSize 5, uniqueness 0 and disp12MaxDiff 0 mirrored
+    # from the cuda matcher's getters, src/GPUStereoProcessor.cpp:22-38, speckle filter 800 / 5 disparities)
+    "C4r": dict(W=1920, H=1080, nd=256, block=11, rectify=True, speckle=(800, 80), idx=4, pft=0, ps=5, uniq=0, disp12=0),
 }
 FRAMES_PER_STEP = 16
 N_SLOTS = int(os.environ.get("B200S_BENCH_SLOTS", "4"))
 
 
 def workload_name(c, name):
-    return "%s: %dx%d mono8 raw pair, %s, xsobel cap31, StereoBM nd=%d block=%d tex10 uniq15%s, DisparityImage f32 + PointCloud2" % (
-        name, c["W"], c["H"], "rectify from camera_info" if c["rectify"] else "pre-rectified", c["nd"], c["block"],
+    return "%s: %dx%d mono8 raw pair, %s, %s cap31, StereoBM nd=%d block=%d tex10 uniq%d%s%s, DisparityImage f32 + PointCloud2" % (
+        name, c["W"], c["H"], "rectify from camera_info" if c["rectify"] else "pre-rectified",
+        "xsobel" if c.get("pft", 1) == 1 else "normalized-response ps%d" % c.get("ps", 9), c["nd"], c["block"], c.get("uniq", 15),
+        (" disp12MaxDiff=%d" % c["disp12"]) if c.get("disp12", -1) >= 0 else "",
         (" speckle(%d,%d)" % c["speckle"]) if c["speckle"][0] else "")
 
 
@@ -143,7 +149,9 @@ def cpu_chain(frames, cal, c, reps_budget_s, threads):
     import cv2
     from oracle import oracle as O, cv2_ref as CV
     cv2.setNumThreads(threads)
-    p = O.BMParams(numDisparities=c["nd"], blockSize=c["block"], speckleWindowSize=c["speckle"][0], speckleRange=c["speckle"][1])
+    p = O.BMParams(numDisparities=c["nd"], blockSize=c["block"], speckleWindowSize=c["speckle"][0], speckleRange=c["speckle"][1],
+                   preFilterType=c.get("pft", 1), preFilterSize=c.get("ps", 9), uniquenessRatio=c.get("uniq", 15),
+                   disp12MaxDiff=c.get("disp12", -1))
     bm = CV.make_bm(p)
     W, H = c["W"], c["H"]
     maps = None
@@ -225,9 +233,11 @@ def run_ours(args, c, name, rank, world, local_rank):
     proc = m.GpuStereoProcessor(dev)
     info = lambda cc: dict(width=W, height=H, K=cc["K"], D=cc["D"], R=cc["R"], P=cc["P"])
     proc.initStereoModel(info(cal["left"]), info(cal["right"]))
-    proc.setParams(numDisparities=nd, blockSize=c["block"], minDisparity=0, preFilterType=1, preFilterSize=9, preFilterCap=31,
-                   textureThreshold=10, uniquenessRatio=15, speckleWindowSize=c["speckle"][0], speckleRange=c["speckle"][1],
-                   disp12MaxDiff=int(os.environ.get("B200S_BENCH_DISP12", "-1")))   # -1 = BASELINE configs; override for experiments
+    proc.setParams(numDisparities=nd, blockSize=c["block"], minDisparity=0, preFilterType=c.get("pft", 1), preFilterSize=c.get("ps", 9),
+                   preFilterCap=31, textureThreshold=10, uniquenessRatio=c.get("uniq", 15), speckleWindowSize=c["speckle"][0],
+                   speckleRange=c["speckle"][1],
+                   # -1 = BASELINE configs; environment override for experiments
+                   disp12MaxDiff=int(os.environ.get("B200S_BENCH_DISP12", str(c.get("disp12", -1)))))
     proc.configureSlots(N_SLOTS, H, W)
     want = capi.OUT_DISPARITY32F | capi.OUT_POINTCLOUD2 | (capi.OUT_RECT_L | capi.OUT_RECT_R if c["rectify"] else 0)
 
