@@ -68,7 +68,7 @@ def evals_per_frame(c):
 
 
 def make_frames(c, n, seed0):
-    from oracle import synth   # input generation only (seeded synthetic pairs + scaled calibration)
+    from tools import synth   # input generation only (seeded synthetic pairs + scaled calibration)
     frames, cal = [], synth.scaled_calibration(c["W"], c["H"])
     for i in range(n):
         if c["rectify"]:
@@ -142,6 +142,22 @@ def bind_to_gpu_numa(gpu_index):
         return "numa node %s, %d cpus" % (node, len(allowed))
     except Exception as e:   # best effort only
         return "not bound (%s)" % type(e).__name__
+
+
+def setup_processor(proc, c, cal):
+    """Calibration + matcher state of config `c` on a GpuStereoProcessor (shared with tests/test_gpu_parity.py)."""
+    W, H = c["W"], c["H"]
+    info = lambda cc: dict(width=W, height=H, K=cc["K"], D=cc["D"], R=cc["R"], P=cc["P"])
+    proc.initStereoModel(info(cal["left"]), info(cal["right"]))
+    proc.setParams(numDisparities=c["nd"], blockSize=c["block"], minDisparity=0, preFilterType=c.get("pft", 1), preFilterSize=c.get("ps", 9),
+                   preFilterCap=31, textureThreshold=10, uniquenessRatio=c.get("uniq", 15), speckleWindowSize=c["speckle"][0],
+                   speckleRange=c["speckle"][1],
+                   # -1 = BASELINE configs (SURVEY.md 8d); environment override for experiments
+                   disp12MaxDiff=int(os.environ.get("B200S_BENCH_DISP12", str(c.get("disp12", -1)))))
+
+
+def want_bits(c, capi):
+    return capi.OUT_DISPARITY32F | capi.OUT_POINTCLOUD2 | (capi.OUT_RECT_L | capi.OUT_RECT_R if c["rectify"] else 0)
 
 
 def cpu_chain(frames, cal, c, reps_budget_s, threads):
@@ -231,15 +247,9 @@ def run_ours(args, c, name, rank, world, local_rank):
     frames, cal = make_frames(c, FRAMES_PER_STEP, 1000 * c["idx"] + rank * FRAMES_PER_STEP)
 
     proc = m.GpuStereoProcessor(dev)
-    info = lambda cc: dict(width=W, height=H, K=cc["K"], D=cc["D"], R=cc["R"], P=cc["P"])
-    proc.initStereoModel(info(cal["left"]), info(cal["right"]))
-    proc.setParams(numDisparities=nd, blockSize=c["block"], minDisparity=0, preFilterType=c.get("pft", 1), preFilterSize=c.get("ps", 9),
-                   preFilterCap=31, textureThreshold=10, uniquenessRatio=c.get("uniq", 15), speckleWindowSize=c["speckle"][0],
-                   speckleRange=c["speckle"][1],
-                   # -1 = BASELINE configs; environment override for experiments
-                   disp12MaxDiff=int(os.environ.get("B200S_BENCH_DISP12", str(c.get("disp12", -1)))))
+    setup_processor(proc, c, cal)
     proc.configureSlots(N_SLOTS, H, W)
-    want = capi.OUT_DISPARITY32F | capi.OUT_POINTCLOUD2 | (capi.OUT_RECT_L | capi.OUT_RECT_R if c["rectify"] else 0)
+    want = want_bits(c, capi)
 
     # ---- device-resident inputs (torch only owns the HBM) --------------------------------------------------
     dL = [torch.from_numpy(f[0]).cuda(dev) for f in frames]

@@ -131,6 +131,7 @@ struct b200s_handle {
     uint64_t model_version = 0;   // bumped by every calibration change (part of the graph key)
     int use_graphs = 1;           // B200S_GRAPH=0 or b200s_set_graph_mode(h, 0) turns the replay off
     uint64_t graph_replays = 0;
+    int pack_direct = 0;          // 1: the pack kernels store straight into pinned (mapped) host destinations
 };
 
 namespace {
@@ -414,6 +415,16 @@ int ensure_misc(b200s_handle* h, Work& w)
     return B200S_OK;
 }
 
+// Device-side alias of a pinned (page-locked, mapped) host buffer, or nullptr when `p` is pageable / not host memory.
+// Under unified addressing every cudaHostAlloc / cudaHostRegister range is directly writable by kernels.
+void* mapped_alias(const void* p)
+{
+    if (!p) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
 int copy_out(b200s_handle* h, void* dst, const void* src, size_t bytes, bool dst_on_device, cudaStream_t st)
 {
     if (!dst) return B200S_OK;
@@ -451,6 +462,7 @@ int b200s_create(int device, b200s_handle** out)
     // state of the reference's CPU matcher after its constructor (src/GPUStereoProcessor.cpp:18-38):
     // createStereoBM(48, 19) mirrored into cv::StereoBM, preFilterSize 5
     if (const char* e = getenv("B200S_GRAPH")) h->use_graphs = atoi(e) != 0;
+    if (const char* e = getenv("B200S_PACK_DIRECT")) h->pack_direct = atoi(e);
     b200s_default_params(&h->prm);
     h->prm.pre_filter_type = 0; h->prm.pre_filter_size = 5; h->prm.num_disparities = 48; h->prm.block_size = 19;
     h->prm.texture_threshold = 3; h->prm.uniqueness_ratio = 0; h->prm.disp12_max_diff = 0;
@@ -1029,12 +1041,15 @@ int run_frame_chain(b200s_handle* h, Work& w, const b200s_frame_io* io, const ui
         h->launches += launch_disparity_to_float((const int16_t*)w.disp.p, want_df ? (float*)w.df.p : nullptr, (int)n,
                                                  h->model_ok ? h->cxd : 0.0, (int*)w.misc.p, st);
     }
+    // pack mode "direct" (the north star's wording): the PointCloud2 records are stored by the kernel straight into the
+    // caller's pinned host buffer (PCIe posted writes), no HBM copy of the cloud and no copy-engine transfer afterwards
+    void* pc_direct = (h->pack_direct && want_pc && !io->outputs_on_device) ? mapped_alias(io->pointcloud2) : nullptr;
     if (want_pc || want_xyz) {
-        if (want_pc && w.pc2.ensure(n * 32)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (point cloud)");
+        if (want_pc && !pc_direct && w.pc2.ensure(n * 32)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (point cloud)");
         if (want_xyz && w.xyz.ensure(n * 12)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (points)");
         h->launches += launch_reproject_pack((const int16_t*)w.disp.p, cols, rows, h->cxd, (const double*)h->Qdev.p, h->qmask,
                                              (const int*)w.misc.p, rl, 1, want_xyz ? (float*)w.xyz.p : nullptr,
-                                             want_pc ? (uint8_t*)w.pc2.p : nullptr, st);
+                                             want_pc ? (pc_direct ? (uint8_t*)pc_direct : (uint8_t*)w.pc2.p) : nullptr, st);
     }
     rc = check_kernels(h, "process_pair");
     if (rc) return rc;
@@ -1045,7 +1060,7 @@ int run_frame_chain(b200s_handle* h, Work& w, const b200s_frame_io* io, const ui
     }
     if ((io->want & B200S_OUT_DISPARITY16) && (rc = copy_out(h, io->disparity16, w.disp.p, n * 2, od, st))) return rc;
     if (want_df && (rc = copy_out(h, io->disparity32f, w.df.p, n * 4, od, st))) return rc;
-    if (want_pc && (rc = copy_out(h, io->pointcloud2, w.pc2.p, n * 32, od, st))) return rc;
+    if (want_pc && !pc_direct && (rc = copy_out(h, io->pointcloud2, w.pc2.p, n * 32, od, st))) return rc;
     if (want_xyz && (rc = copy_out(h, io->points_xyz, w.xyz.p, n * 12, od, st))) return rc;
     return B200S_OK;
 }
