@@ -3,12 +3,17 @@
 // Same public method names, argument meaning and error behaviour as the reference class
 // (reference: include/gpuimageproc/GPUStereoProcessor.h:63-126, src/GPUStereoProcessor.cpp).  The reference takes
 // cv::Mat / sensor_msgs types; neither OpenCV's C++ headers nor ROS exist in the build image, so this header carries a
-// minimal `Mat` (rows, cols, OpenCV type code, contiguous bytes).  With -DB200S_WITH_OPENCV the cv::Mat overloads are
-// enabled as thin adapters.  The reference aborts on errors (assert / cv::Exception); here every failure throws
-// gpuimageproc::Error carrying the b200s_error code and message.
+// minimal `Mat` (rows, cols, OpenCV type code, contiguous bytes).  With -DB200S_WITH_OPENCV the cv::Mat overloads of the
+// reference signatures (uploadMat, downloadMat, rectifyImageLeft/Right, computeDisparity, computeDisparityBare,
+// filterSpeckles, printStats) are compiled in as thin adapters.  The reference aborts on errors (assert /
+// cv::Exception); here every failure throws gpuimageproc::Error carrying the b200s_error code and message.
 #pragma once
+#include <atomic>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
+#include <functional>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -67,10 +72,71 @@ struct CameraInfo   // sensor_msgs::CameraInfo subset (K, D, R, P, size)
     std::vector<double> D;
 };
 
-// payloads that GPUSenderImage / GPUSenderDisparity / GPUSenderPc2 (src/GpuSender*.cpp) would publish
-struct ImagePayload { int height = 0, width = 0, step = 0; std::string encoding; std::vector<uint8_t> data; };
-struct DisparityPayload { b200s_disparity_meta meta{}; std::vector<float> data; };
-struct PointCloud2Payload { b200s_pc2_meta meta{}; std::vector<uint8_t> data; };
+// Senders (src/GpuSenderIfc.cpp, src/GpuSender{Image,Disparity,Pc2}.cpp): each owns the page-locked host buffer its
+// message payload is packed into.  enqueueSend* only enqueues work on the side's stream; once the payload is complete the
+// CUDA runtime's callback thread calls the sender's publisher -- the reference's
+// cv::cuda::Stream::enqueueHostCallback(GPUSender::callback) (src/GpuSenderIfc.cpp:13-26) -- and wasDataSent() turns true.
+struct PinnedBuffer
+{
+    void *p = nullptr;
+    size_t bytes = 0;
+    explicit PinnedBuffer(size_t n) : bytes(n)
+    {
+        if (b200s_host_alloc(&p, n ? n : 1) != B200S_OK) throw Error(B200S_ENOMEM, "cudaHostAlloc failed");
+    }
+    ~PinnedBuffer() { b200s_host_free(p); }
+    PinnedBuffer(const PinnedBuffer &) = delete;
+    PinnedBuffer &operator=(const PinnedBuffer &) = delete;
+};
+
+class GPUSenderIfc
+{
+  public:
+    virtual ~GPUSenderIfc() {}
+    bool wasDataSent() const { return sent_.load(std::memory_order_acquire); }
+    const uint8_t *data() const { return static_cast<const uint8_t *>(buf_->p); }
+    size_t size() const { return buf_->bytes; }
+
+  protected:
+    explicit GPUSenderIfc(size_t bytes) : buf_(new PinnedBuffer(bytes)) {}
+    virtual void publish() = 0;
+    static void callback(void *self, int /*status*/)
+    {
+        GPUSenderIfc *s = static_cast<GPUSenderIfc *>(self);
+        s->publish();
+        s->sent_.store(true, std::memory_order_release);
+    }
+    std::unique_ptr<PinnedBuffer> buf_;
+    std::atomic<bool> sent_{false};
+    friend class GpuStereoProcessor;
+};
+
+struct ImagePayload { int height = 0, width = 0, step = 0; std::string encoding; const uint8_t *data = nullptr; size_t size = 0; };
+struct DisparityPayload { b200s_disparity_meta meta{}; const float *data = nullptr; size_t count = 0; };
+struct PointCloud2Payload { b200s_pc2_meta meta{}; const uint8_t *data = nullptr; size_t size = 0; };
+
+template <typename Payload>
+class GPUSender : public GPUSenderIfc
+{
+  public:
+    typedef std::function<void(const Payload &)> Publisher;     // stands for ros::Publisher::publish
+    GPUSender(size_t bytes, Publisher pub) : GPUSenderIfc(bytes), pub_(pub) {}
+    Payload payload;
+
+  protected:
+    void publish() override
+    {
+        if (pub_) pub_(payload);
+    }
+    Publisher pub_;
+};
+typedef GPUSender<ImagePayload> GPUSenderImage;
+typedef GPUSender<DisparityPayload> GPUSenderDisparity;
+typedef GPUSender<PointCloud2Payload> GPUSenderPc2;
+typedef std::shared_ptr<GPUSenderIfc> GPUSenderIfcPtr;
+typedef std::shared_ptr<GPUSenderImage> GPUSenderImagePtr;
+typedef std::shared_ptr<GPUSenderDisparity> GPUSenderDisparityPtr;
+typedef std::shared_ptr<GPUSenderPc2> GPUSenderPc2Ptr;
 
 class GpuStereoProcessor
 {
@@ -81,7 +147,12 @@ class GpuStereoProcessor
         if (rc) throw Error(rc, "b200s_create failed: no usable CUDA device (there is no CPU fallback)");
         ck(b200s_get_params(h_, &p_));
     }
-    ~GpuStereoProcessor() { b200s_destroy(h_); }
+    ~GpuStereoProcessor()
+    {
+        b200s_wait(h_, 0);      // pending sender callbacks reference buffers owned by senders_
+        senders_.clear();
+        b200s_destroy(h_);
+    }
     GpuStereoProcessor(const GpuStereoProcessor &) = delete;
     GpuStereoProcessor &operator=(const GpuStereoProcessor &) = delete;
 
@@ -94,6 +165,10 @@ class GpuStereoProcessor
     bool isStereoModelInitialised() { return b200s_is_model_initialised(h_) != 0; }
     void convertRawToColor(GpuMatSource side) { ck(b200s_convert_raw_to_color(h_, side)); }
     void convertRawToMono(GpuMatSource side) { ck(b200s_convert_raw_to_mono(h_, side)); }
+    void convertColor(GpuMatSource mat_source, GpuMatSource mat_dst, const std::string &src_encoding, const std::string &dst_encoding)
+    {
+        ck(b200s_convert_color(h_, mat_source, mat_dst, src_encoding.c_str(), dst_encoding.c_str()));
+    }
     void uploadMat(GpuMatSource mat_source, const Mat &m, std::string encoding = "") { ck(b200s_upload(h_, mat_source, m.data.data(), m.rows, m.cols, m.type, m.step(), encoding.c_str())); }
     void downloadMat(GpuMatSource mat_source, Mat &m)
     {
@@ -135,42 +210,70 @@ class GpuStereoProcessor
     void projectDisparityTo3DPoints(GpuMatSource disparity_src, GpuMatSource points_src) { ck(b200s_project_to_3d(h_, disparity_src, points_src)); }
     void waitForStream(GpuMatSource stream_source) { ck(b200s_wait(h_, stream_source & GPU_MAT_SIDE_MASK)); }
     void waitForAllStreams() { ck(b200s_wait(h_, 0)); }
-    void cleanSenders() {}
+    // src/GPUStereoProcessor.cpp:228-234: drop the senders whose data went out
+    void cleanSenders()
+    {
+        std::vector<GPUSenderIfcPtr> keep;
+        for (auto &s : senders_)
+            if (!s->wasDataSent()) keep.push_back(s);
+        senders_.swap(keep);
+    }
+    // printStats (src/GPUStereoProcessor.cpp:421-435) of a named buffer, reduced on the GPU
+    void printStats(const std::string &name, GpuMatSource mat)
+    {
+        double mn[4], mx[4], mean[4];
+        int ch = 0;
+        ck(b200s_mat_stats(h_, mat, mn, mx, mean, &ch));
+        for (int i = 0; i < ch; ++i) std::printf("ARRAY STATS:%s; channel:%d; min:%f; max:%f; mean:%f;\n", name.c_str(), i, mn[i], mx[i], mean[i]);
+    }
+    void printStats(const std::string &name, const Mat &mat)
+    {
+        uploadMat(GPU_MAT_SRC_R_DISPARITY_IMG, mat);      // a scratch id the chain does not use
+        printStats(name, GPU_MAT_SRC_R_DISPARITY_IMG);
+    }
     void filterSpeckles(GpuMatSource disparity_src) { sync(); ck(b200s_filter_speckles(h_, disparity_src)); }
     void filterSpeckles(Mat &disparity)   // CV_16SC1 in place, newVal = FILTERED
     {
         ck(b200s_filter_speckles_host(h_, disparity.ptr<int16_t>(), disparity.rows, disparity.cols, disparity.step(),
                                       (p_.min_disparity - 1) * 16, p_.speckle_window_size, p_.speckle_range));
     }
-    // senders: the packed message payloads (publishing itself is ROS glue)
-    ImagePayload enqueueSendImage(GpuMatSource source, const std::string &encoding)
+    // senders (src/GPUStereoProcessor.cpp:210-226): asynchronous like the reference -- the call returns once the work is
+    // enqueued; `pub` runs on the stream-callback thread when the payload is complete.  waitForStream / waitForAllStreams
+    // (or polling wasDataSent) tell when the message may be read.
+    GPUSenderImagePtr enqueueSendImage(GpuMatSource source, const std::string &encoding, GPUSenderImage::Publisher pub = nullptr)
     {
         int r, c, t, rows, cols, step;
         ck(b200s_mat_info(h_, source, &r, &c, &t));
-        ImagePayload p;
-        p.data.resize((size_t)r * c * Mat::elemSize(t));
-        ck(b200s_pack_image(h_, source, p.data.data(), p.data.size(), &rows, &cols, &step));
-        p.height = rows; p.width = cols; p.step = step; p.encoding = encoding;
-        return p;
+        auto s = std::make_shared<GPUSenderImage>((size_t)r * c * Mat::elemSize(t), pub);
+        senders_.push_back(s);
+        ck(b200s_pack_image_async(h_, source, s->buf_->p, s->buf_->bytes, &rows, &cols, &step, &GPUSenderIfc::callback, s.get()));
+        s->payload.height = rows; s->payload.width = cols; s->payload.step = step; s->payload.encoding = encoding;
+        s->payload.data = s->data(); s->payload.size = s->size();
+        return s;
     }
-    DisparityPayload enqueueSendDisparity(GpuMatSource source)
+    GPUSenderDisparityPtr enqueueSendDisparity(GpuMatSource source, GPUSenderDisparity::Publisher pub = nullptr)
     {
         int r, c, t;
-        ck(b200s_mat_info(h_, source, &r, &c, &t));
-        DisparityPayload p;
-        p.data.resize((size_t)r * c);
+        ck(b200s_mat_info(h_, planeOf(source), &r, &c, &t));
+        auto s = std::make_shared<GPUSenderDisparity>((size_t)r * c * 4, pub);
+        senders_.push_back(s);
         sync();
-        ck(b200s_pack_disparity(h_, source, p.data.data(), p.data.size() * 4, &p.meta));
-        return p;
+        s->payload.data = reinterpret_cast<const float *>(s->data()); s->payload.count = (size_t)r * c;
+        ck(b200s_pack_disparity_async(h_, source, s->buf_->p, s->buf_->bytes, &s->payload.meta, &GPUSenderIfc::callback, s.get()));
+        return s;
     }
-    PointCloud2Payload enqueueSendPoints(GpuMatSource disparity_source, GpuMatSource color_source)
+    // points_source: the reference passes GPU_MAT_SRC_L_POINTS2 (src/StereoProcessor.cpp:281, test/UTest.cpp:382); reprojection
+    // and packing are one kernel here, so that id (or the DISPARITY id) names the side whose fixed-point plane is read
+    GPUSenderPc2Ptr enqueueSendPoints(GpuMatSource points_source, GpuMatSource color_source, GPUSenderPc2::Publisher pub = nullptr)
     {
         int r, c, t;
-        ck(b200s_mat_info(h_, disparity_source, &r, &c, &t));
-        PointCloud2Payload p;
-        p.data.resize((size_t)r * c * 32);
-        ck(b200s_pack_pointcloud2(h_, disparity_source, color_source, p.data.data(), p.data.size(), &p.meta));
-        return p;
+        ck(b200s_mat_info(h_, planeOf(points_source), &r, &c, &t));
+        auto s = std::make_shared<GPUSenderPc2>((size_t)r * c * 32, pub);
+        senders_.push_back(s);
+        s->payload.data = s->data(); s->payload.size = s->size();
+        ck(b200s_pack_pointcloud2_async(h_, points_source, color_source, s->buf_->p, s->buf_->bytes, &s->payload.meta,
+                                        &GPUSenderIfc::callback, s.get()));
+        return s;
     }
     // parameters (src/GPUStereoProcessor.cpp:202-208,389-419 plus the cv::StereoBM ones GPU.cfg lacked)
     void setPreFilterType(int filter_type) { p_.pre_filter_type = filter_type; }
@@ -189,6 +292,47 @@ class GpuStereoProcessor
     void setMaxSpeckleDiff(double maxSpeckleDiff) { p_.speckle_range = (int)(maxSpeckleDiff * 16 + 0.5); }   // integer-disparity units
     void setSpeckleRange(int raw_x16) { p_.speckle_range = raw_x16; }
     b200s_handle *handle() { return h_; }
+
+#ifdef B200S_WITH_OPENCV
+    // ---- cv::Mat overloads with the reference's exact signatures (GPUStereoProcessor.h:73-96) ----------------------
+    void uploadMat(GpuMatSource mat_source, const cv::Mat &cv_mat, std::string encoding = "")
+    {
+        ck(b200s_upload(h_, mat_source, cv_mat.data, cv_mat.rows, cv_mat.cols, cv_mat.type(), cv_mat.step, encoding.c_str()));
+        ck(b200s_wait(h_, mat_source & GPU_MAT_SIDE_MASK));     // pageable cv::Mat memory may be released by the caller
+    }
+    void downloadMat(GpuMatSource mat_source, cv::Mat &cv_mat)
+    {
+        int r, c, t;
+        ck(b200s_mat_info(h_, mat_source, &r, &c, &t));
+        cv_mat.create(r, c, t);
+        ck(b200s_download(h_, mat_source, cv_mat.data, cv_mat.step));
+    }
+    void rectifyImageLeft(const cv::Mat &source, cv::Mat &dest, int interpolation = B200S_INTER_LINEAR) { rectifySideCv(GPU_MAT_SIDE_L, source, dest, interpolation); }
+    void rectifyImageRight(const cv::Mat &source, cv::Mat &dest, int interpolation = B200S_INTER_LINEAR) { rectifySideCv(GPU_MAT_SIDE_R, source, dest, interpolation); }
+    void computeDisparityBare(const cv::Mat &left, const cv::Mat &right, cv::Mat &disparity)
+    {
+        uploadMat(GPU_MAT_SRC_L_RECT_MONO, left);
+        uploadMat(GPU_MAT_SRC_R_RECT_MONO, right);
+        computeDisparity(GPU_MAT_SRC_L_RECT_MONO, GPU_MAT_SRC_R_RECT_MONO, GPU_MAT_SRC_L_DISPARITY);
+        downloadMat(GPU_MAT_SRC_L_DISPARITY, disparity);
+    }
+    void computeDisparity(cv::Mat &left, cv::Mat &right, cv::Mat &disparity)
+    {
+        cv::Mat d16;
+        computeDisparityBare(left, right, d16);
+        downloadMat(GPU_MAT_SRC_L_DISPARITY_32F, disparity);
+    }
+    void filterSpeckles(cv::Mat &disparity)     // CV_16SC1 in place, newVal = FILTERED (GPUStereoProcessor.cpp:367-385)
+    {
+        ck(b200s_filter_speckles_host(h_, reinterpret_cast<int16_t *>(disparity.data), disparity.rows, disparity.cols, disparity.step,
+                                      (p_.min_disparity - 1) * 16, p_.speckle_window_size, p_.speckle_range));
+    }
+    void printStats(const std::string &name, cv::Mat &mat)
+    {
+        uploadMat(GPU_MAT_SRC_R_DISPARITY_IMG, mat);
+        printStats(name, GPU_MAT_SRC_R_DISPARITY_IMG);
+    }
+#endif
 
   private:
     void ck(int rc)
@@ -213,8 +357,22 @@ class GpuStereoProcessor
         rectifyImage(raw, out, interp);
         downloadMat(out, dst);
     }
+#ifdef B200S_WITH_OPENCV
+    void rectifySideCv(GpuMatSource side, const cv::Mat &src, cv::Mat &dst, int interp)
+    {
+        GpuMatSource raw = GPU_MAT_SRC_RAW | side, out = (src.channels() == 1 ? GPU_MAT_SRC_RECT_MONO : GPU_MAT_SRC_RECT_COLOR) | side;
+        uploadMat(raw, src);
+        rectifyImage(raw, out, interp);
+        downloadMat(out, dst);
+    }
+#endif
+    static GpuMatSource planeOf(GpuMatSource id)
+    {
+        return (id & (GPU_MAT_SRC_POINTS2 | GPU_MAT_SRC_DISPARITY_32F)) ? (GPU_MAT_SRC_DISPARITY | (id & GPU_MAT_SIDE_MASK)) : id;
+    }
     b200s_handle *h_ = nullptr;
     b200s_params p_{};
+    std::vector<GPUSenderIfcPtr> senders_;
 };
 
 }  // namespace gpuimageproc

@@ -98,7 +98,9 @@ typedef struct {
 
 /* ---- lifecycle ----------------------------------------------------------------------------------------------- */
 /* GpuStereoProcessor::GpuStereoProcessor()  (src/GPUStereoProcessor.cpp:12-39).  device = CUDA ordinal.
- * Initial parameters are the reference constructor's: numDisparities 48, blockSize 19, preFilterSize 5. */
+ * Initial parameters are the reference constructor's: numDisparities 48, blockSize 19, preFilterSize 5,
+ * PREFILTER_XSOBEL (:27-30), texture threshold 3, uniqueness 0, disp12MaxDiff 0 (copied from the cuda matcher's getters).
+ * Every entry point makes the handle's device current for the call and restores the caller's current device. */
 int b200s_create(int device, b200s_handle** out);
 int b200s_destroy(b200s_handle* h);
 const char* b200s_last_error_string(const b200s_handle* h);
@@ -132,6 +134,9 @@ int b200s_device_ptr(b200s_handle* h, int mat_id, void** dptr, size_t* bytes);
  * Supported raw encodings: mono8, bgr8, rgb8 (others: B200S_EUNSUPPORTED). */
 int b200s_convert_raw_to_mono(b200s_handle* h, int side);
 int b200s_convert_raw_to_color(b200s_handle* h, int side);
+/* convertColor(src, dst, src_encoding, dst_encoding) (src/GPUStereoProcessor.cpp:119-172): mono8 / bgr8 / rgb8 sources,
+ * mono8 / bgr8 destinations; anything else B200S_EUNSUPPORTED (the reference throws on unknown encodings) */
+int b200s_convert_color(b200s_handle* h, int src_id, int dst_id, const char* src_encoding, const char* dst_encoding);
 /* rectifyImage (src/GPUStereoProcessor.cpp:236-250); CPU-semantics result (bit-exact to cv::remap fixed point) */
 int b200s_rectify(b200s_handle* h, int src_id, int dst_id, int interpolation);
 /* computeDisparity (src/GPUStereoProcessor.cpp:264-303) with cv::StereoBM semantics -> CV_16SC1 x16 in disp_id;
@@ -153,16 +158,37 @@ int b200s_filter_speckles_host(b200s_handle* h, int16_t* img, int rows, int cols
                                int max_size, int max_diff);
 /* computeDisparityImage (src/GPUStereoProcessor.cpp:323-330): colour-coded BGRA8 */
 int b200s_compute_disparity_image(b200s_handle* h, int disp_id, int img_id);
-/* projectDisparityTo3DPoints (src/GPUStereoProcessor.cpp:332-346): CV_32FC3, missing -> Z = 10000 */
+/* projectDisparityTo3DPoints (src/GPUStereoProcessor.cpp:332-346): CV_32FC3, missing -> Z = 10000.  disp_id may be the
+ * DISPARITY or, like the reference's call (test/UTest.cpp:378), the DISPARITY_32F id of a side: both read that side's
+ * fixed-point plane. */
 int b200s_project_to_3d(b200s_handle* h, int disp_id, int points_id);
 /* waitForStream / waitForAllStreams (src/GPUStereoProcessor.cpp:348-354); side 0 = all */
 int b200s_wait(b200s_handle* h, int side);
 
 /* ---- message payload packing (replaces GpuSender*::fillInData, src/GpuSender{Image,Disparity,Pc2}.cpp) ------ */
+/* Synchronous forms: return with the payload complete in dst.  b200s_pack_pointcloud2 accepts the DISPARITY id or, like
+ * the reference (src/StereoProcessor.cpp:281, test/UTest.cpp:382), the POINTS2 id of the side.  When dst is page-locked
+ * host memory (b200s_host_alloc, cudaHostAlloc, cudaHostRegister) the float-disparity and PointCloud2 kernels store their
+ * records straight into it ("pack straight into pinned host buffers"); pageable dst goes through a double-buffered pinned
+ * staging copy. */
 int b200s_pack_image(b200s_handle* h, int mat_id, void* dst, size_t cap_bytes, int* rows, int* cols, int* step);
 int b200s_pack_disparity(b200s_handle* h, int disp_id, void* dst, size_t cap_bytes, b200s_disparity_meta* meta);
 int b200s_pack_pointcloud2(b200s_handle* h, int disp_id, int color_id, void* dst, size_t cap_bytes,
                            b200s_pc2_meta* meta);
+/* Asynchronous forms = the reference's senders (src/GpuSenderIfc.cpp:13-26: publish from a stream callback): the work
+ * is enqueued on the side's stream and `done(user, status)` runs on the CUDA runtime's callback thread once the payload
+ * is complete in dst.  No CUDA / b200s calls inside `done`.  meta is filled before the call returns.  done = NULL makes
+ * the call synchronous. */
+typedef void (*b200s_done_fn)(void* user, int status);
+int b200s_pack_image_async(b200s_handle* h, int mat_id, void* dst, size_t cap_bytes, int* rows, int* cols, int* step,
+                           b200s_done_fn done, void* user);
+int b200s_pack_disparity_async(b200s_handle* h, int disp_id, void* dst, size_t cap_bytes, b200s_disparity_meta* meta,
+                               b200s_done_fn done, void* user);
+int b200s_pack_pointcloud2_async(b200s_handle* h, int disp_id, int color_id, void* dst, size_t cap_bytes,
+                                 b200s_pc2_meta* meta, b200s_done_fn done, void* user);
+/* 1 (default): pack kernels write straight into page-locked destinations; 0: always pack into HBM and copy (also
+ * environment B200S_PACK_DIRECT=0).  The bytes are identical. */
+int b200s_set_pack_mode(b200s_handle* h, int direct);
 
 /* ---- fused frame path: the whole StereoProcessor::imageCb chain (src/StereoProcessor.cpp:157-298) ----------- */
 enum {
@@ -171,12 +197,14 @@ enum {
     B200S_OUT_DISPARITY16 = 1 << 2, /* s16 H*W            */
     B200S_OUT_DISPARITY32F = 1 << 3,/* f32 H*W            */
     B200S_OUT_POINTCLOUD2 = 1 << 4, /* 32 B * H*W         */
-    B200S_OUT_POINTS_XYZ = 1 << 5   /* f32 3 * H*W        */
+    B200S_OUT_POINTS_XYZ = 1 << 5,  /* f32 3 * H*W        */
+    B200S_OUT_RECT_COLOR_L = 1 << 6 /* u8  3 * H*W (BGR); needs color_left                                  */
 };
+enum { B200S_COLOR_NONE = 0, B200S_COLOR_BGR8 = 1, B200S_COLOR_RGB8 = 2 };
 typedef struct {
     uint32_t want;          /* which products to compute (B200S_OUT_*)                                      */
     int rectify;            /* 1: inputs are raw images, rectify first; 0: inputs are already rectified     */
-    int inputs_on_device;   /* 1: left/right are device pointers                                            */
+    int inputs_on_device;   /* 1: left/right/color_left are device pointers                                 */
     int outputs_on_device;  /* 1: the destination pointers below are device pointers                        */
     void* rect_left;        /* destinations; NULL = leave the product in the slot's device buffer           */
     void* rect_right;
@@ -184,6 +212,13 @@ typedef struct {
     void* disparity32f;
     void* pointcloud2;
     void* points_xyz;
+    /* colour camera (src/StereoProcessor.cpp:201-217,239-256: L_RECT_COLOR feeds enqueueSendPoints): optional raw LEFT
+     * colour image, 8UC3 of the slot size.  It is rectified like the mono image and colours the PointCloud2 records; when
+     * the `left` argument of the call is NULL the matcher's grey image is derived from it (convertRawToMono). */
+    const void* color_left;
+    int color_encoding;     /* B200S_COLOR_BGR8 / B200S_COLOR_RGB8 when color_left is set                   */
+    int rows, cols;         /* size of the caller's images; 0 = unchecked, otherwise must equal the slot size */
+    void* rect_color_left;  /* destination of B200S_OUT_RECT_COLOR_L                                        */
 } b200s_frame_io;
 
 /* Frame slots: independent stream + device buffers each, so that copy-in, compute and copy-out of consecutive
@@ -191,15 +226,25 @@ typedef struct {
  * that slot's outputs are complete.  Image size = calibration size (or rows/cols when no calibration is needed). */
 int b200s_configure_slots(b200s_handle* h, int n_slots, int rows, int cols);
 int b200s_process_pair_async(b200s_handle* h, int slot, const void* left, const void* right, const b200s_frame_io* io);
+/* Batches ("batched stereo stream"): a slot can hold up to frames_per_slot (<= 32) frames and process them together --
+ * every kernel of the chain takes the whole batch in one launch (frame = a grid dimension), so small images still fill
+ * all SMs and the matcher works on tall row bands.  left / right / ios are arrays of n_frames entries; all frames of a
+ * batch must ask for the same products and flags, each has its own destinations.  Results are identical to n_frames
+ * single calls. */
+int b200s_configure_slots_batched(b200s_handle* h, int n_slots, int rows, int cols, int frames_per_slot);
+int b200s_process_batch_async(b200s_handle* h, int slot, int n_frames, const void* const* left, const void* const* right,
+                              const b200s_frame_io* ios);
 int b200s_wait_slot(b200s_handle* h, int slot);
 /* non-blocking: *done = 1 when the slot's last frame (outputs included) is complete; the polled counterpart of the
  * reference's stream callback that publishes a message (src/GpuSenderIfc.cpp:13-26) */
 int b200s_poll_slot(b200s_handle* h, int slot, int* done);
 int b200s_slot_device_ptr(b200s_handle* h, int slot, uint32_t which /* one B200S_OUT_* */, void** dptr, size_t* bytes);
+int b200s_slot_frame_device_ptr(b200s_handle* h, int slot, int frame, uint32_t which, void** dptr, size_t* bytes);
 /* synchronous convenience: slot 0, process + wait */
 int b200s_process_pair(b200s_handle* h, const void* left, const void* right, const b200s_frame_io* io);
 /* The frame chain of a slot is captured into a CUDA graph the second time it runs with the same parameters, products
- * and output addresses, and replayed with one cudaGraphLaunch afterwards (inputs are copied into the slot first).
+ * and output addresses, and replayed with one cudaGraphLaunch afterwards (inputs are copied into the slot first); a
+ * slot caches a few graphs, so alternating destination buffers keep replaying.
  * on = 0 launches every kernel individually (also: environment B200S_GRAPH=0).  Results are identical. */
 int b200s_set_graph_mode(b200s_handle* h, int on);
 uint64_t b200s_graph_replays(const b200s_handle* h);
@@ -236,6 +281,14 @@ uint64_t b200s_kernel_launches(const b200s_handle* h);
  * valid after b200s_wait_slot.  evals_effective receives the (pixel, disparity) evaluations it performed. */
 int b200s_last_bm_time(b200s_handle* h, int slot, float* ms, double* evals_effective);
 int b200s_enable_timing(b200s_handle* h, int on);
+/* device time of each stage of the slot's last (timed) frame chain: rectify + prefilter, matcher, validate + speckle,
+ * disparity -> float, reproject + PointCloud2 pack */
+enum { B200S_STAGE_RECTIFY = 0, B200S_STAGE_MATCH = 1, B200S_STAGE_POST = 2, B200S_STAGE_TOFLOAT = 3, B200S_STAGE_PACK = 4,
+       B200S_STAGE_COUNT = 5 };
+int b200s_last_stage_times(b200s_handle* h, int slot, float* ms /* [B200S_STAGE_COUNT] */);
+/* printStats (src/GPUStereoProcessor.cpp:421-435): per-channel min / max / mean of a named buffer, reduced on the GPU.
+ * mn / mx / mean receive one value per channel (up to 4); *channels the channel count.  Syncs that side's stream. */
+int b200s_mat_stats(b200s_handle* h, int mat_id, double* mn, double* mx, double* mean, int* channels);
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA runtime of their own */
 int b200s_host_alloc(void** p, size_t bytes);
 int b200s_host_free(void* p);

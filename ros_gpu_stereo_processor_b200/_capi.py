@@ -18,7 +18,10 @@ SRC_DISPARITY, SRC_DISPARITY_32F, SRC_DISPARITY_IMG, SRC_POINTS2 = 128, 256, 512
 T_8UC1, T_16SC1, T_32FC1, T_8UC3, T_32FC3, T_8UC4 = 0, 3, 5, 16, 21, 24
 INTER_NEAREST, INTER_LINEAR = 0, 1
 
-OUT_RECT_L, OUT_RECT_R, OUT_DISPARITY16, OUT_DISPARITY32F, OUT_POINTCLOUD2, OUT_POINTS_XYZ = 1, 2, 4, 8, 16, 32
+OUT_RECT_L, OUT_RECT_R, OUT_DISPARITY16, OUT_DISPARITY32F, OUT_POINTCLOUD2, OUT_POINTS_XYZ, OUT_RECT_COLOR_L = 1, 2, 4, 8, 16, 32, 64
+COLOR_NONE, COLOR_BGR8, COLOR_RGB8 = 0, 1, 2
+STAGE_NAMES = ("rectify_prefilter", "match", "post", "to_float", "reproject_pack")
+MAX_BATCH = 32
 
 
 class CamInfo(C.Structure):
@@ -49,7 +52,11 @@ class FrameIO(C.Structure):
     _fields_ = [("want", C.c_uint32), ("rectify", C.c_int), ("inputs_on_device", C.c_int),
                 ("outputs_on_device", C.c_int), ("rect_left", C.c_void_p), ("rect_right", C.c_void_p),
                 ("disparity16", C.c_void_p), ("disparity32f", C.c_void_p), ("pointcloud2", C.c_void_p),
-                ("points_xyz", C.c_void_p)]
+                ("points_xyz", C.c_void_p), ("color_left", C.c_void_p), ("color_encoding", C.c_int),
+                ("rows", C.c_int), ("cols", C.c_int), ("rect_color_left", C.c_void_p)]
+
+
+DONE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int)
 
 
 # every symbol include/b200_stereo.h declares: name -> (restype, argtypes)
@@ -110,6 +117,16 @@ SYMBOLS = {
     "b200s_set_graph_mode": (C.c_int, [H, C.c_int]),
     "b200s_graph_replays": (C.c_uint64, [H]),
     "b200s_int_peak": (C.c_int, [H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "b200s_convert_color": (C.c_int, [H, C.c_int, C.c_int, C.c_char_p, C.c_char_p]),
+    "b200s_pack_image_async": (C.c_int, [H, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), DONE_FN, C.c_void_p]),
+    "b200s_pack_disparity_async": (C.c_int, [H, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(DisparityMeta), DONE_FN, C.c_void_p]),
+    "b200s_pack_pointcloud2_async": (C.c_int, [H, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(Pc2Meta), DONE_FN, C.c_void_p]),
+    "b200s_set_pack_mode": (C.c_int, [H, C.c_int]),
+    "b200s_configure_slots_batched": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "b200s_process_batch_async": (C.c_int, [H, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(FrameIO)]),
+    "b200s_slot_frame_device_ptr": (C.c_int, [H, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "b200s_last_stage_times": (C.c_int, [H, C.c_int, C.POINTER(C.c_float)]),
+    "b200s_mat_stats": (C.c_int, [H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
 }
 
 _lib = None

@@ -1,9 +1,8 @@
-// Host pipeline + extern "C" layer of libb200stereo.so (declared in include/b200_stereo.h).
+// Named-buffer API + extern "C" layer of libb200stereo.so (declared in include/b200_stereo.h).
 // Mirrors the state and method set of gpuimageproc::GpuStereoProcessor
 // (reference: include/gpuimageproc/GPUStereoProcessor.h:63-126, src/GPUStereoProcessor.cpp) with the
-// OpenCV / image_geometry calls replaced by the sm_100a kernels in this directory.
-#include "../../include/b200_stereo.h"
-#include "kernels.h"
+// OpenCV / image_geometry calls replaced by the sm_100a kernels in this directory.  The fused frame path lives in slots.cu.
+#include "handle.h"
 
 #include <cmath>
 #include <cstdio>
@@ -11,130 +10,10 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
-#include <string>
-#include <unordered_map>
-#include <vector>
 
 using namespace b200s;
 
-namespace {
-
-int elem_size(int type)
-{
-    switch (type) {
-        case B200S_8UC1: return 1;
-        case B200S_16SC1: return 2;
-        case B200S_32FC1: return 4;
-        case B200S_8UC3: return 3;
-        case B200S_32FC3: return 12;
-        case B200S_8UC4: return 4;
-        default: return 0;
-    }
-}
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t bytes)
-    {
-        if (bytes <= cap) return 0;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        if (cudaMalloc(&p, bytes) != cudaSuccess) return -1;
-        cap = bytes;
-        return 0;
-    }
-    void release()
-    {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
-struct Mat {
-    DevBuf buf;
-    int rows = 0, cols = 0, type = -1;
-    std::string enc;
-    size_t bytes() const { return (size_t)rows * cols * elem_size(type); }
-    bool empty() const { return type < 0 || rows == 0 || cols == 0; }
-};
-
-// all device scratch one pipeline instance needs
-struct Work {
-    cudaStream_t st = nullptr;
-    bool own_stream = false;
-    DevBuf rawL, rawR, rectL, rectR, preL, preR, disp, cost, df, xyz, pc2, vol, ccl, normtmp, misc;
-    cudaEvent_t ev_bm0 = nullptr, ev_bm1 = nullptr, ev_done = nullptr;
-    double last_evals = 0;
-    bool timed = false;
-    // CUDA graph of the frame chain of this slot: the first frame with a given key runs eagerly (allocations, map
-    // build), the second is captured, the following ones are replayed with one cudaGraphLaunch
-    std::string gkey, warm_key;
-    cudaGraphExec_t gexec = nullptr;
-    uint64_t glaunches = 0;
-    double gevals = 0;
-    void drop_graph()
-    {
-        if (gexec) cudaGraphExecDestroy(gexec);
-        gexec = nullptr;
-        gkey.clear();
-        warm_key.clear();
-    }
-    void release()
-    {
-        drop_graph();
-        DevBuf* all[] = {&rawL, &rawR, &rectL, &rectR, &preL, &preR, &disp, &cost, &df, &xyz, &pc2, &vol, &ccl, &normtmp, &misc};
-        for (DevBuf* b : all) b->release();
-        if (ev_bm0) cudaEventDestroy(ev_bm0);
-        if (ev_bm1) cudaEventDestroy(ev_bm1);
-        if (ev_done) cudaEventDestroy(ev_done);
-        if (own_stream && st) cudaStreamDestroy(st);
-        ev_bm0 = ev_bm1 = ev_done = nullptr;
-        st = nullptr;
-    }
-};
-
-struct Camera {
-    b200s_caminfo info;
-    CamModel cm;
-    DevBuf map;   // int2 per pixel
-    bool map_valid = false;
-};
-
-}  // namespace
-
-struct b200s_handle {
-    int device = 0;
-    std::string err;
-    b200s_params prm;
-    bool model_ok = false;
-    bool rect_fly = false;
-    bool timing = false;
-    Camera cam[2];
-    double Q[16];
-    double baseline = 0, fx_right = 0, cxd = 0;
-    unsigned qmask = 0xFFFFu;
-    DevBuf Qdev;
-    std::unordered_map<int, Mat> mats;
-    cudaStream_t l_strm = nullptr, r_strm = nullptr;
-    cudaEvent_t ev_r = nullptr;
-    Work w0;                  // scratch of the named-buffer API (runs on l_strm)
-    std::vector<Work> slots;
-    std::vector<cudaEvent_t> batch_end;
-    cudaEvent_t batch_start = nullptr;
-    int slot_rows = 0, slot_cols = 0;
-    uint64_t launches = 0;
-    void* stage_host[2] = {nullptr, nullptr};   // pinned staging for device->host copies into pageable user memory
-    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
-    uint64_t model_version = 0;   // bumped by every calibration change (part of the graph key)
-    int use_graphs = 1;           // B200S_GRAPH=0 or b200s_set_graph_mode(h, 0) turns the replay off
-    uint64_t graph_replays = 0;
-    int pack_direct = 0;          // 1: the pack kernels store straight into pinned (mapped) host destinations
-};
-
-namespace {
+namespace b200s {
 
 int fail(b200s_handle* h, int code, const std::string& msg)
 {
@@ -142,22 +21,19 @@ int fail(b200s_handle* h, int code, const std::string& msg)
     return code;
 }
 
-#define CUDA_OK(h, call)                                                                        \
-    do {                                                                                        \
-        cudaError_t e__ = (call);                                                               \
-        if (e__ != cudaSuccess)                                                                 \
-            return fail(h, B200S_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));  \
-    } while (0)
-
-struct DeviceGuard {
-    explicit DeviceGuard(int d) { cudaSetDevice(d); }
-};
-
 int check_kernels(b200s_handle* h, const char* what)
 {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, B200S_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
     return B200S_OK;
+}
+
+void* mapped_alias(const void* p)
+{
+    if (!p) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
 // Device -> host copy of a packed payload followed by a stream sync.  Pinned (or registered) destinations take one DMA.
@@ -301,6 +177,10 @@ int load_caminfo_yaml(b200s_handle* h, const char* path, b200s_caminfo* ci)
     return B200S_OK;
 }
 
+}  // namespace b200s
+
+namespace {
+
 Mat* find_mat(b200s_handle* h, int id)
 {
     auto it = h->mats.find(id);
@@ -320,23 +200,66 @@ int alloc_mat(b200s_handle* h, int id, int rows, int cols, int type, const char*
 
 cudaStream_t stream_of(b200s_handle* h, int id) { return (id & B200S_SIDE_R) && !(id & B200S_SIDE_L) ? h->r_strm : h->l_strm; }
 
+// The left stream reads right-side planes (matcher, point cloud); work that overwrites them on the right stream waits
+// for the last such reader (the reverse dependency is ev_r; the reference has neither).
+cudaError_t order_after_left_readers(b200s_handle* h, cudaStream_t st)
+{
+    return st == h->r_strm ? cudaStreamWaitEvent(st, h->ev_l, 0) : cudaSuccess;
+}
+
+// The reference hands its POINTS2 / DISPARITY_32F ids to projectDisparityTo3DPoints and enqueueSendPoints
+// (test/UTest.cpp:378-382, src/StereoProcessor.cpp:281); here reprojection and packing read the fixed-point plane of
+// the same side directly.
+int fixed_point_plane_of(int id)
+{
+    return (id & (B200S_SRC_POINTS2 | B200S_SRC_DISPARITY_32F)) ? (B200S_SRC_DISPARITY | (id & B200S_SIDE_MASK)) : id;
+}
+
+}  // namespace
+
+namespace b200s {
+
 int ensure_map(b200s_handle* h, int side /*0 L, 1 R*/, cudaStream_t st)
 {
     Camera& c = h->cam[side];
     if (c.map_valid) return B200S_OK;
-    size_t n = (size_t)c.info.width * c.info.height;
-    if (c.map.ensure(n * sizeof(int2)) != 0) return fail(h, B200S_ENOMEM, "cudaMalloc failed for the rectification map");
-    h->launches += launch_build_map(c.cm, c.info.width, c.info.height, (int2*)c.map.p, st);
-    // the map may be consumed on another stream: make it visible everywhere once
-    CUDA_OK(h, cudaStreamSynchronize(st));
+    const size_t n = (size_t)c.info.width * c.info.height;
+    if (h->flagdev.ensure(256)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (flags)");
+    // 4 B/px delta table first; a calibration whose shifts exceed +-1024 px falls back to the 8 B/px absolute table
+    static const int force_abs = getenv("B200S_MAP_ABS32") ? atoi(getenv("B200S_MAP_ABS32")) : 0;
+    for (int attempt = force_abs ? 1 : 0; attempt < 2; ++attempt) {
+        const MapMode mode = attempt == 0 ? MAP_DELTA16 : MAP_ABS32;
+        if (c.map.ensure(n * (mode == MAP_DELTA16 ? 4 : 8))) return fail(h, B200S_ENOMEM, "cudaMalloc failed for the rectification map");
+        h->launches += launch_build_map(c.cm, c.info.width, c.info.height, c.map.p, mode, (int*)h->flagdev.p, st);
+        int overflow = 0;
+        if (mode == MAP_DELTA16) CUDA_OK(h, cudaMemcpyAsync(&overflow, h->flagdev.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        // the map may be consumed on another stream: make it visible everywhere once
+        CUDA_OK(h, cudaStreamSynchronize(st));
+        c.map_mode = mode;
+        if (!overflow) break;
+    }
     c.map_valid = true;
     return check_kernels(h, "build_map");
 }
 
-// pitched prefiltered planes with readable slack on both sides (zeroed once so that stray reads are defined)
-int ensure_pre_planes(b200s_handle* h, Work& w, int rows, int cols)
+int map_for(b200s_handle* h, int side, cudaStream_t st, MapMode* mode, const void** map)
 {
-    size_t need = plane_bytes(cols, rows);
+    if (h->rect_fly) {
+        *mode = MAP_FLY;
+        *map = nullptr;
+        return B200S_OK;
+    }
+    int rc = ensure_map(h, side, st);
+    if (rc) return rc;
+    *mode = h->cam[side].map_mode;
+    *map = h->cam[side].map.p;
+    return B200S_OK;
+}
+
+// pitched prefiltered planes with readable slack on both sides (zeroed once so that stray reads are defined)
+int ensure_pre_planes(b200s_handle* h, Work& w, int rows, int cols, int nf)
+{
+    const size_t need = plane_stride(cols, rows) * (size_t)nf;
     for (DevBuf* b : {&w.preL, &w.preR}) {
         if (b->cap < need) {
             if (b->ensure(need)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (prefilter planes)");
@@ -346,9 +269,9 @@ int ensure_pre_planes(b200s_handle* h, Work& w, int rows, int cols)
     return B200S_OK;
 }
 
-// prefilter + match + post-filters on rectified device planes; disp must hold rows*cols int16
+// prefilter + match + post-filters on rectified device planes; disp must hold rows*cols int16 per frame
 int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, bool already_prefiltered, int rows,
-                  int cols, int16_t* disp, cudaStream_t st)
+                  int cols, int16_t* disp, cudaStream_t st, int nf, size_t src_stride, size_t disp_stride)
 {
     const b200s_params& p = h->prm;
     int rc = validate_params(h, p);
@@ -357,33 +280,37 @@ int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, 
         return fail(h, B200S_EINVAL, "SADWindowSize must be odd, be within 5..255 and be not larger than image width or height");
     size_t n = (size_t)rows * cols;
     BMConfig cfg = bm_config(p);
-    const size_t pitch = plane_pitch(cols);
+    const size_t pitch = plane_pitch(cols), pstride = plane_stride(cols, rows);
+    if (nf <= 1 && disp_stride == 0) disp_stride = n * 2;
+    const int cap_nf = nf > w.depth ? nf : w.depth;     // buffers are sized for the slot's whole batch once
     if (!already_prefiltered) {
-        int rc2 = ensure_pre_planes(h, w, rows, cols);
+        int rc2 = ensure_pre_planes(h, w, rows, cols, cap_nf);
         if (rc2) return rc2;
         uint8_t* pl = (uint8_t*)w.preL.p + PLANE_LEAD;
         uint8_t* pr = (uint8_t*)w.preR.p + PLANE_LEAD;
         if (p.pre_filter_type == 1) {
-            h->launches += launch_prefilter_xsobel(L, pl, pitch, cols, rows, p.pre_filter_cap, st);
-            h->launches += launch_prefilter_xsobel(R, pr, pitch, cols, rows, p.pre_filter_cap, st);
+            // tiled x-Sobel of both sides (and all frames) in one launch: the fused kernel with the identity map
+            h->launches += launch_rectify_xsobel_pair(L, R, cols, rows, MAP_NONE, nullptr, nullptr, h->cam[0].cm, h->cam[1].cm, nullptr,
+                                                      nullptr, pl, pr, pitch, cols, rows, p.pre_filter_cap, st, nf, src_stride, 0, pstride);
         } else {
-            const int one = launch_norm_prefilter_pair(L, R, cols, rows, false, nullptr, nullptr, h->cam[0].cm, h->cam[1].cm, nullptr, nullptr,
-                                                       pl, pr, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, st);
+            const int one = launch_norm_prefilter_pair(L, R, cols, rows, MAP_NONE, nullptr, nullptr, h->cam[0].cm, h->cam[1].cm, nullptr, nullptr,
+                                                       pl, pr, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, st, nf, src_stride, 0, pstride);
             h->launches += one;
-            if (!one) {     // preFilterSize > 21: two passes through a scratch plane
+            if (!one) {     // preFilterSize > 21: two passes through a scratch plane, frame by frame
                 if (w.normtmp.ensure(n * sizeof(int))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (prefilter scratch)");
-                h->launches += launch_prefilter_norm(L, pl, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, (int*)w.normtmp.p, st);
-                h->launches += launch_prefilter_norm(R, pr, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, (int*)w.normtmp.p, st);
+                for (int f = 0; f < nf; ++f) {
+                    h->launches += launch_prefilter_norm(L + f * src_stride, pl + f * pstride, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, (int*)w.normtmp.p, st);
+                    h->launches += launch_prefilter_norm(R + f * src_stride, pr + f * pstride, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, (int*)w.normtmp.p, st);
+                }
             }
         }
     }
     // the matcher always reads the pitched, slack-padded prefiltered planes of this Work
     const uint8_t* Lp = (const uint8_t*)w.preL.p + PLANE_LEAD;
     const uint8_t* Rp = (const uint8_t*)w.preR.p + PLANE_LEAD;
-    (void)L; (void)R;
     int16_t* cost = nullptr;
     if (cfg.disp12MaxDiff >= 0) {
-        if (w.cost.ensure(n * sizeof(int16_t))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (cost plane)");
+        if (w.cost.ensure(disp_stride * cap_nf)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (cost plane)");
         cost = (int16_t*)w.cost.p;
     }
     if (w.vol.ensure(bm_scratch_bytes(cols, rows, cfg))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (matcher scratch)");
@@ -392,20 +319,26 @@ int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, 
         if (!w.ev_bm0) { cudaEventCreate(&w.ev_bm0); cudaEventCreate(&w.ev_bm1); }
         cudaEventRecord(w.ev_bm0, st);
     }
-    int l = launch_block_match(Lp, Rp, pitch, cols, rows, cfg, disp, cost, &sc, st, &w.last_evals);
+    int l = launch_block_match(Lp, Rp, pitch, cols, rows, cfg, disp, cost, &sc, st, &w.last_evals, nf, pstride, disp_stride);
+    w.last_evals *= nf;
     if (h->timing) { cudaEventRecord(w.ev_bm1, st); w.timed = true; }
     if (l < 0) return fail(h, B200S_ECUDA, "block matcher launch failed (code " + std::to_string(l) + "): " + cudaGetErrorString(cudaGetLastError()));
     h->launches += l;
     if (cfg.disp12MaxDiff >= 0) {
-        int v = launch_validate_disp12(disp, cost, cols, rows, cfg, st);
-        if (v < 0) return fail(h, B200S_EUNSUPPORTED, "disp12MaxDiff needs image width <= 65535");
-        h->launches += v;     // the valid-ROI mask of the rows is applied by the same kernel
+        for (int f = 0; f < nf; ++f) {
+            int v = launch_validate_disp12((int16_t*)((uint8_t*)disp + f * disp_stride), (const int16_t*)((const uint8_t*)cost + f * disp_stride),
+                                           cols, rows, cfg, st);
+            if (v < 0) return fail(h, B200S_EUNSUPPORTED, "disp12MaxDiff needs image width <= 65535");
+            h->launches += v;     // the valid-ROI mask of the rows is applied by the same kernel
+        }
     }
     if (p.speckle_window_size > 0 && p.speckle_range >= 0) {
-        if (w.ccl.ensure(3 * n * sizeof(int))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (speckle scratch)");
+        const size_t cstride = align256(3 * n * sizeof(int) + 64);
+        if (w.ccl.ensure(cstride * cap_nf)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (speckle scratch)");
         h->launches += launch_filter_speckles(disp, cols, rows, (p.min_disparity - 1) * 16, p.speckle_window_size,
-                                              p.speckle_range, (int*)w.ccl.p, st);
+                                              p.speckle_range, (int*)w.ccl.p, st, nf, disp_stride, cstride);
     }
+    ++h->stats_frames;
     return check_kernels(h, "disparity chain");
 }
 
@@ -415,29 +348,35 @@ int ensure_misc(b200s_handle* h, Work& w)
     return B200S_OK;
 }
 
-// Device-side alias of a pinned (page-locked, mapped) host buffer, or nullptr when `p` is pageable / not host memory.
-// Under unified addressing every cudaHostAlloc / cudaHostRegister range is directly writable by kernels.
-void* mapped_alias(const void* p)
+void fill_disparity_meta(const b200s_handle* h, int rows, int cols, b200s_disparity_meta* m)
 {
-    if (!p) return nullptr;
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+    const b200s_params& p = h->prm;
+    m->width = cols; m->height = rows; m->step = cols * 4;
+    m->f = (float)h->fx_right;
+    m->T = (float)h->baseline;
+    m->min_disparity = (float)p.min_disparity;
+    m->max_disparity = (float)(p.min_disparity + p.num_disparities - 1);
+    m->delta_d = 1.0f / 16.0f;
+    int border = p.block_size / 2;
+    int left = p.num_disparities + p.min_disparity + border - 1;
+    int wtf = p.min_disparity >= 0 ? border + p.min_disparity : (border > -p.min_disparity ? border : -p.min_disparity);
+    int right = cols - 1 - wtf, top = border, bottom = rows - 1 - border;
+    m->valid_x_offset = left; m->valid_y_offset = top; m->valid_width = right - left; m->valid_height = bottom - top;
 }
 
-int copy_out(b200s_handle* h, void* dst, const void* src, size_t bytes, bool dst_on_device, cudaStream_t st)
+void fill_pc2_meta(int rows, int cols, b200s_pc2_meta* m)
 {
-    if (!dst) return B200S_OK;
-    CUDA_OK(h, cudaMemcpyAsync(dst, src, bytes, dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-    return B200S_OK;
+    m->width = cols; m->height = rows; m->point_step = 32; m->row_step = 32 * cols;
+    m->is_bigendian = 0; m->is_dense = 0;
+    m->off_x = 0; m->off_y = 4; m->off_z = 8; m->off_rgb = 16;
 }
 
-}  // namespace
+}  // namespace b200s
 
 // ==========================================================================================================
 extern "C" {
 
-const char* b200s_version(void) { return "b200-stereo 0.1 (sm_100a)"; }
+const char* b200s_version(void) { return "b200-stereo 0.2 (sm_100a)"; }
 
 int b200s_default_params(b200s_params* p)
 {
@@ -460,15 +399,17 @@ int b200s_create(int device, b200s_handle** out)
     if (!h) return B200S_ENOMEM;
     h->device = device;
     // state of the reference's CPU matcher after its constructor (src/GPUStereoProcessor.cpp:18-38):
-    // createStereoBM(48, 19) mirrored into cv::StereoBM, preFilterSize 5
+    // createStereoBM(48, 19) mirrored into cv::StereoBM, preFilterSize 5, PREFILTER_XSOBEL (:27-30), texture threshold /
+    // uniqueness / disp12MaxDiff copied from the cuda matcher's getters (3 / 0 / 0)
     if (const char* e = getenv("B200S_GRAPH")) h->use_graphs = atoi(e) != 0;
     if (const char* e = getenv("B200S_PACK_DIRECT")) h->pack_direct = atoi(e);
     b200s_default_params(&h->prm);
-    h->prm.pre_filter_type = 0; h->prm.pre_filter_size = 5; h->prm.num_disparities = 48; h->prm.block_size = 19;
+    h->prm.pre_filter_type = 1; h->prm.pre_filter_size = 5; h->prm.num_disparities = 48; h->prm.block_size = 19;
     h->prm.texture_threshold = 3; h->prm.uniqueness_ratio = 0; h->prm.disp12_max_diff = 0;
     if (cudaStreamCreateWithFlags(&h->l_strm, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->r_strm, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_r, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&h->ev_r, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_l, cudaEventDisableTiming) != cudaSuccess) {
         delete h;
         return B200S_ECUDA;
     }
@@ -480,14 +421,16 @@ int b200s_create(int device, b200s_handle** out)
 int b200s_destroy(b200s_handle* h)
 {
     if (!h) return B200S_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard g(h->device);
     cudaDeviceSynchronize();
     for (auto& kv : h->mats) kv.second.buf.release();
     for (Work& w : h->slots) w.release();
     h->w0.release();
     for (int s = 0; s < 2; ++s) h->cam[s].map.release();
     h->Qdev.release();
+    h->flagdev.release();
     if (h->ev_r) cudaEventDestroy(h->ev_r);
+    if (h->ev_l) cudaEventDestroy(h->ev_l);
     for (int i = 0; i < 2; ++i) {
         if (h->stage_host[i]) cudaFreeHost(h->stage_host[i]);
         if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
@@ -532,6 +475,9 @@ int b200s_set_calibration(b200s_handle* h, const b200s_caminfo* left, const b200
     h->fx_right = Pr[0];
     h->cxd = cx - cxr;
     if (h->Qdev.ensure(sizeof(h->Q))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (Q)");
+    // frames in flight on the (non-blocking) slot streams still read the old Q and maps: drain the device first
+    CUDA_OK(h, cudaDeviceSynchronize());
+    for (Work& w : h->slots) w.drop_graphs();
     CUDA_OK(h, cudaMemcpy(h->Qdev.p, h->Q, sizeof(h->Q), cudaMemcpyHostToDevice));
     h->model_ok = true;
     ++h->model_version;
@@ -606,6 +552,7 @@ int b200s_upload(b200s_handle* h, int mat_id, const void* data, int rows, int co
     int rc = alloc_mat(h, mat_id, rows, cols, type, encoding ? encoding : "", &m);
     if (rc) return rc;
     cudaStream_t st = stream_of(h, mat_id);
+    CUDA_OK(h, order_after_left_readers(h, st));
     CUDA_OK(h, cudaMemcpy2DAsync(m->buf.p, (size_t)cols * es, data, step, (size_t)cols * es, rows, cudaMemcpyHostToDevice, st));
     return B200S_OK;
 }
@@ -659,6 +606,7 @@ static int convert_raw(b200s_handle* h, int side, bool to_color)
     if (!((mono && src->type == B200S_8UC1) || ((bgr || rgb) && src->type == B200S_8UC3)))
         return fail(h, B200S_EUNSUPPORTED, "raw encoding '" + e + "' is outside the hot path (mono8, bgr8, rgb8 are supported)");
     cudaStream_t st = stream_of(h, side);
+    CUDA_OK(h, order_after_left_readers(h, st));
     int n = src->rows * src->cols;
     Mat* dst;
     int rc = alloc_mat(h, (to_color ? B200S_SRC_COLOR : B200S_SRC_MONO) | side, src->rows, src->cols,
@@ -701,16 +649,16 @@ int b200s_rectify(b200s_handle* h, int src_id, int dst_id, int interpolation)
     int rc = alloc_mat(h, dst_id, H, W, type, enc.c_str(), &dst);
     if (rc) return rc;
     src = find_mat(h, src_id);
-    const int2* map = nullptr;
-    if (!h->rect_fly && interpolation == B200S_INTER_LINEAR) {
-        rc = ensure_map(h, side, st);
+    CUDA_OK(h, order_after_left_readers(h, st));
+    if (interpolation == B200S_INTER_LINEAR) {
+        MapMode mode = MAP_FLY;
+        const void* map = nullptr;
+        rc = map_for(h, side, st, &mode, &map);
         if (rc) return rc;
-        map = (const int2*)h->cam[side].map.p;
+        h->launches += launch_remap((const uint8_t*)src->buf.p, sW, sH, ch, map, mode, cam.cm, (uint8_t*)dst->buf.p, W, H, st);
+    } else {
+        h->launches += launch_remap_nearest((const uint8_t*)src->buf.p, sW, sH, ch, cam.cm, (uint8_t*)dst->buf.p, W, H, st);
     }
-    if (interpolation == B200S_INTER_LINEAR)
-        h->launches += launch_remap((const uint8_t*)src->buf.p, sW, sH, ch, map, cam.cm, (uint8_t*)dst->buf.p, W, H, st);
-    else
-        h->launches += launch_remap_nearest((const uint8_t*)src->buf.p, sW, sH, ch, map, cam.cm, (uint8_t*)dst->buf.p, W, H, st);
     return check_kernels(h, "rectify");
 }
 
@@ -746,6 +694,7 @@ int b200s_compute_disparity(b200s_handle* h, int left_id, int right_id, int disp
     if (rc) return rc;
     h->launches += launch_disparity_to_float((const int16_t*)D->buf.p, (float*)F->buf.p, rows * cols,
                                              h->model_ok ? h->cxd : 0.0, (int*)h->w0.misc.p, st);
+    CUDA_OK(h, cudaEventRecord(h->ev_l, st));    // the right-side stream must not overwrite its planes before this point
     return check_kernels(h, "compute_disparity");
 }
 
@@ -782,6 +731,7 @@ int b200s_compute_disparity_cuda_compat(b200s_handle* h, int left_id, int right_
                                          cols, rows, p.num_disparities, p.block_size, xs, p.pre_filter_cap, p.texture_threshold,
                                          (uint8_t*)D->buf.p, st);
     (void)n;
+    CUDA_OK(h, cudaEventRecord(h->ev_l, st));
     return check_kernels(h, "compute_disparity_cuda_compat");
 }
 
@@ -851,6 +801,7 @@ int b200s_project_to_3d(b200s_handle* h, int disp_id, int points_id)
     if (!h) return B200S_EINVAL;
     DeviceGuard g(h->device);
     if (!h->model_ok) return fail(h, B200S_ENOTINIT, "stereo model not initialised");
+    disp_id = fixed_point_plane_of(disp_id);
     Mat* D = find_mat(h, disp_id);
     if (!D || D->type != B200S_16SC1) return fail(h, B200S_ENOBUF, "disparity buffer is empty or not CV_16SC1");
     int rows = D->rows, cols = D->cols;
@@ -877,67 +828,98 @@ int b200s_wait(b200s_handle* h, int side)
 }
 
 // ---- packing ---------------------------------------------------------------------------------------------
-int b200s_pack_image(b200s_handle* h, int mat_id, void* dst, size_t cap_bytes, int* rows, int* cols, int* step)
+// The reference's senders publish from a stream callback once the device->host copy has finished
+// (src/GpuSenderIfc.cpp:13-26).  The *_async entry points do the same: kernels (+ copy) are enqueued on the side's
+// stream, then `done(user, status)` is called by the CUDA runtime's callback thread when the payload is complete in
+// dst (no CUDA calls inside `done`).  done == NULL makes the call synchronous (returns with the payload in dst).
+namespace {
+
+struct DoneCtx {
+    b200s_done_fn fn;
+    void* user;
+};
+
+void CUDART_CB done_trampoline(void* p)
+{
+    DoneCtx* c = (DoneCtx*)p;
+    c->fn(c->user, B200S_OK);
+    delete c;
+}
+
+// src == nullptr: a kernel has already written the payload straight into (pinned) dst
+int finish_pack(b200s_handle* h, cudaStream_t st, void* dst, const void* src, size_t bytes, b200s_done_fn done, void* user)
+{
+    if (!done) {
+        if (src) return d2h_sync(h, dst, src, bytes, st);
+        CUDA_OK(h, cudaStreamSynchronize(st));
+        return B200S_OK;
+    }
+    if (src) CUDA_OK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    DoneCtx* c = new DoneCtx{done, user};
+    cudaError_t e = cudaLaunchHostFunc(st, done_trampoline, c);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(h, B200S_ECUDA, std::string("cudaLaunchHostFunc: ") + cudaGetErrorString(e));
+    }
+    return B200S_OK;
+}
+
+}  // namespace
+
+int b200s_pack_image_async(b200s_handle* h, int mat_id, void* dst, size_t cap_bytes, int* rows, int* cols, int* step,
+                           b200s_done_fn done, void* user)
 {
     if (!h || !dst) return B200S_EINVAL;
     DeviceGuard g(h->device);
     Mat* m = find_mat(h, mat_id);
     if (!m) return fail(h, B200S_ENOBUF, "named buffer is empty");
     if (cap_bytes < m->bytes()) return fail(h, B200S_EINVAL, "destination too small");
-    cudaStream_t st = stream_of(h, mat_id);
-    { int rcd = d2h_sync(h, dst, m->buf.p, m->bytes(), st); if (rcd) return rcd; }
     if (rows) *rows = m->rows;
     if (cols) *cols = m->cols;
     if (step) *step = m->cols * elem_size(m->type);   // GpuSenderImage.cpp:20: width * bitdepth * channels / 8
-    return B200S_OK;
+    return finish_pack(h, stream_of(h, mat_id), dst, m->buf.p, m->bytes(), done, user);
 }
 
-static void fill_disparity_meta(const b200s_handle* h, int rows, int cols, b200s_disparity_meta* m)
+int b200s_pack_image(b200s_handle* h, int mat_id, void* dst, size_t cap_bytes, int* rows, int* cols, int* step)
 {
-    const b200s_params& p = h->prm;
-    m->width = cols; m->height = rows; m->step = cols * 4;
-    m->f = (float)h->fx_right;
-    m->T = (float)h->baseline;
-    m->min_disparity = (float)p.min_disparity;
-    m->max_disparity = (float)(p.min_disparity + p.num_disparities - 1);
-    m->delta_d = 1.0f / 16.0f;
-    int border = p.block_size / 2;
-    int left = p.num_disparities + p.min_disparity + border - 1;
-    int wtf = p.min_disparity >= 0 ? border + p.min_disparity : (border > -p.min_disparity ? border : -p.min_disparity);
-    int right = cols - 1 - wtf, top = border, bottom = rows - 1 - border;
-    m->valid_x_offset = left; m->valid_y_offset = top; m->valid_width = right - left; m->valid_height = bottom - top;
+    return b200s_pack_image_async(h, mat_id, dst, cap_bytes, rows, cols, step, nullptr, nullptr);
 }
 
-int b200s_pack_disparity(b200s_handle* h, int disp_id, void* dst, size_t cap_bytes, b200s_disparity_meta* meta)
+int b200s_pack_disparity_async(b200s_handle* h, int disp_id, void* dst, size_t cap_bytes, b200s_disparity_meta* meta,
+                               b200s_done_fn done, void* user)
 {
     if (!h || !dst) return B200S_EINVAL;
     DeviceGuard g(h->device);
+    disp_id = fixed_point_plane_of(disp_id);
     Mat* D = find_mat(h, disp_id);
     if (!D || D->type != B200S_16SC1) return fail(h, B200S_ENOBUF, "disparity buffer is empty or not CV_16SC1");
     size_t n = (size_t)D->rows * D->cols;
     if (cap_bytes < n * 4) return fail(h, B200S_EINVAL, "destination too small");
     int rc = ensure_misc(h, h->w0);
     if (rc) return rc;
-    if (h->w0.df.ensure(n * 4)) return fail(h, B200S_ENOMEM, "cudaMalloc failed");
     cudaStream_t st = stream_of(h, disp_id);
-    h->launches += launch_disparity_to_float((const int16_t*)D->buf.p, (float*)h->w0.df.p, (int)n, h->model_ok ? h->cxd : 0.0, (int*)h->w0.misc.p, st);
-    { int rcd = d2h_sync(h, dst, h->w0.df.p, n * 4, st); if (rcd) return rcd; }
+    void* direct = h->pack_direct ? mapped_alias(dst) : nullptr;
+    if (!direct && h->w0.df.ensure(n * 4)) return fail(h, B200S_ENOMEM, "cudaMalloc failed");
+    h->launches += launch_disparity_to_float((const int16_t*)D->buf.p, direct ? (float*)direct : (float*)h->w0.df.p, (int)n,
+                                             h->model_ok ? h->cxd : 0.0, (int*)h->w0.misc.p, st);
     if (meta) fill_disparity_meta(h, D->rows, D->cols, meta);
-    return check_kernels(h, "pack_disparity");
+    rc = check_kernels(h, "pack_disparity");
+    if (rc) return rc;
+    return finish_pack(h, st, dst, direct ? nullptr : h->w0.df.p, n * 4, done, user);
 }
 
-static void fill_pc2_meta(int rows, int cols, b200s_pc2_meta* m)
+int b200s_pack_disparity(b200s_handle* h, int disp_id, void* dst, size_t cap_bytes, b200s_disparity_meta* meta)
 {
-    m->width = cols; m->height = rows; m->point_step = 32; m->row_step = 32 * cols;
-    m->is_bigendian = 0; m->is_dense = 0;
-    m->off_x = 0; m->off_y = 4; m->off_z = 8; m->off_rgb = 16;
+    return b200s_pack_disparity_async(h, disp_id, dst, cap_bytes, meta, nullptr, nullptr);
 }
 
-int b200s_pack_pointcloud2(b200s_handle* h, int disp_id, int color_id, void* dst, size_t cap_bytes, b200s_pc2_meta* meta)
+int b200s_pack_pointcloud2_async(b200s_handle* h, int disp_id, int color_id, void* dst, size_t cap_bytes, b200s_pc2_meta* meta,
+                                 b200s_done_fn done, void* user)
 {
     if (!h || !dst) return B200S_EINVAL;
     DeviceGuard g(h->device);
     if (!h->model_ok) return fail(h, B200S_ENOTINIT, "stereo model not initialised");
+    disp_id = fixed_point_plane_of(disp_id);     // the reference passes its POINTS2 buffer (src/StereoProcessor.cpp:281)
     Mat* D = find_mat(h, disp_id);
     Mat* Cc = find_mat(h, color_id);
     if (!D || D->type != B200S_16SC1) return fail(h, B200S_ENOBUF, "disparity buffer is empty or not CV_16SC1");
@@ -947,408 +929,97 @@ int b200s_pack_pointcloud2(b200s_handle* h, int disp_id, int color_id, void* dst
     if (cap_bytes < n * 32) return fail(h, B200S_EINVAL, "destination too small");
     int rc = ensure_misc(h, h->w0);
     if (rc) return rc;
-    if (h->w0.pc2.ensure(n * 32)) return fail(h, B200S_ENOMEM, "cudaMalloc failed");
+    void* direct = h->pack_direct ? mapped_alias(dst) : nullptr;
+    if (!direct && h->w0.pc2.ensure(n * 32)) return fail(h, B200S_ENOMEM, "cudaMalloc failed");
     cudaStream_t st = h->l_strm;
     CUDA_OK(h, cudaEventRecord(h->ev_r, h->r_strm));
     CUDA_OK(h, cudaStreamWaitEvent(st, h->ev_r, 0));
     h->launches += launch_disparity_to_float((const int16_t*)D->buf.p, nullptr, (int)n, h->cxd, (int*)h->w0.misc.p, st);
     h->launches += launch_reproject_pack((const int16_t*)D->buf.p, D->cols, D->rows, h->cxd, (const double*)h->Qdev.p, h->qmask,
                                          (const int*)h->w0.misc.p, (const uint8_t*)Cc->buf.p, Cc->type == B200S_8UC3 ? 3 : 1,
-                                         nullptr, (uint8_t*)h->w0.pc2.p, st);
-    { int rcd = d2h_sync(h, dst, h->w0.pc2.p, n * 32, st); if (rcd) return rcd; }
+                                         nullptr, direct ? (uint8_t*)direct : (uint8_t*)h->w0.pc2.p, st);
+    CUDA_OK(h, cudaEventRecord(h->ev_l, st));
     if (meta) fill_pc2_meta(D->rows, D->cols, meta);
-    return check_kernels(h, "pack_pointcloud2");
+    rc = check_kernels(h, "pack_pointcloud2");
+    if (rc) return rc;
+    return finish_pack(h, st, dst, direct ? nullptr : h->w0.pc2.p, n * 32, done, user);
 }
 
-// ---- fused frame path ------------------------------------------------------------------------------------
-int b200s_configure_slots(b200s_handle* h, int n_slots, int rows, int cols)
+int b200s_pack_pointcloud2(b200s_handle* h, int disp_id, int color_id, void* dst, size_t cap_bytes, b200s_pc2_meta* meta)
 {
-    if (!h || n_slots < 1 || n_slots > 64 || rows <= 0 || cols <= 0) return B200S_EINVAL;
+    return b200s_pack_pointcloud2_async(h, disp_id, color_id, dst, cap_bytes, meta, nullptr, nullptr);
+}
+
+// convertColor(src, dst, src_encoding, dst_encoding) (src/GPUStereoProcessor.cpp:119-172) for the encodings on the hot
+// path: mono8 <-> bgr8 / rgb8 / bgra8 source, mono8 or bgr8 destination
+int b200s_convert_color(b200s_handle* h, int src_id, int dst_id, const char* src_encoding, const char* dst_encoding)
+{
+    if (!h || !src_encoding || !dst_encoding) return B200S_EINVAL;
     DeviceGuard g(h->device);
-    cudaDeviceSynchronize();
-    for (Work& w : h->slots) w.release();
-    h->slots.clear();
-    h->slots.resize(n_slots);
-    for (Work& w : h->slots) {
-        if (cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking) != cudaSuccess) return fail(h, B200S_ECUDA, "cudaStreamCreate failed");
-        w.own_stream = true;
-        cudaEventCreateWithFlags(&w.ev_done, cudaEventDisableTiming);
-        cudaEventCreate(&w.ev_bm0);
-        cudaEventCreate(&w.ev_bm1);
-    }
-    h->slot_rows = rows;
-    h->slot_cols = cols;
-    return B200S_OK;
-}
-
-namespace {
-
-// everything of a frame after the inputs are on the device: rectify -> disparity -> float / reproject+pack -> outputs
-int run_frame_chain(b200s_handle* h, Work& w, const b200s_frame_io* io, const uint8_t* L, const uint8_t* R, cudaStream_t st)
-{
-    const int rows = h->slot_rows, cols = h->slot_cols;
-    const size_t n = (size_t)rows * cols;
-    bool prefiltered = false;
-    const uint8_t *rl = L, *rr = R;
-    if (io->rectify) {
-        if (w.rectL.ensure(n + 64) || w.rectR.ensure(n + 64)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (rectified planes)");
-        const int2 *mapL = nullptr, *mapR = nullptr;
-        if (!h->rect_fly) {
-            int rc = ensure_map(h, 0, st);
-            if (rc) return rc;
-            rc = ensure_map(h, 1, st);
-            if (rc) return rc;
-            mapL = (const int2*)h->cam[0].map.p;
-            mapR = (const int2*)h->cam[1].map.p;
-        }
-        if (h->prm.pre_filter_type == 1) {
-            int rc2 = ensure_pre_planes(h, w, rows, cols);
-            if (rc2) return rc2;
-            const size_t pitch = plane_pitch(cols);
-            h->launches += launch_rectify_xsobel_pair(L, R, cols, rows, mapL, mapR, h->cam[0].cm, h->cam[1].cm, (uint8_t*)w.rectL.p,
-                                                      (uint8_t*)w.rectR.p, (uint8_t*)w.preL.p + PLANE_LEAD,
-                                                      (uint8_t*)w.preR.p + PLANE_LEAD, pitch, cols, rows, h->prm.pre_filter_cap, st);
-            prefiltered = true;
-        } else {
-            int one = 0;
-            if (h->prm.pre_filter_size <= 21) {
-                int rc2 = ensure_pre_planes(h, w, rows, cols);
-                if (rc2) return rc2;
-                one = launch_norm_prefilter_pair(L, R, cols, rows, true, mapL, mapR, h->cam[0].cm, h->cam[1].cm, (uint8_t*)w.rectL.p,
-                                                 (uint8_t*)w.rectR.p, (uint8_t*)w.preL.p + PLANE_LEAD, (uint8_t*)w.preR.p + PLANE_LEAD,
-                                                 plane_pitch(cols), cols, rows, h->prm.pre_filter_size, h->prm.pre_filter_cap, st);
-            }
-            if (one) {
-                h->launches += one;
-                prefiltered = true;
-            } else {
-                h->launches += launch_remap(L, cols, rows, 1, mapL, h->cam[0].cm, (uint8_t*)w.rectL.p, cols, rows, st);
-                h->launches += launch_remap(R, cols, rows, 1, mapR, h->cam[1].cm, (uint8_t*)w.rectR.p, cols, rows, st);
-            }
-        }
-        rl = (const uint8_t*)w.rectL.p;
-        rr = (const uint8_t*)w.rectR.p;
-    }
-    if (w.disp.ensure(n * 2 + 64)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (disparity plane)");
-    int rc = run_disparity(h, w, rl, rr, prefiltered, rows, cols, (int16_t*)w.disp.p, st);
+    Mat* src = find_mat(h, src_id);
+    if (!src) return fail(h, B200S_ENOBUF, "source buffer is empty");
+    const std::string se = src_encoding, de = dst_encoding;
+    const bool s_mono = se == "mono8", s_bgr = se == "bgr8", s_rgb = se == "rgb8";
+    const bool d_mono = de == "mono8", d_bgr = de == "bgr8";
+    if (!(s_mono || s_bgr || s_rgb) || !(d_mono || d_bgr))
+        return fail(h, B200S_EUNSUPPORTED, "convertColor: '" + se + "' -> '" + de + "' is outside the hot path (mono8, bgr8, rgb8 -> mono8, bgr8)");
+    if ((s_mono && src->type != B200S_8UC1) || (!s_mono && src->type != B200S_8UC3))
+        return fail(h, B200S_EINVAL, "convertColor: buffer type does not match the source encoding");
+    cudaStream_t st = stream_of(h, src_id);
+    CUDA_OK(h, order_after_left_readers(h, st));
+    const int rows = src->rows, cols = src->cols, n = rows * cols;
+    Mat* dst;
+    int rc = alloc_mat(h, dst_id, rows, cols, d_mono ? B200S_8UC1 : B200S_8UC3, de.c_str(), &dst);
     if (rc) return rc;
-    const bool want_pc = io->want & B200S_OUT_POINTCLOUD2, want_xyz = io->want & B200S_OUT_POINTS_XYZ;
-    const bool want_df = io->want & B200S_OUT_DISPARITY32F;
-    if (want_df || want_pc || want_xyz) {
-        rc = ensure_misc(h, w);
-        if (rc) return rc;
-        if (want_df && w.df.ensure(n * 4)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (float disparity)");
-        h->launches += launch_disparity_to_float((const int16_t*)w.disp.p, want_df ? (float*)w.df.p : nullptr, (int)n,
-                                                 h->model_ok ? h->cxd : 0.0, (int*)w.misc.p, st);
-    }
-    // pack mode "direct" (the north star's wording): the PointCloud2 records are stored by the kernel straight into the
-    // caller's pinned host buffer (PCIe posted writes), no HBM copy of the cloud and no copy-engine transfer afterwards
-    void* pc_direct = (h->pack_direct && want_pc && !io->outputs_on_device) ? mapped_alias(io->pointcloud2) : nullptr;
-    if (want_pc || want_xyz) {
-        if (want_pc && !pc_direct && w.pc2.ensure(n * 32)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (point cloud)");
-        if (want_xyz && w.xyz.ensure(n * 12)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (points)");
-        h->launches += launch_reproject_pack((const int16_t*)w.disp.p, cols, rows, h->cxd, (const double*)h->Qdev.p, h->qmask,
-                                             (const int*)w.misc.p, rl, 1, want_xyz ? (float*)w.xyz.p : nullptr,
-                                             want_pc ? (pc_direct ? (uint8_t*)pc_direct : (uint8_t*)w.pc2.p) : nullptr, st);
-    }
-    rc = check_kernels(h, "process_pair");
-    if (rc) return rc;
-    const bool od = io->outputs_on_device != 0;
-    if (io->rectify) {
-        if ((io->want & B200S_OUT_RECT_L) && (rc = copy_out(h, io->rect_left, w.rectL.p, n, od, st))) return rc;
-        if ((io->want & B200S_OUT_RECT_R) && (rc = copy_out(h, io->rect_right, w.rectR.p, n, od, st))) return rc;
-    }
-    if ((io->want & B200S_OUT_DISPARITY16) && (rc = copy_out(h, io->disparity16, w.disp.p, n * 2, od, st))) return rc;
-    if (want_df && (rc = copy_out(h, io->disparity32f, w.df.p, n * 4, od, st))) return rc;
-    if (want_pc && !pc_direct && (rc = copy_out(h, io->pointcloud2, w.pc2.p, n * 32, od, st))) return rc;
-    if (want_xyz && (rc = copy_out(h, io->points_xyz, w.xyz.p, n * 12, od, st))) return rc;
-    return B200S_OK;
+    src = find_mat(h, src_id);
+    if (s_mono && d_mono) CUDA_OK(h, cudaMemcpyAsync(dst->buf.p, src->buf.p, src->bytes(), cudaMemcpyDeviceToDevice, st));
+    else if (s_mono) h->launches += launch_gray_to_bgr((const uint8_t*)src->buf.p, (uint8_t*)dst->buf.p, n, st);
+    else if (d_mono) h->launches += launch_bgr_to_gray((const uint8_t*)src->buf.p, (uint8_t*)dst->buf.p, n, s_rgb ? 1 : 0, st);
+    else if (s_rgb) h->launches += launch_swap_rb((const uint8_t*)src->buf.p, (uint8_t*)dst->buf.p, n, st);
+    else CUDA_OK(h, cudaMemcpyAsync(dst->buf.p, src->buf.p, src->bytes(), cudaMemcpyDeviceToDevice, st));
+    return check_kernels(h, "convert_color");
 }
 
-// everything a captured chain depends on besides the (fixed) slot buffers
-std::string frame_graph_key(const b200s_handle* h, const b200s_frame_io* io)
-{
-    std::string k;
-    auto add = [&k](const void* p, size_t n) { k.append((const char*)p, n); };
-    add(&h->prm, sizeof h->prm);
-    add(io, sizeof *io);
-    add(&h->model_version, sizeof h->model_version);
-    add(&h->slot_rows, sizeof h->slot_rows);
-    add(&h->slot_cols, sizeof h->slot_cols);
-    return k;
-}
-
-}  // namespace
-
-int b200s_process_pair_async(b200s_handle* h, int slot, const void* left, const void* right, const b200s_frame_io* io)
-{
-    if (!h || !left || !right || !io) return B200S_EINVAL;
-    DeviceGuard g(h->device);
-    if (slot < 0 || slot >= (int)h->slots.size()) return fail(h, B200S_EINVAL, "slot out of range (call b200s_configure_slots)");
-    Work& w = h->slots[slot];
-    const int rows = h->slot_rows, cols = h->slot_cols;
-    const size_t n = (size_t)rows * cols;
-    cudaStream_t st = w.st;
-    const bool need_model = io->rectify || (io->want & (B200S_OUT_POINTCLOUD2 | B200S_OUT_POINTS_XYZ));
-    if (need_model && !h->model_ok) return fail(h, B200S_ENOTINIT, "stereo model not initialised");
-    if (io->rectify && (h->cam[0].info.width != cols || h->cam[0].info.height != rows))
-        return fail(h, B200S_EINVAL, "slot size differs from the calibration size");
-    const bool graphs = h->use_graphs && !h->timing;
-    // inputs: host frames always go through the slot's raw planes; with graph replay device frames do too, so that
-    // the captured kernels see fixed addresses
-    const uint8_t *L = (const uint8_t*)left, *R = (const uint8_t*)right;
-    if (!io->inputs_on_device || graphs) {
-        if (w.rawL.ensure(n + 64) || w.rawR.ensure(n + 64)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (input planes)");
-        const cudaMemcpyKind kind = io->inputs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-        CUDA_OK(h, cudaMemcpyAsync(w.rawL.p, left, n, kind, st));
-        CUDA_OK(h, cudaMemcpyAsync(w.rawR.p, right, n, kind, st));
-        L = (const uint8_t*)w.rawL.p;
-        R = (const uint8_t*)w.rawR.p;
-    }
-    int rc = B200S_OK;
-    if (!graphs) {
-        rc = run_frame_chain(h, w, io, L, R, st);
-    } else {
-        const std::string key = frame_graph_key(h, io);
-        if (w.gexec && key == w.gkey) {
-            CUDA_OK(h, cudaGraphLaunch(w.gexec, st));
-            h->launches += w.glaunches;
-            w.last_evals = w.gevals;
-            ++h->graph_replays;
-        } else if (key == w.warm_key) {
-            // second frame with this key: every buffer exists, the maps are built -> capture, instantiate, launch
-            if (w.gexec) { cudaGraphExecDestroy(w.gexec); w.gexec = nullptr; w.gkey.clear(); }
-            const uint64_t l0 = h->launches;
-            cudaGraph_t graph = nullptr;
-            cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
-            if (e == cudaSuccess) {
-                rc = run_frame_chain(h, w, io, L, R, st);
-                e = cudaStreamEndCapture(st, &graph);
-                if (rc == B200S_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&w.gexec, graph, 0);
-                if (graph) cudaGraphDestroy(graph);
-            }
-            if (rc != B200S_OK || e != cudaSuccess || !w.gexec) {
-                // capture is an optimisation only: fall back to eager launches for this handle
-                cudaGetLastError();
-                w.drop_graph();
-                h->use_graphs = 0;
-                h->launches = l0;
-                rc = run_frame_chain(h, w, io, L, R, st);
-            } else {
-                w.glaunches = h->launches - l0;
-                w.gevals = w.last_evals;
-                w.gkey = key;
-                h->launches = l0 + w.glaunches;
-                CUDA_OK(h, cudaGraphLaunch(w.gexec, st));
-            }
-        } else {
-            rc = run_frame_chain(h, w, io, L, R, st);
-            w.warm_key = rc == B200S_OK ? key : std::string();
-        }
-    }
-    if (rc) return rc;
-    CUDA_OK(h, cudaEventRecord(w.ev_done, st));
-    return B200S_OK;
-}
-
-int b200s_set_graph_mode(b200s_handle* h, int on)
+// printStats (src/GPUStereoProcessor.cpp:421-435) on a named buffer
+int b200s_mat_stats(b200s_handle* h, int mat_id, double* mn, double* mx, double* mean, int* channels)
 {
     if (!h) return B200S_EINVAL;
-    h->use_graphs = on ? 1 : 0;
-    for (Work& w : h->slots) w.drop_graph();
-    return B200S_OK;
-}
-
-uint64_t b200s_graph_replays(const b200s_handle* h) { return h ? h->graph_replays : 0; }
-
-int b200s_wait_slot(b200s_handle* h, int slot)
-{
-    if (!h) return B200S_EINVAL;
-    if (slot < 0 || slot >= (int)h->slots.size()) return fail(h, B200S_EINVAL, "slot out of range");
     DeviceGuard g(h->device);
-    CUDA_OK(h, cudaStreamSynchronize(h->slots[slot].st));
-    return B200S_OK;
-}
-
-// non-blocking completion test of a slot's last frame (the reference publishes from a stream callback, GpuSenderIfc.cpp:13-26)
-int b200s_poll_slot(b200s_handle* h, int slot, int* done)
-{
-    if (!h || !done) return B200S_EINVAL;
-    if (slot < 0 || slot >= (int)h->slots.size()) return fail(h, B200S_EINVAL, "slot out of range");
-    DeviceGuard g(h->device);
-    cudaError_t e = cudaEventQuery(h->slots[slot].ev_done);
-    if (e != cudaSuccess && e != cudaErrorNotReady) return fail(h, B200S_ECUDA, cudaGetErrorString(e));
-    *done = e == cudaSuccess;
-    return B200S_OK;
-}
-
-int b200s_slot_device_ptr(b200s_handle* h, int slot, uint32_t which, void** dptr, size_t* bytes)
-{
-    if (!h || !dptr) return B200S_EINVAL;
-    if (slot < 0 || slot >= (int)h->slots.size()) return fail(h, B200S_EINVAL, "slot out of range");
-    Work& w = h->slots[slot];
-    size_t n = (size_t)h->slot_rows * h->slot_cols;
-    DevBuf* b = nullptr;
-    size_t sz = 0;
-    switch (which) {
-        case B200S_OUT_RECT_L: b = &w.rectL; sz = n; break;
-        case B200S_OUT_RECT_R: b = &w.rectR; sz = n; break;
-        case B200S_OUT_DISPARITY16: b = &w.disp; sz = n * 2; break;
-        case B200S_OUT_DISPARITY32F: b = &w.df; sz = n * 4; break;
-        case B200S_OUT_POINTCLOUD2: b = &w.pc2; sz = n * 32; break;
-        case B200S_OUT_POINTS_XYZ: b = &w.xyz; sz = n * 12; break;
-        default: return fail(h, B200S_EINVAL, "unknown product");
+    Mat* m = find_mat(h, mat_id);
+    if (!m) return fail(h, B200S_ENOBUF, "named buffer is empty");
+    int ch = 1, kind = 0;
+    switch (m->type) {
+        case B200S_8UC1: ch = 1; kind = 0; break;
+        case B200S_8UC3: ch = 3; kind = 0; break;
+        case B200S_8UC4: ch = 4; kind = 0; break;
+        case B200S_16SC1: ch = 1; kind = 1; break;
+        case B200S_32FC1: ch = 1; kind = 2; break;
+        case B200S_32FC3: ch = 3; kind = 2; break;
+        default: return fail(h, B200S_EUNSUPPORTED, "unsupported element type");
     }
-    if (!b->p) return fail(h, B200S_ENOBUF, "product has not been computed on this slot yet");
-    *dptr = b->p;
-    if (bytes) *bytes = sz;
-    return B200S_OK;
-}
-
-int b200s_process_pair(b200s_handle* h, const void* left, const void* right, const b200s_frame_io* io)
-{
-    if (!h) return B200S_EINVAL;
-    if (h->slots.empty()) return fail(h, B200S_EINVAL, "call b200s_configure_slots first");
-    int rc = b200s_process_pair_async(h, 0, left, right, io);
-    if (rc) return rc;
-    return b200s_wait_slot(h, 0);
-}
-
-// ---- multi-GPU pool: one handle (stream set, slots, calibration, parameters) per GPU inside one process ----------
-// Independent stereo frames shard over the GPUs with no exchange step: frame k -> GPU k mod N, slot
-// (k div N) mod S.  All calls only enqueue work, so one host thread drives every GPU; with graph replay a submit is
-// two copies and one graph launch.
-struct b200s_pool {
-    std::vector<b200s_handle*> h;
-    int slots = 0;
-    std::string err;
-};
-
-int b200s_pool_create(int n_gpus, const int* devices, int slots_per_gpu, int rows, int cols, b200s_pool** out)
-{
-    if (!out || n_gpus < 1 || n_gpus > 64 || slots_per_gpu < 1) return B200S_EINVAL;
-    b200s_pool* p = new b200s_pool;
-    p->slots = slots_per_gpu;
-    for (int i = 0; i < n_gpus; ++i) {
-        b200s_handle* h = nullptr;
-        int rc = b200s_create(devices ? devices[i] : i, &h);
-        if (rc == B200S_OK) {
-            p->h.push_back(h);
-            rc = b200s_configure_slots(h, slots_per_gpu, rows, cols);
+    const int nb = 128;
+    DevBuf part;
+    if (part.ensure((size_t)nb * ch * 3 * sizeof(double))) return fail(h, B200S_ENOMEM, "cudaMalloc failed");
+    cudaStream_t st = stream_of(h, mat_id);
+    const size_t npix = (size_t)m->rows * m->cols;
+    h->launches += launch_mat_stats(m->buf.p, kind, npix, ch, (double*)part.p, nb, st);
+    std::vector<double> hp((size_t)nb * ch * 3);
+    cudaError_t e = cudaMemcpyAsync(hp.data(), part.p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    part.release();
+    if (e != cudaSuccess) return fail(h, B200S_ECUDA, cudaGetErrorString(e));
+    for (int c = 0; c < ch; ++c) {
+        double a = 1e300, b = -1e300, s = 0;
+        for (int k = 0; k < nb; ++k) {
+            const double* o = &hp[((size_t)k * ch + c) * 3];
+            a = std::min(a, o[0]); b = std::max(b, o[1]); s += o[2];
         }
-        if (rc != B200S_OK) {
-            for (b200s_handle* q : p->h) b200s_destroy(q);
-            delete p;
-            return rc;
-        }
+        if (mn) mn[c] = a;
+        if (mx) mx[c] = b;
+        if (mean) mean[c] = s / (double)npix;
     }
-    *out = p;
-    return B200S_OK;
-}
-
-int b200s_pool_destroy(b200s_pool* p)
-{
-    if (!p) return B200S_OK;
-    for (b200s_handle* h : p->h) b200s_destroy(h);
-    delete p;
-    return B200S_OK;
-}
-
-int b200s_pool_size(const b200s_pool* p) { return p ? (int)p->h.size() : 0; }
-b200s_handle* b200s_pool_handle(b200s_pool* p, int gpu) { return (p && gpu >= 0 && gpu < (int)p->h.size()) ? p->h[gpu] : nullptr; }
-const char* b200s_pool_last_error_string(const b200s_pool* p) { return p ? p->err.c_str() : "null pool"; }
-
-extern "C++" {
-namespace {
-template <class F>
-int pool_each(b200s_pool* p, F f)
-{
-    if (!p) return B200S_EINVAL;
-    for (b200s_handle* h : p->h) {
-        int rc = f(h);
-        if (rc != B200S_OK) { p->err = h->err; return rc; }
-    }
-    return B200S_OK;
-}
-}  // namespace
-}
-
-int b200s_pool_set_calibration(b200s_pool* p, const b200s_caminfo* l, const b200s_caminfo* r)
-{
-    return pool_each(p, [&](b200s_handle* h) { return b200s_set_calibration(h, l, r); });
-}
-
-int b200s_pool_set_params(b200s_pool* p, const b200s_params* prm)
-{
-    return pool_each(p, [&](b200s_handle* h) { return b200s_set_params(h, prm); });
-}
-
-int b200s_pool_submit(b200s_pool* p, uint64_t frame_index, const void* left, const void* right, const b200s_frame_io* io, int* gpu, int* slot)
-{
-    if (!p || p->h.empty()) return B200S_EINVAL;
-    const int n = (int)p->h.size();
-    const int g = (int)(frame_index % (uint64_t)n), s = (int)((frame_index / (uint64_t)n) % (uint64_t)p->slots);
-    if (gpu) *gpu = g;
-    if (slot) *slot = s;
-    b200s_handle* h = p->h[g];
-    // the slot's previous frame (and the caller's output buffers for it) must be complete before it is reused
-    int rc = b200s_wait_slot(h, s);
-    if (rc == B200S_OK) rc = b200s_process_pair_async(h, s, left, right, io);
-    if (rc != B200S_OK) p->err = h->err;
-    return rc;
-}
-
-int b200s_pool_wait(b200s_pool* p, int gpu, int slot)
-{
-    b200s_handle* h = b200s_pool_handle(p, gpu);
-    if (!h) return B200S_EINVAL;
-    int rc = b200s_wait_slot(h, slot);
-    if (rc != B200S_OK) p->err = h->err;
-    return rc;
-}
-
-int b200s_pool_wait_all(b200s_pool* p)
-{
-    return pool_each(p, [&](b200s_handle* h) {
-        for (int s = 0; s < (int)h->slots.size(); ++s) {
-            int rc = b200s_wait_slot(h, s);
-            if (rc != B200S_OK) return rc;
-        }
-        return (int)B200S_OK;
-    });
-}
-
-// ---- batch timing: one start event all slot streams wait on, one end event per slot stream ----------------
-int b200s_batch_begin(b200s_handle* h)
-{
-    if (!h || h->slots.empty()) return B200S_EINVAL;
-    DeviceGuard g(h->device);
-    if (!h->batch_start) CUDA_OK(h, cudaEventCreate(&h->batch_start));
-    while (h->batch_end.size() < h->slots.size()) {
-        cudaEvent_t e;
-        CUDA_OK(h, cudaEventCreate(&e));
-        h->batch_end.push_back(e);
-    }
-    CUDA_OK(h, cudaDeviceSynchronize());
-    CUDA_OK(h, cudaEventRecord(h->batch_start, h->slots[0].st));
-    for (size_t i = 1; i < h->slots.size(); ++i) CUDA_OK(h, cudaStreamWaitEvent(h->slots[i].st, h->batch_start, 0));
-    return B200S_OK;
-}
-
-int b200s_batch_end(b200s_handle* h, float* ms)
-{
-    if (!h || !ms || !h->batch_start || h->batch_end.size() < h->slots.size()) return B200S_EINVAL;
-    DeviceGuard g(h->device);
-    for (size_t i = 0; i < h->slots.size(); ++i) CUDA_OK(h, cudaEventRecord(h->batch_end[i], h->slots[i].st));
-    float best = 0;
-    for (size_t i = 0; i < h->slots.size(); ++i) {
-        CUDA_OK(h, cudaEventSynchronize(h->batch_end[i]));
-        float t = 0;
-        CUDA_OK(h, cudaEventElapsedTime(&t, h->batch_start, h->batch_end[i]));
-        if (t > best) best = t;
-    }
-    *ms = best;
-    return B200S_OK;
+    if (channels) *channels = ch;
+    return check_kernels(h, "mat_stats");
 }
 
 // ---- instrumentation -------------------------------------------------------------------------------------

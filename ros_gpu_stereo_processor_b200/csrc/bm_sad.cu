@@ -21,7 +21,8 @@ namespace b200s {
 int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg, int r, int lofs,
                  int XA, int XB, int YA, int YB, int16_t* disp, int16_t* cost, cudaStream_t st);
 int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg, int r, int lofs,
-                 int XA, int XB, int YA, int YB, int16_t* disp, int16_t* cost, cudaStream_t st);
+                 int XA, int XB, int YA, int YB, int16_t* disp, int16_t* cost, cudaStream_t st, int nf, size_t pre_stride,
+                 size_t disp_stride);
 
 __global__ void fill_s16_kernel(int16_t* p, size_t n, int16_t v)
 {
@@ -32,8 +33,10 @@ __global__ void fill_s16_kernel(int16_t* p, size_t n, int16_t v)
 // FILTERED everywhere outside [x0, x1) x [y0, y1) (that rectangle is written completely by the matcher kernels).
 // The thread index space is compact: first the nb = x0 + (W - x1) border columns of every row, then the interior
 // columns of the rows above y0 and below y1.
-__global__ void __launch_bounds__(256) fill_border_kernel(int16_t* __restrict__ p, int W, int H, int x0, int x1, int y0, int y1, int16_t v)
+__global__ void __launch_bounds__(256) fill_border_kernel(int16_t* __restrict__ p, int W, int H, int x0, int x1, int y0, int y1, int16_t v,
+                                                          size_t frame_stride)
 {
+    p = (int16_t*)((uint8_t*)p + blockIdx.y * frame_stride);      // blockIdx.y = frame of the batch
     const int nb = x0 + (W - x1), ni = x1 - x0, nrows_tb = y0 + (H - y1);
     const long long n_side = (long long)nb * H, total = n_side + (long long)ni * nrows_tb;
     long long i = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -664,15 +667,22 @@ static cudaError_t launch_fast(const FastParams& P, dim3 grid, int nt, size_t sm
     return cudaGetLastError();
 }
 
-int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg,
-                       int16_t* disp, int16_t* cost, BMScratch* sc, cudaStream_t st, double* evals)
+// one frame (nf == 1), or a whole batch when the warp-specialised matcher covers everything the configuration needs;
+// NOT_BATCHABLE tells the caller to go frame by frame
+static const int NOT_BATCHABLE = -1000;
+
+static int block_match_impl(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg,
+                            int16_t* disp, int16_t* cost, BMScratch* sc, cudaStream_t st, double* evals, int nf,
+                            size_t pre_stride, size_t disp_stride)
 {
     const Geom g = geom(W, H, cfg);
     const int16_t FILTERED = (int16_t)((cfg.minD - 1) * 16);
     int launches = 0;
     size_t n = (size_t)W * H;
-    if (cost) { cudaMemsetAsync(cost, 0, n * sizeof(int16_t), st); }
     if (evals) *evals = 0;
+    if (nf > 1 && g.degenerate) return NOT_BATCHABLE;
+    if (cost)
+        for (int f = 0; f < nf; ++f) cudaMemsetAsync((uint8_t*)cost + f * disp_stride, 0, n * sizeof(int16_t), st);
     if (g.degenerate) {
         fill_s16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(disp, n, FILTERED);
         return launches + 1;
@@ -683,13 +693,15 @@ int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W
     const int outX0 = need_bands ? compX0 : std::max(compX0, g.roiX0);
     const int outX1 = need_bands ? compX1 : std::min(compX1, g.roiX1);
     if (outX1 <= outX0) {
+        if (nf > 1) return NOT_BATCHABLE;
         fill_s16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(disp, n, FILTERED);
         return launches + 1;
     }
     {
         const long long nfill = (long long)(outX0 + (W - outX1)) * H + (long long)(outX1 - outX0) * (g.roiY0 + (H - g.roiY1));
         if (nfill > 0)
-            fill_border_kernel<<<(unsigned)((nfill + 255) / 256), 256, 0, st>>>(disp, W, H, outX0, outX1, g.roiY0, g.roiY1, FILTERED);
+            fill_border_kernel<<<dim3((unsigned)((nfill + 255) / 256), nf), 256, 0, st>>>(disp, W, H, outX0, outX1, g.roiY0, g.roiY1,
+                                                                                        FILTERED, disp_stride);
     }
     ++launches;
     if (evals) {
@@ -772,9 +784,25 @@ int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W
     static const int kernel_sel = getenv("B200S_KERNEL") ? atoi(getenv("B200S_KERNEL")) : 7;
     bool ws_done = false;
     if (fast_ok_base && kernel_sel >= 7) {
-        int rc = launch_bm_vh(Lp, Rp, pitch, W, H, cfg, g.r, g.lofs, XA, XB, g.roiY0, g.roiY1, disp, cost, st);
+        int rc = launch_bm_vh(Lp, Rp, pitch, W, H, cfg, g.r, g.lofs, XA, XB, g.roiY0, g.roiY1, disp, cost, st, nf, pre_stride,
+                              disp_stride);
         if (rc < 0) return -1;
         ws_done = rc == 1;
+    }
+    if (nf > 1) {
+        // a batch needs bm_vh (the border fill above is harmless to repeat frame by frame otherwise); the border strips
+        // of the L/R-check path go through the generic kernels frame by frame
+        if (!ws_done) return NOT_BATCHABLE;
+        ++launches;
+        for (int f = 0; f < nf; ++f) {
+            GenPlanes gf{Lp + f * pre_stride, Rp + f * pre_stride, pitch};
+            int l = run_generic_pair(gf, W, H, cfg, g, outX0 - g.lofs, XA - g.lofs, XB - g.lofs, outX1 - g.lofs,
+                                     (int16_t*)((uint8_t*)disp + f * disp_stride),
+                                     cost ? (int16_t*)((uint8_t*)cost + f * disp_stride) : nullptr, sc, st);
+            if (l < 0) return l;
+            launches += l;
+        }
+        return launches;
     }
     if (!ws_done && fast_ok_base && kernel_sel >= 4) {
         int rc = launch_bm_ws(Lp, Rp, pitch, W, H, cfg, g.r, g.lofs, XA, XB, g.roiY0, g.roiY1, disp, cost, st);
@@ -807,6 +835,23 @@ int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W
         launches += l;
     }
     return launches;
+}
+
+int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg,
+                       int16_t* disp, int16_t* cost, BMScratch* sc, cudaStream_t st, double* evals, int nf, size_t pre_stride,
+                       size_t disp_stride)
+{
+    if (nf <= 1) return block_match_impl(Lp, Rp, pitch, W, H, cfg, disp, cost, sc, st, evals, 1, 0, 0);
+    int rc = block_match_impl(Lp, Rp, pitch, W, H, cfg, disp, cost, sc, st, evals, nf, pre_stride, disp_stride);
+    if (rc != NOT_BATCHABLE) return rc;
+    int total = 0;
+    for (int f = 0; f < nf; ++f) {
+        rc = block_match_impl(Lp + f * pre_stride, Rp + f * pre_stride, pitch, W, H, cfg, (int16_t*)((uint8_t*)disp + f * disp_stride),
+                              cost ? (int16_t*)((uint8_t*)cost + f * disp_stride) : nullptr, sc, st, evals, 1, 0, 0);
+        if (rc < 0) return rc;
+        total += rc;
+    }
+    return total;
 }
 
 }  // namespace b200s

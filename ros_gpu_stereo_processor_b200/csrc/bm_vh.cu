@@ -50,6 +50,7 @@ struct VhParams {
     int oTc;                         // [8][ncols] words: texture column sums (ring over output rows)
     int oS[2], oK[2];
     int oMbar;                       // 8 mbarriers
+    size_t pre_stride, disp_stride;  // bytes between the frames of a batch (blockIdx.z = frame)
 };
 
 namespace vh {
@@ -103,6 +104,11 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int NVt = P.nVw * 32, NWt = P.nWw * 32, NSt = P.nSw * 32;
+    // frame of the batch this block works on
+    const uint8_t* __restrict__ const gLp = P.Lp + blockIdx.z * P.pre_stride;
+    const uint8_t* __restrict__ const gRp = P.Rp + blockIdx.z * P.pre_stride;
+    int16_t* __restrict__ const gdisp = (int16_t*)((uint8_t*)P.disp + blockIdx.z * P.disp_stride);
+    int16_t* __restrict__ const gcost = P.cost ? (int16_t*)((uint8_t*)P.cost + blockIdx.z * P.disp_stride) : nullptr;
     const int X0 = P.X0base + blockIdx.x * P.TW;
     const int yb0 = P.YA + blockIdx.y * P.BH;
     const int yb1 = min(yb0 + P.BH, P.YB);
@@ -324,8 +330,8 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
                         out = (int16_t)(((nd - mind - 1 + P.minD) * 256 + (num < 0 ? -q : q) + 15) >> 4);
                     }
                     const int y = yb0 + o;
-                    P.disp[(size_t)y * P.W + X] = out;
-                    if (P.cost) P.cost[(size_t)y * P.W + X] = (int16_t)minsad;
+                    gdisp[(size_t)y * P.W + X] = out;
+                    if (gcost) gcost[(size_t)y * P.W + X] = (int16_t)minsad;
                 }
             }
             mbar_arrive(mb + 8 * (MB_EMPTY_S + cb));
@@ -345,7 +351,7 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
 #pragma unroll
             for (int m = 0; m < MAXL; ++m) {
                 const int c = lane + 32 * m;
-                an[m] = c < P.ncolsP ? (int)__ldg(P.Lp + (size_t)y_in0 * P.pitch + Xl0 + c) : 0;
+                an[m] = c < P.ncolsP ? (int)__ldg(gLp + (size_t)y_in0 * P.pitch + Xl0 + c) : 0;
                 ao[m] = 0;
                 trun[m] = 0;
             }
@@ -357,8 +363,8 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
                 if (j + 1 < nIn) {
                     const int yi = y_in0 + j + 1;
                     const bool has_old = j + 1 >= b;
-                    const uint8_t* ln = P.Lp + (size_t)yi * P.pitch + Xl0;
-                    const uint8_t* lo = P.Lp + (size_t)max(yi - b, 0) * P.pitch + Xl0;
+                    const uint8_t* ln = gLp + (size_t)yi * P.pitch + Xl0;
+                    const uint8_t* lo = gLp + (size_t)max(yi - b, 0) * P.pitch + Xl0;
 #pragma unroll
                     for (int m = 0; m < MAXL; ++m) {
                         const int c = lane + 32 * m;
@@ -395,7 +401,7 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
 #pragma unroll
             for (int m = 0; m < MAXR; ++m) {
                 const int wi = w0 + wstep * m;
-                vn[m] = wi < P.RLW ? __ldg((const uint32_t*)(P.Rp + (size_t)y_in0 * P.pitch + Xr0) + wi) : 0u;
+                vn[m] = wi < P.RLW ? __ldg((const uint32_t*)(gRp + (size_t)y_in0 * P.pitch + Xr0) + wi) : 0u;
                 vo[m] = 0u;
             }
             for (int j = 0; j < nIn; ++j) {
@@ -406,8 +412,8 @@ __global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
                 if (j + 1 < nIn) {
                     const int yi = y_in0 + j + 1;
                     const bool has_old = j + 1 >= b;
-                    const uint32_t* rn = (const uint32_t*)(P.Rp + (size_t)yi * P.pitch + Xr0);
-                    const uint32_t* ro = (const uint32_t*)(P.Rp + (size_t)max(yi - b, 0) * P.pitch + Xr0);
+                    const uint32_t* rn = (const uint32_t*)(gRp + (size_t)yi * P.pitch + Xr0);
+                    const uint32_t* ro = (const uint32_t*)(gRp + (size_t)max(yi - b, 0) * P.pitch + Xr0);
 #pragma unroll
                     for (int m = 0; m < MAXR; ++m) {
                         const int wi = w0 + wstep * m;
@@ -463,7 +469,8 @@ static cudaError_t launch_vh(const VhParams& P, dim3 grid, int nt, size_t smem, 
 
 // returns 1 when launched, 0 when this configuration is not handled (caller falls back), < 0 on CUDA errors
 int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg, int r, int lofs,
-                 int XA, int XB, int YA, int YB, int16_t* disp, int16_t* cost, cudaStream_t st)
+                 int XA, int XB, int YA, int YB, int16_t* disp, int16_t* cost, cudaStream_t st, int nf, size_t pre_stride,
+                 size_t disp_stride)
 {
     using vh::NC;
     const int nd = cfg.nd;
@@ -517,7 +524,7 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
             if (bands_env > 0 && bands != std::min(bands_env, max_bands)) continue;
             const int BH = (rows + bands - 1) / bands;
             if (128 * (BH + 2 * r + 1) + 2 * cfg.cap * (2 * r + 1) * (2 * r + 1) > 65535) continue;   // bias of the odd columns
-            const int nb = tilesX * ((rows + BH - 1) / BH);
+            const int nb = tilesX * ((rows + BH - 1) / BH) * nf;
             const int per_sm = (nb + n_sm - 1) / n_sm;
             const int conc = std::min(occ, per_sm), waves = (per_sm + occ - 1) / occ;
             // Measured on B200 (tools/sweep_vh.sh, profiles/r01_v7_planner_sweep.md): a block row costs about
@@ -539,12 +546,13 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
     P.W = W; P.H = H; P.nd = nd; P.minD = cfg.minD; P.r = r; P.cap = cfg.cap;
     P.texThr = cfg.textureThreshold; P.uniq = cfg.uniquenessRatio; P.lofs = lofs;
     P.X0base = X0base; P.XA = XA; P.XB = XB; P.YA = YA; P.YB = YB;
+    P.pre_stride = pre_stride; P.disp_stride = disp_stride;
     const int tilesX = (need + P.TW - 1) / P.TW;
     P.BH = (rows + best_bands - 1) / best_bands;
-    dim3 grid(tilesX, (rows + P.BH - 1) / P.BH);
+    dim3 grid(tilesX, (rows + P.BH - 1) / P.BH, nf);
     if (verbose)
-        fprintf(stderr, "bm_vh plan: NCB=%d TW=%d BH=%d grid=%dx%d warps V/W/S=%d/%d/%d smem=%zu\n", P.NCB, P.TW, P.BH, grid.x, grid.y,
-                P.nVw, P.nWw, P.nSw, smem);
+        fprintf(stderr, "bm_vh plan: NCB=%d TW=%d BH=%d grid=%dx%dx%d warps V/W/S=%d/%d/%d smem=%zu\n", P.NCB, P.TW, P.BH, grid.x, grid.y,
+                grid.z, P.nVw, P.nWw, P.nSw, smem);
     cudaError_t e;
     switch (r) {
     case 2: e = launch_vh<2>(P, grid, nt, smem, st); break;

@@ -123,9 +123,15 @@ __device__ __forceinline__ void sm_union(int* L, int a, int b)
 // Every run end then adds its run length to the tile-local root's pixel count (one shared-memory atomic per run, not per
 // pixel).  Writes L[i] = global index of the tile-local root (or -1 for newVal pixels) and sz[i] = pixel count of the
 // tile-local component at its root, 0 everywhere else.
+// Batches: the frame index is the last used grid dimension of every ccl kernel; `ist` / `sst` are the byte distances
+// between the image planes and between the scratch blocks (L, sz) of consecutive frames.
 __global__ void __launch_bounds__(256) ccl_local_kernel(const int16_t* __restrict__ img, int* __restrict__ L,
-                                                        int* __restrict__ sz, int W, int H, int newVal, int maxDiff)
+                                                        int* __restrict__ sz, int W, int H, int newVal, int maxDiff,
+                                                        size_t ist, size_t sst)
 {
+    img = (const int16_t*)((const uint8_t*)img + blockIdx.z * ist);
+    L = (int*)((uint8_t*)L + blockIdx.z * sst);
+    sz = (int*)((uint8_t*)sz + blockIdx.z * sst);
     __shared__ int16_t v[CTY * CTX];
     __shared__ int16_t rs[CTY * CTX];     // immutable run start (tile index) of every pixel, -1 for newVal
     __shared__ int lab[CTY * CTX];        // union-find parents over tile indices (only run starts ever get hooked)
@@ -212,8 +218,10 @@ __global__ void __launch_bounds__(256) ccl_local_kernel(const int16_t* __restric
 
 // ---- stage 2: unions across tile borders (global union-find), one thread per border pixel ------------------------
 __global__ void __launch_bounds__(256) ccl_border_kernel(const int16_t* __restrict__ img, int* __restrict__ L, int W,
-                                                         int H, int newVal, int maxDiff)
+                                                         int H, int newVal, int maxDiff, size_t ist, size_t sst)
 {
+    img = (const int16_t*)((const uint8_t*)img + blockIdx.y * ist);
+    L = (int*)((uint8_t*)L + blockIdx.y * sst);
     const int ncx = (W - 1) / CTX;            // tile columns that have a right neighbour
     const int ncy = (H - 1) / CTY;            // tile rows that have a lower neighbour
     const long long nR = (long long)ncx * H, total = nR + (long long)ncy * W;
@@ -247,8 +255,10 @@ __global__ void __launch_bounds__(256) ccl_border_kernel(const int16_t* __restri
 
 // ---- stage 3: every tile-local root (sz > 0) that was hooked under another root adds its count to the global root
 // and is pointed straight at it, so that afterwards L[L[i]] is the global root of any pixel i ----------------------
-__global__ void __launch_bounds__(256) ccl_merge_counts_kernel(int* __restrict__ L, int* __restrict__ sz, int n)
+__global__ void __launch_bounds__(256) ccl_merge_counts_kernel(int* __restrict__ L, int* __restrict__ sz, int n, size_t sst)
 {
+    L = (int*)((uint8_t*)L + blockIdx.y * sst);
+    sz = (int*)((uint8_t*)sz + blockIdx.y * sst);
     // four pixels per thread (one 16-byte load of the counts): roots are sparse, most threads stop here
     const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i0 >= n) return;
@@ -273,8 +283,12 @@ __global__ void __launch_bounds__(256) ccl_merge_counts_kernel(int* __restrict__
 }
 
 __global__ void __launch_bounds__(256) ccl_apply_kernel(int16_t* __restrict__ img, const int* __restrict__ L,
-                                                        const int* __restrict__ sz, int n, int newVal, int maxSize)
+                                                        const int* __restrict__ sz, int n, int newVal, int maxSize,
+                                                        size_t ist, size_t sst)
 {
+    img = (int16_t*)((uint8_t*)img + blockIdx.y * ist);
+    L = (const int*)((const uint8_t*)L + blockIdx.y * sst);
+    sz = (const int*)((const uint8_t*)sz + blockIdx.y * sst);
     const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i0 >= n) return;
     int p4[4] = {-1, -1, -1, -1};
@@ -314,19 +328,22 @@ int launch_roi_mask(int16_t* disp, int W, int H, const BMConfig& cfg, cudaStream
     return 1;
 }
 
-int launch_filter_speckles(int16_t* img, int W, int H, int newVal, int maxSize, int maxDiff, int* scratch, cudaStream_t st)
+int launch_filter_speckles(int16_t* img, int W, int H, int newVal, int maxSize, int maxDiff, int* scratch, cudaStream_t st,
+                           int nf, size_t img_stride, size_t scratch_stride)
 {
     int n = W * H;
     int* L = scratch;
     int* sz = scratch + (((size_t)n + 3) & ~(size_t)3);   // 16-byte aligned like L (the scratch holds 3n ints)
-    ccl_local_kernel<<<dim3((W + CTX - 1) / CTX, (H + CTY - 1) / CTY), 256, 0, st>>>(img, L, sz, W, H, newVal, maxDiff);
+    ccl_local_kernel<<<dim3((W + CTX - 1) / CTX, (H + CTY - 1) / CTY, nf), 256, 0, st>>>(img, L, sz, W, H, newVal, maxDiff, img_stride,
+                                                                                        scratch_stride);
     {
         const long long nbp = (long long)((W - 1) / CTX) * H + (long long)((H - 1) / CTY) * W;
-        if (nbp > 0) ccl_border_kernel<<<(unsigned)((nbp + 255) / 256), 256, 0, st>>>(img, L, W, H, newVal, maxDiff);
+        if (nbp > 0)
+            ccl_border_kernel<<<dim3((unsigned)((nbp + 255) / 256), nf), 256, 0, st>>>(img, L, W, H, newVal, maxDiff, img_stride, scratch_stride);
     }
     const int nb4 = (n + 1023) / 1024;
-    ccl_merge_counts_kernel<<<nb4, 256, 0, st>>>(L, sz, n);
-    ccl_apply_kernel<<<nb4, 256, 0, st>>>(img, L, sz, n, newVal, maxSize);
+    ccl_merge_counts_kernel<<<dim3(nb4, nf), 256, 0, st>>>(L, sz, n, scratch_stride);
+    ccl_apply_kernel<<<dim3(nb4, nf), 256, 0, st>>>(img, L, sz, n, newVal, maxSize, img_stride, scratch_stride);
     return 4;
 }
 

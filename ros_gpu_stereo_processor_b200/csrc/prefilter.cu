@@ -78,6 +78,45 @@ __global__ void swap_rb_kernel(const uint8_t* __restrict__ src, uint8_t* __restr
     dst[3 * (size_t)i] = c; dst[3 * (size_t)i + 1] = b; dst[3 * (size_t)i + 2] = a;
 }
 
+// printStats: per-channel min / max / sum of a plane; one partial (min, max, sum) triple per block and channel
+template <typename T>
+__global__ void __launch_bounds__(256) mat_stats_kernel(const T* __restrict__ src, size_t npix, int ch, double* __restrict__ part)
+{
+    __shared__ double smn[256], smx[256], ssum[256];
+    for (int c = 0; c < ch; ++c) {
+        double mn = 1e300, mx = -1e300, sum = 0;
+        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < npix; i += (size_t)gridDim.x * 256) {
+            const double v = (double)src[i * ch + c];
+            mn = fmin(mn, v); mx = fmax(mx, v); sum += v;
+        }
+        smn[threadIdx.x] = mn; smx[threadIdx.x] = mx; ssum[threadIdx.x] = sum;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                smn[threadIdx.x] = fmin(smn[threadIdx.x], smn[threadIdx.x + s]);
+                smx[threadIdx.x] = fmax(smx[threadIdx.x], smx[threadIdx.x + s]);
+                ssum[threadIdx.x] += ssum[threadIdx.x + s];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            double* o = part + ((size_t)blockIdx.x * ch + c) * 3;
+            o[0] = smn[0]; o[1] = smx[0]; o[2] = ssum[0];
+        }
+        __syncthreads();
+    }
+}
+
+int launch_mat_stats(const void* src, int elem_kind, size_t npix, int ch, double* partials, int nblocks, cudaStream_t st)
+{
+    switch (elem_kind) {
+    case 0: mat_stats_kernel<uint8_t><<<nblocks, 256, 0, st>>>((const uint8_t*)src, npix, ch, partials); break;
+    case 1: mat_stats_kernel<int16_t><<<nblocks, 256, 0, st>>>((const int16_t*)src, npix, ch, partials); break;
+    default: mat_stats_kernel<float><<<nblocks, 256, 0, st>>>((const float*)src, npix, ch, partials); break;
+    }
+    return 1;
+}
+
 static inline dim3 grid2d(int W, int H) { return dim3((W + 31) / 32, (H + 7) / 8); }
 
 int launch_prefilter_xsobel(const uint8_t* src, uint8_t* dst, size_t dst_pitch, int W, int H, int cap, cudaStream_t st)

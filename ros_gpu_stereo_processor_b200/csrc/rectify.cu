@@ -58,20 +58,44 @@ __device__ __forceinline__ int sample_linear(const uint8_t* __restrict__ s, int 
     return (acc + 512) >> 10;
 }
 
-__global__ void __launch_bounds__(256) build_map_kernel(CamModel cm, int W, int H, int2* __restrict__ map)
-{
-    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x < W && y < H) map[(size_t)y * W + x] = map_point(cm, x, y);
-}
-
-template <bool FLY, int CH>
-__global__ void __launch_bounds__(256) remap_kernel(const uint8_t* __restrict__ src, int sW, int sH,
-                                                    const int2* __restrict__ map, CamModel cm,
-                                                    uint8_t* __restrict__ dst, int W, int H)
+// DELTA: 4 B/px table of (sx - 32 x, sy - 32 y) as int16 pairs; *overflow is raised when a delta does not fit
+template <bool DELTA>
+__global__ void __launch_bounds__(256) build_map_kernel(CamModel cm, int W, int H, void* __restrict__ map, int* __restrict__ overflow)
 {
     int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= W || y >= H) return;
-    int2 m = FLY ? map_point(cm, x, y) : __ldg(map + (size_t)y * W + x);
+    const int2 m = map_point(cm, x, y);
+    if (!DELTA) {
+        ((int2*)map)[(size_t)y * W + x] = m;
+        return;
+    }
+    const int dx = m.x - 32 * x, dy = m.y - 32 * y;
+    if (dx < -32768 || dx > 32767 || dy < -32768 || dy > 32767) atomicOr(overflow, 1);
+    ((uint32_t*)map)[(size_t)y * W + x] = ((uint32_t)dx & 0xffffu) | ((uint32_t)dy << 16);
+}
+
+template <int MODE>
+__device__ __forceinline__ int2 map_at(const void* __restrict__ map, const CamModel& cm, int x, int y, int W)
+{
+    if (MODE == MAP_FLY) return map_point(cm, x, y);
+    if (MODE == MAP_DELTA16) {
+        const uint32_t v = __ldg((const uint32_t*)map + (size_t)y * W + x);
+        return make_int2(32 * x + (int)(int16_t)(v & 0xffffu), 32 * y + ((int)v >> 16));
+    }
+    if (MODE == MAP_ABS32) return __ldg((const int2*)map + (size_t)y * W + x);
+    return make_int2(32 * x, 32 * y);
+}
+
+template <int MODE, int CH>
+__global__ void __launch_bounds__(256) remap_kernel(const uint8_t* __restrict__ src, int sW, int sH,
+                                                    const void* __restrict__ map, CamModel cm,
+                                                    uint8_t* __restrict__ dst, int W, int H, size_t src_stride, size_t dst_stride)
+{
+    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    src += blockIdx.z * src_stride;
+    dst += blockIdx.z * dst_stride;
+    const int2 m = map_at<MODE>(map, cm, x, y, W);
 #pragma unroll
     for (int c = 0; c < CH; ++c) dst[((size_t)y * W + x) * CH + c] = (uint8_t)sample_linear(src, sW, sH, CH, c, m);
 }
@@ -99,22 +123,27 @@ constexpr int FT_PER = (FT_N + 255) / 256;           // pixels per thread
 
 struct RectSide {
     const uint8_t* src;
-    const int2* map;
+    const void* map;
     uint8_t* rect;
     uint8_t* pre;
     CamModel cm;
 };
+struct BatchStrides {      // bytes between consecutive frames of a batch (blockIdx.z = 2 * frame + side)
+    size_t src, rect, pre;
+};
 
-// blockIdx.z selects the side, so that one launch rectifies and prefilters the left and the right image.
-// Each thread first fetches (or evaluates) the map entries of its FT_PER tile pixels, then issues all 4*FT_PER
-// gathers, then blends: the dependent global loads of different pixels overlap.
-template <bool FLY>
-__global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSide sr, int sW, int sH, size_t ppitch,
-                                                             int W, int H, int cap)
+// blockIdx.z selects frame and side, so that one launch rectifies and prefilters the left and the right images of a
+// whole batch.  Each thread first fetches (or evaluates) the map entries of its FT_PER tile pixels, then issues all
+// 4*FT_PER gathers, then blends: the dependent global loads of different pixels overlap.
+// MODE = MAP_NONE: the source is already rectified (tile = source pixels, no rectified plane is written).
+template <int MODE>
+__global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSide sr, BatchStrides bs, int sW, int sH,
+                                                             size_t ppitch, int W, int H, int cap)
 {
     __shared__ __align__(16) uint8_t tile[FTY + 2][FTX + 2 + 2];
-    const RectSide& S = blockIdx.z ? sr : sl;
-    const uint8_t* __restrict__ src = S.src;
+    const RectSide& S = (blockIdx.z & 1) ? sr : sl;
+    const int frame = blockIdx.z >> 1;
+    const uint8_t* __restrict__ src = S.src + frame * bs.src;
     const int x0 = blockIdx.x * FTX, y0 = blockIdx.y * FTY;
     int2 m[FT_PER];
     bool ok[FT_PER];
@@ -127,14 +156,16 @@ __global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSi
         const int ys = y < 0 ? 1 : (y >= H ? H - 2 : y);
         ok[k] = i < FT_N && x >= 0 && x < W && ys >= 0 && ys < H;
         m[k] = make_int2(0, 0);
-        if (ok[k]) m[k] = FLY ? map_point(S.cm, x, ys) : __ldg(S.map + (size_t)ys * W + x);
+        if (ok[k]) m[k] = map_at<MODE>(S.map, S.cm, x, ys, W);
     }
     int s00[FT_PER], s01[FT_PER], s10[FT_PER], s11[FT_PER];
 #pragma unroll
     for (int k = 0; k < FT_PER; ++k) {
         const int X0 = sat16(m[k].x >> 5), Y0 = sat16(m[k].y >> 5);
         s00[k] = s01[k] = s10[k] = s11[k] = 0;
-        if (ok[k]) {
+        if (MODE == MAP_NONE) {
+            if (ok[k]) s00[k] = __ldg(src + (size_t)Y0 * sW + X0);      // identity map: a = b = 0, only s00 counts
+        } else if (ok[k]) {
             if ((unsigned)X0 < (unsigned)(sW - 1) && (unsigned)Y0 < (unsigned)(sH - 1)) {
                 // the whole 2x2 footprint is inside the source image (the common case): no per-tap border test
                 const uint8_t* p = src + (size_t)Y0 * sW + X0;
@@ -192,14 +223,13 @@ __global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSi
                 for (int i = 0; i < 4; ++i)
                     if (x + i == 0 || x + i >= W - 1) pre4 = (pre4 & ~(0xffu << (8 * i))) | ((uint32_t)cap << (8 * i));
             }
-            uint8_t* pp = S.pre + (size_t)y * ppitch + x;
-            uint8_t* rp = S.rect + (size_t)y * W + x;
-            if (x + 3 < W) {
-                *(uint32_t*)pp = pre4;                               // ppitch % 16 == 0 and x % 4 == 0
-                if ((W & 3) == 0) *(uint32_t*)rp = rect4;
-                else { rp[0] = (uint8_t)rect4; rp[1] = (uint8_t)(rect4 >> 8); rp[2] = (uint8_t)(rect4 >> 16); rp[3] = (uint8_t)(rect4 >> 24); }
-            } else {
-                for (int i = 0; i < 4 && x + i < W; ++i) { pp[i] = (uint8_t)(pre4 >> (8 * i)); rp[i] = (uint8_t)(rect4 >> (8 * i)); }
+            uint8_t* pp = S.pre + frame * bs.pre + (size_t)y * ppitch + x;
+            if (x + 3 < W) *(uint32_t*)pp = pre4;                    // ppitch % 16 == 0 and x % 4 == 0
+            else for (int i = 0; i < 4 && x + i < W; ++i) pp[i] = (uint8_t)(pre4 >> (8 * i));
+            if (MODE != MAP_NONE) {
+                uint8_t* rp = S.rect + frame * bs.rect + (size_t)y * W + x;
+                if (x + 3 < W && (W & 3) == 0 && (bs.rect & 3) == 0) *(uint32_t*)rp = rect4;
+                else for (int i = 0; i < 4 && x + i < W; ++i) rp[i] = (uint8_t)(rect4 >> (8 * i));
             }
         }
     }
@@ -214,14 +244,15 @@ __global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSi
 constexpr int NTX = 64, NTY = 16, NP2MAX = 10;                 // preFilterSize <= 21
 constexpr int NTW = NTX + 2 * NP2MAX + 4;                      // tile row stride (bytes / u16 entries)
 
-template <int MODE>     // 0: source is already rectified, 1: cached rectification map, 2: map evaluated on the fly
-__global__ void __launch_bounds__(256) norm_prefilter_kernel(RectSide sl, RectSide sr, int sW, int sH, size_t ppitch, int W,
-                                                             int H, int p2, int scale_g, int scale_s, int cap)
+template <int MODE>     // MapMode: MAP_NONE = source is already rectified
+__global__ void __launch_bounds__(256) norm_prefilter_kernel(RectSide sl, RectSide sr, BatchStrides bs, int sW, int sH,
+                                                             size_t ppitch, int W, int H, int p2, int scale_g, int scale_s, int cap)
 {
     __shared__ __align__(16) uint8_t tile[NTY + 2 * NP2MAX][NTW];
     __shared__ __align__(16) uint16_t vs[NTY][NTW];
-    const RectSide& S = blockIdx.z ? sr : sl;
-    const uint8_t* __restrict__ src = S.src;
+    const RectSide& S = (blockIdx.z & 1) ? sr : sl;
+    const int frame = blockIdx.z >> 1;
+    const uint8_t* __restrict__ src = S.src + frame * bs.src;
     const int x0 = blockIdx.x * NTX, y0 = blockIdx.y * NTY;
     const int tw = NTX + 2 * p2, th = NTY + 2 * p2, tn = tw * th;
     for (int i0 = threadIdx.x; i0 < tn; i0 += 4 * 256) {
@@ -236,14 +267,14 @@ __global__ void __launch_bounds__(256) norm_prefilter_kernel(RectSide sl, RectSi
             xs[k] = min(max(x0 + tx - p2, 0), W - 1);           // replicate border of the (rectified) image
             ys[k] = min(max(y0 + ty - p2, 0), H - 1);
             m[k] = make_int2(0, 0);
-            if (MODE != 0 && in[k]) m[k] = MODE == 2 ? map_point(S.cm, xs[k], ys[k]) : __ldg(S.map + (size_t)ys[k] * W + xs[k]);
+            if (MODE != MAP_NONE && in[k]) m[k] = map_at<MODE>(S.map, S.cm, xs[k], ys[k], W);
         }
         int v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             v[k] = 0;
             if (!in[k]) continue;
-            if (MODE == 0) v[k] = __ldg(src + (size_t)ys[k] * sW + xs[k]);
+            if (MODE == MAP_NONE) v[k] = __ldg(src + (size_t)ys[k] * sW + xs[k]);
             else v[k] = sample_linear(src, sW, sH, 1, 0, m[k]);
         }
 #pragma unroll
@@ -283,77 +314,97 @@ __global__ void __launch_bounds__(256) norm_prefilter_kernel(RectSide sl, RectSi
                 rect4 |= (uint32_t)cr[0] << (8 * i);
                 if (i < 3) sum += (int)vs[ty][tx + i + 2 * p2 + 1] - (int)vs[ty][tx + i];
             }
-            uint8_t* pp = S.pre + (size_t)y * ppitch + x;
+            uint8_t* pp = S.pre + frame * bs.pre + (size_t)y * ppitch + x;
             if (x + 3 < W) *(uint32_t*)pp = pre4;                // ppitch % 16 == 0 and x % 4 == 0
             else for (int i = 0; i < 4 && x + i < W; ++i) pp[i] = (uint8_t)(pre4 >> (8 * i));
-            if (MODE != 0 && S.rect) {
-                uint8_t* rp = S.rect + (size_t)y * W + x;
-                if (x + 3 < W && (W & 3) == 0) *(uint32_t*)rp = rect4;
+            if (MODE != MAP_NONE && S.rect) {
+                uint8_t* rp = S.rect + frame * bs.rect + (size_t)y * W + x;
+                if (x + 3 < W && (W & 3) == 0 && (bs.rect & 3) == 0) *(uint32_t*)rp = rect4;
                 else for (int i = 0; i < 4 && x + i < W; ++i) rp[i] = (uint8_t)(rect4 >> (8 * i));
             }
         }
     }
 }
 
-static inline dim3 grid2d(int W, int H) { return dim3((W + 31) / 32, (H + 7) / 8); }
+static inline dim3 grid2d(int W, int H, int nf = 1) { return dim3((W + 31) / 32, (H + 7) / 8, nf); }
 
 // returns 0 when preFilterSize is too large for the tile kernel (the caller uses the two-pass kernels then)
-int launch_norm_prefilter_pair(const uint8_t* srcL, const uint8_t* srcR, int sW, int sH, bool rectify, const int2* mapL,
-                               const int2* mapR, const CamModel& cmL, const CamModel& cmR, uint8_t* rectL, uint8_t* rectR,
-                               uint8_t* preL, uint8_t* preR, size_t pre_pitch, int W, int H, int ps, int cap, cudaStream_t st)
+int launch_norm_prefilter_pair(const uint8_t* srcL, const uint8_t* srcR, int sW, int sH, MapMode mode, const void* mapL,
+                               const void* mapR, const CamModel& cmL, const CamModel& cmR, uint8_t* rectL, uint8_t* rectR,
+                               uint8_t* preL, uint8_t* preR, size_t pre_pitch, int W, int H, int ps, int cap, cudaStream_t st,
+                               int nf, size_t src_stride, size_t rect_stride, size_t pre_stride)
 {
     const int p2 = ps / 2;
     if (p2 > NP2MAX) return 0;
     int scale_g = ps * ps / 8, scale_s = (1024 + scale_g) / (scale_g * 2);
     scale_g *= scale_s;
-    dim3 g((W + NTX - 1) / NTX, (H + NTY - 1) / NTY, 2);
+    dim3 g((W + NTX - 1) / NTX, (H + NTY - 1) / NTY, 2 * nf);
     RectSide l{srcL, mapL, rectL, preL, cmL}, r{srcR, mapR, rectR, preR, cmR};
-    if (!rectify) norm_prefilter_kernel<0><<<g, 256, 0, st>>>(l, r, sW, sH, pre_pitch, W, H, p2, scale_g, scale_s, cap);
-    else if (mapL && mapR) norm_prefilter_kernel<1><<<g, 256, 0, st>>>(l, r, sW, sH, pre_pitch, W, H, p2, scale_g, scale_s, cap);
-    else norm_prefilter_kernel<2><<<g, 256, 0, st>>>(l, r, sW, sH, pre_pitch, W, H, p2, scale_g, scale_s, cap);
+    BatchStrides bs{src_stride, rect_stride, pre_stride};
+    switch (mode) {
+    case MAP_NONE: norm_prefilter_kernel<MAP_NONE><<<g, 256, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, p2, scale_g, scale_s, cap); break;
+    case MAP_ABS32: norm_prefilter_kernel<MAP_ABS32><<<g, 256, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, p2, scale_g, scale_s, cap); break;
+    case MAP_DELTA16: norm_prefilter_kernel<MAP_DELTA16><<<g, 256, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, p2, scale_g, scale_s, cap); break;
+    default: norm_prefilter_kernel<MAP_FLY><<<g, 256, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, p2, scale_g, scale_s, cap); break;
+    }
     return 1;
 }
 
-int launch_build_map(const CamModel& cm, int W, int H, int2* map, cudaStream_t st)
+int launch_build_map(const CamModel& cm, int W, int H, void* map, MapMode mode, int* overflow, cudaStream_t st)
 {
-    build_map_kernel<<<grid2d(W, H), 256, 0, st>>>(cm, W, H, map);
+    if (mode == MAP_DELTA16) {
+        cudaMemsetAsync(overflow, 0, sizeof(int), st);
+        build_map_kernel<true><<<grid2d(W, H), 256, 0, st>>>(cm, W, H, map, overflow);
+    } else {
+        build_map_kernel<false><<<grid2d(W, H), 256, 0, st>>>(cm, W, H, map, overflow);
+    }
     return 1;
 }
 
-int launch_remap(const uint8_t* src, int sW, int sH, int ch, const int2* map, const CamModel& cm, uint8_t* dst,
-                 int W, int H, cudaStream_t st)
+template <int CH>
+static void launch_remap_ch(const uint8_t* src, int sW, int sH, const void* map, MapMode mode, const CamModel& cm, uint8_t* dst,
+                            int W, int H, cudaStream_t st, int nf, size_t ss, size_t ds)
 {
-    dim3 g = grid2d(W, H);
-    if (ch == 1) {
-        if (map) remap_kernel<false, 1><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H);
-        else remap_kernel<true, 1><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H);
-    } else if (ch == 3) {
-        if (map) remap_kernel<false, 3><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H);
-        else remap_kernel<true, 3><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H);
-    } else if (ch == 4) {
-        if (map) remap_kernel<false, 4><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H);
-        else remap_kernel<true, 4><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H);
-    } else
-        return -1;
+    const dim3 g = grid2d(W, H, nf);
+    switch (mode) {
+    case MAP_ABS32: remap_kernel<MAP_ABS32, CH><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H, ss, ds); break;
+    case MAP_DELTA16: remap_kernel<MAP_DELTA16, CH><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H, ss, ds); break;
+    default: remap_kernel<MAP_FLY, CH><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H, ss, ds); break;
+    }
+}
+
+int launch_remap(const uint8_t* src, int sW, int sH, int ch, const void* map, MapMode mode, const CamModel& cm, uint8_t* dst,
+                 int W, int H, cudaStream_t st, int nf, size_t src_stride, size_t dst_stride)
+{
+    if (!map) mode = MAP_FLY;
+    if (ch == 1) launch_remap_ch<1>(src, sW, sH, map, mode, cm, dst, W, H, st, nf, src_stride, dst_stride);
+    else if (ch == 3) launch_remap_ch<3>(src, sW, sH, map, mode, cm, dst, W, H, st, nf, src_stride, dst_stride);
+    else if (ch == 4) launch_remap_ch<4>(src, sW, sH, map, mode, cm, dst, W, H, st, nf, src_stride, dst_stride);
+    else return -1;
     return 1;
 }
 
-int launch_remap_nearest(const uint8_t* src, int sW, int sH, int ch, const int2* map, const CamModel& cm,
-                         uint8_t* dst, int W, int H, cudaStream_t st)
+int launch_remap_nearest(const uint8_t* src, int sW, int sH, int ch, const CamModel& cm, uint8_t* dst, int W, int H,
+                         cudaStream_t st)
 {
-    (void)map;
     remap_nearest_kernel<<<grid2d(W, H), 256, 0, st>>>(src, sW, sH, ch, cm, dst, W, H);
     return 1;
 }
 
-int launch_rectify_xsobel_pair(const uint8_t* srcL, const uint8_t* srcR, int sW, int sH, const int2* mapL, const int2* mapR,
-                               const CamModel& cmL, const CamModel& cmR, uint8_t* rectL, uint8_t* rectR, uint8_t* preL,
-                               uint8_t* preR, size_t pre_pitch, int W, int H, int cap, cudaStream_t st)
+int launch_rectify_xsobel_pair(const uint8_t* srcL, const uint8_t* srcR, int sW, int sH, MapMode mode, const void* mapL,
+                               const void* mapR, const CamModel& cmL, const CamModel& cmR, uint8_t* rectL, uint8_t* rectR,
+                               uint8_t* preL, uint8_t* preR, size_t pre_pitch, int W, int H, int cap, cudaStream_t st,
+                               int nf, size_t src_stride, size_t rect_stride, size_t pre_stride)
 {
-    dim3 g((W + FTX - 1) / FTX, (H + FTY - 1) / FTY, 2);
+    dim3 g((W + FTX - 1) / FTX, (H + FTY - 1) / FTY, 2 * nf);
     RectSide l{srcL, mapL, rectL, preL, cmL}, r{srcR, mapR, rectR, preR, cmR};
-    if (mapL && mapR) rectify_xsobel_kernel<false><<<g, 256, 0, st>>>(l, r, sW, sH, pre_pitch, W, H, cap);
-    else rectify_xsobel_kernel<true><<<g, 256, 0, st>>>(l, r, sW, sH, pre_pitch, W, H, cap);
+    BatchStrides bs{src_stride, rect_stride, pre_stride};
+    switch (mode) {
+    case MAP_NONE: rectify_xsobel_kernel<MAP_NONE><<<g, 256, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
+    case MAP_ABS32: rectify_xsobel_kernel<MAP_ABS32><<<g, 256, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
+    case MAP_DELTA16: rectify_xsobel_kernel<MAP_DELTA16><<<g, 256, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
+    default: rectify_xsobel_kernel<MAP_FLY><<<g, 256, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
+    }
     return 1;
 }
 

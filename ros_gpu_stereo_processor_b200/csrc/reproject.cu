@@ -18,37 +18,46 @@ __device__ __forceinline__ float disp_to_float(int d16, double cxd)
 
 __global__ void __launch_bounds__(256) set_int_kernel(int* p, int v) { *p = v; }
 
-// 8 disparities per thread (one 16-byte load), block-level min, one atomic per block
+struct FrameDst {          // per-frame destinations of a batch: strided planes, or one caller-owned (mapped pinned) buffer per frame
+    size_t stride;
+    int use_list;
+    PtrList list;
+};
+
+// 8 disparities per thread as two groups of 4, 128 floats apart inside the warp's 256-element chunk: every store
+// instruction of a warp writes 512 contiguous bytes (full lines for HBM and for posted PCIe writes into pinned host
+// memory alike); block-level min, one atomic per block; blockIdx.y = frame of the batch
 __global__ void __launch_bounds__(256) disparity_to_float_kernel(const int16_t* __restrict__ d16, float* __restrict__ df,
-                                                                 int n, double cxd, int* __restrict__ min_d16)
+                                                                 int n, double cxd, int* __restrict__ min_d16, size_t d_stride,
+                                                                 const FrameDst fd)
 {
     __shared__ int wmin[8];
-    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    d16 = (const int16_t*)((const uint8_t*)d16 + blockIdx.y * d_stride);
+    if (fd.use_list) df = (float*)fd.list.p[blockIdx.y];
+    else if (df) df = (float*)((uint8_t*)df + blockIdx.y * fd.stride);
+    min_d16 += blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int base = blockIdx.x * 2048 + warp * 256;
     int v = INT_MAX;
-    if (i0 + 8 <= n) {
-        const uint4 q = *(const uint4*)(d16 + i0);
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-        float f[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int a = (int)(int16_t)(w[k] & 0xffffu), b = (int)(int16_t)(w[k] >> 16);
-            v = min(v, min(a, b));
-            f[2 * k] = disp_to_float(a, cxd);
-            f[2 * k + 1] = disp_to_float(b, cxd);
-        }
-        if (df) {
-            *(float4*)(df + i0) = make_float4(f[0], f[1], f[2], f[3]);
-            *(float4*)(df + i0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
-        }
-    } else {
-        for (int i = i0; i < n; ++i) {
-            const int a = d16[i];
-            v = min(v, a);
-            if (df) df[i] = disp_to_float(a, cxd);
+    for (int g = 0; g < 2; ++g) {
+        const int i0 = base + g * 128 + 4 * lane;
+        if (i0 + 4 <= n) {
+            const uint2 q = *(const uint2*)(d16 + i0);
+            const int a = (int)(int16_t)(q.x & 0xffffu), b = (int)(int16_t)(q.x >> 16);
+            const int c = (int)(int16_t)(q.y & 0xffffu), d = (int)(int16_t)(q.y >> 16);
+            v = min(v, min(min(a, b), min(c, d)));
+            if (df) *(float4*)(df + i0) = make_float4(disp_to_float(a, cxd), disp_to_float(b, cxd), disp_to_float(c, cxd), disp_to_float(d, cxd));
+        } else {
+            for (int i = i0; i < n; ++i) {
+                const int a = d16[i];
+                v = min(v, a);
+                if (df) df[i] = disp_to_float(a, cxd);
+            }
         }
     }
     v = __reduce_min_sync(0xffffffffu, v);
-    if ((threadIdx.x & 31) == 0) wmin[threadIdx.x >> 5] = v;
+    if (lane == 0) wmin[warp] = v;
     __syncthreads();
     if (threadIdx.x < 8) {
         v = wmin[threadIdx.x];
@@ -60,53 +69,75 @@ __global__ void __launch_bounds__(256) disparity_to_float_kernel(const int16_t* 
 __global__ void __launch_bounds__(256) reproject_pack_kernel(const int16_t* __restrict__ d16, int W, int H, double cxd,
                                                              const double* __restrict__ Q, const int* __restrict__ min_d16,
                                                              const uint8_t* __restrict__ color, int ch,
-                                                             float* __restrict__ xyz, uint8_t* __restrict__ pc2, unsigned qmask)
+                                                             float* __restrict__ xyz, uint8_t* __restrict__ pc2, unsigned qmask,
+                                                             size_t d_stride, size_t color_stride, size_t xyz_stride, const FrameDst fd)
 {
-    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= W || y >= H) return;
-    size_t i = (size_t)y * W + x;
-    const int dv = d16[i], dmin = *min_d16;
-    if (!xyz && dv == dmin) {
-        // missing value (d == min over the image): cv::reprojectImageTo3D sets Z = 10000, which isValidPoint rejects,
-        // so the record is NaN xyz + colour whatever X and Y were; no arithmetic needed
-        uint32_t bgr;
-        if (ch == 3) bgr = (uint32_t)color[i * 3] | ((uint32_t)color[i * 3 + 1] << 8) | ((uint32_t)color[i * 3 + 2] << 16);
-        else { uint32_t g = color ? color[i] : 0; bgr = g | (g << 8) | (g << 16); }
-        uint4* o = (uint4*)(pc2 + i * 32);
-        o[0] = make_uint4(0x7fc00000u, 0x7fc00000u, 0x7fc00000u, 0u);
-        o[1] = make_uint4(bgr, 0u, 0u, 0u);
-        return;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    {
+        const int f = blockIdx.z;          // frame of the batch
+        d16 = (const int16_t*)((const uint8_t*)d16 + f * d_stride);
+        if (color) color += f * color_stride;
+        if (xyz) xyz = (float*)((uint8_t*)xyz + f * xyz_stride);
+        if (fd.use_list) pc2 = (uint8_t*)fd.list.p[f];
+        else if (pc2) pc2 += f * fd.stride;
+        min_d16 += f;
     }
-    const float dfl = disp_to_float(dv, cxd);
-    const double d = (double)dfl;
-    const double minDisp = (double)disp_to_float(dmin, cxd);
-    double h[4];
+    // One PointCloud2 record = 32 bytes = two 16-byte halves, [x y z 0] and [bgr 0 0 0].  The 32 records of a warp are
+    // 1 KiB contiguous; lanes exchange halves so that each of the two store instructions of the warp writes 512
+    // contiguous bytes (lane l: half (l & 1) of record (l >> 1) + 16 * instruction) -- full lines for HBM and for
+    // posted PCIe writes when pc2 is pinned host memory.  Rows are padded to whole warps by the launcher (W % 32 == 0)
+    // or fall back to per-thread stores.
+    uint32_t ux = 0x7fc00000u, uy = 0x7fc00000u, uz = 0x7fc00000u;
+    float p[3] = {0.f, 0.f, 0.f};
+    const bool inside = x < W && y < H;
+    const size_t i = inside ? (size_t)y * W + x : 0;
+    const int dv = inside ? (int)d16[i] : 0, dmin = *min_d16;
+    // missing value (d == min over the image): cv::reprojectImageTo3D sets Z = 10000, which isValidPoint rejects, so the
+    // record is NaN xyz + colour whatever X and Y were; no arithmetic needed unless the xyz plane is wanted too
+    if (inside && (xyz || dv != dmin)) {
+        const float dfl = disp_to_float(dv, cxd);
+        const double d = (double)dfl;
+        const double minDisp = (double)disp_to_float(dmin, cxd);
+        double h[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        // entries of Q that are exactly zero are skipped (qmask bit = entry is non-zero): 0 * v = +-0 and s + (+-0) = s,
-        // so the sum is bit-identical to the full 4-term product of cv::reprojectImageTo3D (finite v)
-        double s = (qmask >> (r * 4 + 0)) & 1u ? __dmul_rn(__ldg(Q + r * 4 + 0), (double)x) : 0.0;
-        if ((qmask >> (r * 4 + 1)) & 1u) s = __dadd_rn(s, __dmul_rn(__ldg(Q + r * 4 + 1), (double)y));
-        if ((qmask >> (r * 4 + 2)) & 1u) s = __dadd_rn(s, __dmul_rn(__ldg(Q + r * 4 + 2), d));
-        if ((qmask >> (r * 4 + 3)) & 1u) s = __dadd_rn(s, __ldg(Q + r * 4 + 3));
-        h[r] = s;
-    }
-    float p[3];
+        for (int r = 0; r < 4; ++r) {
+            // entries of Q that are exactly zero are skipped (qmask bit = entry is non-zero): 0 * v = +-0 and s + (+-0) = s,
+            // so the sum is bit-identical to the full 4-term product of cv::reprojectImageTo3D (finite v)
+            double s = (qmask >> (r * 4 + 0)) & 1u ? __dmul_rn(__ldg(Q + r * 4 + 0), (double)x) : 0.0;
+            if ((qmask >> (r * 4 + 1)) & 1u) s = __dadd_rn(s, __dmul_rn(__ldg(Q + r * 4 + 1), (double)y));
+            if ((qmask >> (r * 4 + 2)) & 1u) s = __dadd_rn(s, __dmul_rn(__ldg(Q + r * 4 + 2), d));
+            if ((qmask >> (r * 4 + 3)) & 1u) s = __dadd_rn(s, __ldg(Q + r * 4 + 3));
+            h[r] = s;
+        }
 #pragma unroll
-    for (int r = 0; r < 3; ++r) p[r] = __double2float_rn(__ddiv_rn((double)__double2float_rn(h[r]), h[3]));
-    if (fabs(__dadd_rn(d, -minDisp)) <= (double)1.1920928955078125e-07f) p[2] = 10000.0f;
-    if (xyz) {
-        xyz[i * 3] = p[0]; xyz[i * 3 + 1] = p[1]; xyz[i * 3 + 2] = p[2];
-    }
-    if (pc2) {
+        for (int r = 0; r < 3; ++r) p[r] = __double2float_rn(__ddiv_rn((double)__double2float_rn(h[r]), h[3]));
+        if (fabs(__dadd_rn(d, -minDisp)) <= (double)1.1920928955078125e-07f) p[2] = 10000.0f;
+        if (xyz) {
+            xyz[i * 3] = p[0]; xyz[i * 3 + 1] = p[1]; xyz[i * 3 + 2] = p[2];
+        }
         // isValidPoint (src/GpuSenderPc2.cpp:84-89): z != MISSING_Z and not inf; invalid -> quiet NaN
-        bool valid = (p[2] != 10000.0f) && !isinf(p[2]);
-        uint32_t ux = valid ? __float_as_uint(p[0]) : 0x7fc00000u;
-        uint32_t uy = valid ? __float_as_uint(p[1]) : 0x7fc00000u;
-        uint32_t uz = valid ? __float_as_uint(p[2]) : 0x7fc00000u;
-        uint32_t bgr;
+        if ((p[2] != 10000.0f) && !isinf(p[2])) {
+            ux = __float_as_uint(p[0]); uy = __float_as_uint(p[1]); uz = __float_as_uint(p[2]);
+        }
+    }
+    if (!pc2) return;
+    uint32_t bgr = 0;
+    if (inside) {
         if (ch == 3) bgr = (uint32_t)color[i * 3] | ((uint32_t)color[i * 3 + 1] << 8) | ((uint32_t)color[i * 3 + 2] << 16);
         else { uint32_t g = color ? color[i] : 0; bgr = g | (g << 8) | (g << 16); }
+    }
+    const int lane = threadIdx.x & 31;
+    const int x0 = blockIdx.x * 32;
+    if (x0 + 32 <= W && y < H) {
+        uint4* row = (uint4*)(pc2 + ((size_t)y * W + x0) * 32);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int src = (lane >> 1) + 16 * k;
+            const uint32_t sx = __shfl_sync(0xffffffffu, ux, src), sy = __shfl_sync(0xffffffffu, uy, src);
+            const uint32_t sz = __shfl_sync(0xffffffffu, uz, src), sc = __shfl_sync(0xffffffffu, bgr, src);
+            row[32 * k + lane] = (lane & 1) ? make_uint4(sc, 0u, 0u, 0u) : make_uint4(sx, sy, sz, 0u);
+        }
+    } else if (inside) {
         uint4* o = (uint4*)(pc2 + i * 32);
         o[0] = make_uint4(ux, uy, uz, 0u);
         o[1] = make_uint4(bgr, 0u, 0u, 0u);
@@ -142,18 +173,32 @@ __global__ void __launch_bounds__(256) disparity_color_kernel(const int16_t* __r
     ((uint32_t*)bgra)[i] = bb | (gg << 8) | (rr << 16) | (255u << 24);
 }
 
-int launch_disparity_to_float(const int16_t* d16, float* df, int n, double cxd, int* min_d16, cudaStream_t st)
+static FrameDst frame_dst(size_t stride, const PtrList* list)
 {
-    cudaMemsetAsync(min_d16, 0x7f, sizeof(int), st);     // 0x7f7f7f7f: larger than any int16
-    disparity_to_float_kernel<<<(n + 2047) / 2048, 256, 0, st>>>(d16, df, n, cxd, min_d16);
+    FrameDst fd;
+    fd.stride = stride;
+    fd.use_list = list ? 1 : 0;
+    if (list) fd.list = *list;
+    else for (int i = 0; i < MAX_BATCH; ++i) fd.list.p[i] = nullptr;
+    return fd;
+}
+
+int launch_disparity_to_float(const int16_t* d16, float* df, int n, double cxd, int* min_d16, cudaStream_t st, int nf,
+                              size_t d_stride, size_t df_stride, const PtrList* df_list)
+{
+    cudaMemsetAsync(min_d16, 0x7f, nf * sizeof(int), st);     // 0x7f7f7f7f: larger than any int16
+    disparity_to_float_kernel<<<dim3((n + 2047) / 2048, nf), 256, 0, st>>>(d16, df, n, cxd, min_d16, d_stride, frame_dst(df_stride, df_list));
     return 1;
 }
 
 int launch_reproject_pack(const int16_t* d16, int W, int H, double cxd, const double* Q, unsigned qmask, const int* min_d16,
-                          const uint8_t* color, int ch, float* xyz, uint8_t* pc2, cudaStream_t st)
+                          const uint8_t* color, int ch, float* xyz, uint8_t* pc2, cudaStream_t st, int nf, size_t d_stride,
+                          size_t color_stride, size_t xyz_stride, size_t pc2_stride, const PtrList* pc2_list)
 {
-    dim3 g((W + 31) / 32, (H + 7) / 8);
-    reproject_pack_kernel<<<g, 256, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask);
+    dim3 g((W + 31) / 32, (H + 7) / 8, nf);
+    if (pc2_list && !pc2) pc2 = (uint8_t*)pc2_list->p[0];     // the kernel tests pc2 for "records wanted"
+    reproject_pack_kernel<<<g, 256, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask, d_stride, color_stride,
+                                             xyz_stride, frame_dst(pc2_stride, pc2_list));
     return 1;
 }
 

@@ -36,6 +36,12 @@ def _type_of(a):
     raise capi.B200StereoError(capi.EUNSUPPORTED, "unsupported array dtype/channels %s x%d" % (a.dtype, ch))
 
 
+def _fixed_point_plane_of(mat_source):
+    """POINTS2 / DISPARITY_32F ids name the side whose CV_16SC1 plane the reprojection and pack kernels read."""
+    m = int(mat_source)
+    return (SRC_DISPARITY | (m & 3)) if (m & (SRC_POINTS2 | SRC_DISPARITY_32F)) else m
+
+
 def _caminfo(d):
     ci = capi.CamInfo()
     ci.width, ci.height = int(d["width"]), int(d["height"])
@@ -50,13 +56,29 @@ def _caminfo(d):
 
 
 class Sender(object):
-    """Stand-in for GPUSenderImage/Disparity/Pc2 (src/GpuSender*.cpp): holds the packed message payload."""
+    """Stand-in for GPUSenderImage/Disparity/Pc2 (src/GpuSender*.cpp): holds the packed message payload.  Like the
+    reference's senders (src/GpuSenderIfc.cpp:13-26) an asynchronous one is completed -- and its publisher called -- from
+    the CUDA stream callback once the payload has arrived in host memory."""
 
-    def __init__(self, kind, message):
-        self.kind, self.message, self._sent = kind, message, True
+    def __init__(self, kind, message, pub=None, sent=True):
+        self.kind, self.message, self._pub, self._sent = kind, message, pub, sent
+        self._pinned = None      # (ptr, free function) of a pinned payload buffer owned by this sender
+        self._cb = None          # keeps the ctypes callback alive until it has run
+
+    def _complete(self, _user=None, _status=0):
+        if self._pub is not None:
+            self._pub(self.message)
+        self._sent = True
 
     def wasDataSent(self):
         return self._sent
+
+    def release(self):
+        if self._pinned is not None:
+            ptr, free = self._pinned
+            self._pinned = None
+            self.message = None
+            free(ptr)
 
 
 class GpuStereoProcessor(object):
@@ -70,6 +92,7 @@ class GpuStereoProcessor(object):
         self._ck(self._lib.b200s_get_params(self._h, C.byref(self._p)))
         self._senders = []
         self._slots = 0
+        self._slot_shape = None
         self._keep = []
 
     # ---- plumbing -------------------------------------------------------------------------------------
@@ -197,6 +220,7 @@ class GpuStereoProcessor(object):
         self._ck(self._lib.b200s_compute_disparity_image(self._h, int(disparity_src), int(disp_image_dest)))
 
     def projectDisparityTo3DPoints(self, disparity_src, points_src):
+        """disparity_src: DISPARITY or, as the reference calls it (test/UTest.cpp:378), DISPARITY_32F of a side."""
         self._ck(self._lib.b200s_project_to_3d(self._h, int(disparity_src), int(points_src)))
 
     def filterSpeckles(self, disparity):
@@ -227,55 +251,88 @@ class GpuStereoProcessor(object):
         self._keep.clear()
 
     def cleanSenders(self):
-        self._senders = []
+        """src/GPUStereoProcessor.cpp:228-234: drops the senders whose data went out (call after waitForAllStreams)."""
+        keep = []
+        for s in self._senders:
+            if s.wasDataSent():
+                s.release()
+            else:
+                keep.append(s)
+        self._senders = keep
 
     # ---- senders (src/GPUStereoProcessor.cpp:210-234, src/GpuSender*.cpp) -----------------------------
-    def enqueueSendImage(self, source, imagePattern=None, encoding="", pub=None):
+    # asynchronous=True is the reference's behaviour: the call only enqueues work on the side's stream; the payload
+    # lands in a pinned buffer owned by the sender and `pub(message)` is called from the stream callback
+    # (src/GpuSenderIfc.cpp:13-26).  The default returns with the message complete, which the tests read directly.
+    def _payload(self, nbytes, asynchronous):
+        if not asynchronous:
+            return np.empty(nbytes, np.uint8), None
+        arr, ptr = self.hostAlloc(nbytes)
+        return arr, (ptr, self.hostFree)
+
+    def _finish_sender(self, snd, pinned, asynchronous, call):
+        """call(done_fn) -> return code of the *_async entry point"""
+        self._senders.append(snd)
+        if not asynchronous:
+            self._ck(call(capi.DONE_FN(0)))
+            snd._complete()
+            return snd
+        snd._pinned = pinned
+        snd._sent = False
+        snd._cb = capi.DONE_FN(snd._complete)
+        self._ck(call(snd._cb))
+        return snd
+
+    def enqueueSendImage(self, source, imagePattern=None, encoding="", pub=None, asynchronous=False):
         rows, cols, t = self.matInfo(source)
         dt, ch = _NP_OF_TYPE[t]
-        data = np.empty(rows * cols * ch * np.dtype(dt).itemsize, np.uint8)
+        data, pinned = self._payload(rows * cols * ch * np.dtype(dt).itemsize, asynchronous)
         r, c, s = C.c_int(), C.c_int(), C.c_int()
-        self._ck(self._lib.b200s_pack_image(self._h, int(source), data.ctypes.data, data.size, C.byref(r), C.byref(c), C.byref(s)))
-        msg = dict(header=imagePattern, height=r.value, width=c.value, step=s.value, encoding=encoding, data=data)
-        snd = Sender("image", msg)
-        self._senders.append(snd)
-        if pub is not None:
-            pub(msg)
-        return snd
+        msg = dict(header=imagePattern, height=rows, width=cols, step=cols * ch * np.dtype(dt).itemsize, encoding=encoding, data=data)
+        snd = Sender("image", msg, pub)
+        return self._finish_sender(snd, pinned, asynchronous, lambda cb: self._lib.b200s_pack_image_async(
+            self._h, int(source), data.ctypes.data, data.size, C.byref(r), C.byref(c), C.byref(s), cb, None))
 
-    def enqueueSendDisparity(self, source, imagePattern=None, pub=None):
-        rows, cols, _ = self.matInfo(source)
-        data = np.empty((rows, cols), np.float32)
+    def enqueueSendDisparity(self, source, imagePattern=None, pub=None, asynchronous=False):
+        rows, cols, _ = self.matInfo(_fixed_point_plane_of(source))
+        raw, pinned = self._payload(rows * cols * 4, asynchronous)
+        data = raw.view(np.float32).reshape(rows, cols)
         meta = capi.DisparityMeta()
         self._sync_params()
-        self._ck(self._lib.b200s_pack_disparity(self._h, int(source), data.ctypes.data, data.nbytes, C.byref(meta)))
-        msg = dict(header=imagePattern, image=dict(height=meta.height, width=meta.width, step=meta.step, encoding="32FC1", data=data),
-                   f=meta.f, T=meta.T, min_disparity=meta.min_disparity, max_disparity=meta.max_disparity, delta_d=meta.delta_d,
-                   valid_window=dict(x_offset=meta.valid_x_offset, y_offset=meta.valid_y_offset, width=meta.valid_width,
-                                     height=meta.valid_height))
-        snd = Sender("disparity", msg)
-        self._senders.append(snd)
-        if pub is not None:
-            pub(msg)
-        return snd
+        msg = dict(header=imagePattern, image=dict(height=rows, width=cols, step=cols * 4, encoding="32FC1", data=data))
+        snd = Sender("disparity", msg, pub)
 
-    def enqueueSendPoints(self, points_source, color_source, imagePattern=None, pub=None):
-        """points_source names the DISPARITY buffer the cloud is made from (the reference passes its POINTS2
-        buffer; here reprojection and packing are one kernel, so the disparity plane is the input)."""
-        disp_id = (SRC_DISPARITY | (int(points_source) & 3)) if (int(points_source) & SRC_POINTS2) else int(points_source)
-        rows, cols, _ = self.matInfo(disp_id)
-        data = np.empty((rows, cols, 32), np.uint8)
+        def call(cb):
+            rc = self._lib.b200s_pack_disparity_async(self._h, int(source), data.ctypes.data, data.nbytes, C.byref(meta), cb, None)
+            msg.update(f=meta.f, T=meta.T, min_disparity=meta.min_disparity, max_disparity=meta.max_disparity, delta_d=meta.delta_d,
+                       valid_window=dict(x_offset=meta.valid_x_offset, y_offset=meta.valid_y_offset, width=meta.valid_width,
+                                         height=meta.valid_height))
+            return rc
+        return self._finish_sender(snd, pinned, asynchronous, call)
+
+    def enqueueSendPoints(self, points_source, color_source, imagePattern=None, pub=None, asynchronous=False):
+        """points_source: the reference passes its POINTS2 buffer (src/StereoProcessor.cpp:281); reprojection and packing
+        are one kernel here, so that id -- or the DISPARITY id -- names the side whose fixed-point plane is read."""
+        rows, cols, _ = self.matInfo(_fixed_point_plane_of(points_source))
+        raw, pinned = self._payload(rows * cols * 32, asynchronous)
+        data = raw.reshape(rows, cols, 32)
         meta = capi.Pc2Meta()
-        self._ck(self._lib.b200s_pack_pointcloud2(self._h, disp_id, int(color_source), data.ctypes.data, data.nbytes, C.byref(meta)))
-        fields = [dict(name="x", offset=meta.off_x, datatype=7, count=1), dict(name="y", offset=meta.off_y, datatype=7, count=1),
-                  dict(name="z", offset=meta.off_z, datatype=7, count=1), dict(name="rgb", offset=meta.off_rgb, datatype=7, count=1)]
-        msg = dict(header=imagePattern, height=meta.height, width=meta.width, fields=fields, is_bigendian=bool(meta.is_bigendian),
-                   point_step=meta.point_step, row_step=meta.row_step, is_dense=bool(meta.is_dense), data=data)
-        snd = Sender("points2", msg)
-        self._senders.append(snd)
-        if pub is not None:
-            pub(msg)
-        return snd
+        msg = dict(header=imagePattern, height=rows, width=cols, data=data)
+        snd = Sender("points2", msg, pub)
+
+        def call(cb):
+            rc = self._lib.b200s_pack_pointcloud2_async(self._h, int(points_source), int(color_source), data.ctypes.data, data.nbytes,
+                                                        C.byref(meta), cb, None)
+            fields = [dict(name="x", offset=meta.off_x, datatype=7, count=1), dict(name="y", offset=meta.off_y, datatype=7, count=1),
+                      dict(name="z", offset=meta.off_z, datatype=7, count=1), dict(name="rgb", offset=meta.off_rgb, datatype=7, count=1)]
+            msg.update(fields=fields, is_bigendian=bool(meta.is_bigendian), point_step=meta.point_step, row_step=meta.row_step,
+                       is_dense=bool(meta.is_dense))
+            return rc
+        return self._finish_sender(snd, pinned, asynchronous, call)
+
+    def convertColor(self, mat_source, mat_dst, src_encoding, dst_encoding):
+        """src/GPUStereoProcessor.cpp:119-172 for the encodings on the hot path (mono8, bgr8, rgb8)."""
+        self._ck(self._lib.b200s_convert_color(self._h, int(mat_source), int(mat_dst), src_encoding.encode(), dst_encoding.encode()))
 
     # ---- parameters (src/GPUStereoProcessor.cpp:202-208,389-419 + the cv::StereoBM ones GPU.cfg lacks) ---
     def setPreFilterType(self, filter_type): self._p.pre_filter_type = int(filter_type)
@@ -307,18 +364,72 @@ class GpuStereoProcessor(object):
     def getParams(self):
         return {n: getattr(self._p, n) for n, _ in self._p._fields_}
 
+    def matStats(self, mat_source):
+        """Per-channel (min, max, mean) of a named buffer, reduced on the GPU."""
+        mn, mx, mean, ch = (C.c_double * 4)(), (C.c_double * 4)(), (C.c_double * 4)(), C.c_int()
+        self._ck(self._lib.b200s_mat_stats(self._h, int(mat_source), mn, mx, mean, C.byref(ch)))
+        return [(mn[i], mx[i], mean[i]) for i in range(ch.value)]
+
     def printStats(self, name, mat):
-        m = np.asarray(mat)
-        print("%s: min %s max %s mean %s" % (name, m.min(), m.max(), m.mean()))
+        """src/GPUStereoProcessor.cpp:421-435; mat is a GpuMatSource id (reduced on the GPU) or a host array (uploaded first)."""
+        if not isinstance(mat, (int, np.integer)):
+            self.uploadMat(SRC_DISPARITY_IMG | SIDE_R, np.asarray(mat))
+            mat = SRC_DISPARITY_IMG | SIDE_R
+        lines = ["ARRAY STATS:%s; channel:%d; min:%f; max:%f; mean:%f;" % (name, i, a, b, m) for i, (a, b, m) in enumerate(self.matStats(mat))]
+        print("\n".join(lines))
+        return lines
 
     # ---- fused frame path (StereoProcessor::imageCb chain, src/StereoProcessor.cpp:157-298) -----------
-    def configureSlots(self, n_slots, rows, cols):
-        self._ck(self._lib.b200s_configure_slots(self._h, int(n_slots), int(rows), int(cols)))
+    def configureSlots(self, n_slots, rows, cols, frames_per_slot=1):
+        self._ck(self._lib.b200s_configure_slots_batched(self._h, int(n_slots), int(rows), int(cols), int(frames_per_slot)))
         self._slots = n_slots
+        self._slot_shape = (int(rows), int(cols))
 
     def processPairAsync(self, slot, left, right, io):
         self._sync_params()
         self._ck(self._lib.b200s_process_pair_async(self._h, int(slot), left, right, C.byref(io)))
+
+    def processBatchAsync(self, slot, lefts, rights, ios):
+        """One batch of frames on a slot (b200s_process_batch_async): lefts / rights are sequences of host or device
+        addresses, ios a ctypes array (FrameIO * n) or a sequence of FrameIO."""
+        n = len(lefts)
+        la = (C.c_void_p * n)(*[int(p) if p else None for p in lefts])
+        ra = (C.c_void_p * n)(*[int(p) for p in rights])
+        if not isinstance(ios, C.Array):
+            ios = (capi.FrameIO * n)(*ios)
+        self._sync_params()
+        self._ck(self._lib.b200s_process_batch_async(self._h, int(slot), n, la, ra, ios))
+
+    def makeBatch(self, lefts, rights, ios):
+        """Pre-built argument arrays of a batch for processBatchRaw (keeps the per-call host work minimal)."""
+        n = len(rights)
+        la = (C.c_void_p * n)(*[int(p) if p else None for p in lefts])
+        ra = (C.c_void_p * n)(*[int(p) for p in rights])
+        if not isinstance(ios, C.Array):
+            ios = (capi.FrameIO * n)(*ios)
+        return n, la, ra, ios
+
+    def processBatchRaw(self, slot, batch):
+        n, la, ra, ios = batch
+        rc = self._lib.b200s_process_batch_async(self._h, slot, n, la, ra, ios)
+        if rc != 0:
+            self._ck(rc)
+
+    def syncParams(self):
+        self._sync_params()
+
+    def setPackMode(self, direct):
+        self._ck(self._lib.b200s_set_pack_mode(self._h, int(bool(direct))))
+
+    def lastStageTimes(self, slot):
+        ms = (C.c_float * len(capi.STAGE_NAMES))()
+        self._ck(self._lib.b200s_last_stage_times(self._h, int(slot), ms))
+        return dict(zip(capi.STAGE_NAMES, [float(v) for v in ms]))
+
+    def slotFrameDevicePtr(self, slot, frame, which):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self._lib.b200s_slot_frame_device_ptr(self._h, int(slot), int(frame), int(which), C.byref(p), C.byref(n)))
+        return p.value, n.value
 
     def waitSlot(self, slot):
         self._ck(self._lib.b200s_wait_slot(self._h, int(slot)))
@@ -329,25 +440,35 @@ class GpuStereoProcessor(object):
         self._ck(self._lib.b200s_poll_slot(self._h, int(slot), C.byref(d)))
         return bool(d.value)
 
-    def processPair(self, left, right, rectify=True, want=("disparity16",)):
-        """Synchronous convenience on slot 0 with host arrays; returns a dict of numpy outputs."""
-        L = np.ascontiguousarray(left, np.uint8)
+    def processPair(self, left, right, rectify=True, want=("disparity16",), color=None, color_encoding="bgr8"):
+        """Synchronous convenience on slot 0 with host arrays; returns a dict of numpy outputs.  color: optional raw
+        left colour image (H, W, 3) that colours the point cloud; left=None derives the grey image from it."""
         R = np.ascontiguousarray(right, np.uint8)
-        rows, cols = L.shape
-        if self._slots == 0:
-            self.configureSlots(1, rows, cols)
+        L = None if left is None else np.ascontiguousarray(left, np.uint8)
+        Cimg = None if color is None else np.ascontiguousarray(color, np.uint8)
+        rows, cols = R.shape
+        for a in (L, Cimg):
+            if a is not None and a.shape[:2] != (rows, cols):
+                raise capi.B200StereoError(capi.EINVAL, "left / right / colour images differ in size")
+        if self._slots == 0 or self._slot_shape != (rows, cols):
+            self.configureSlots(max(self._slots, 1), rows, cols)     # the slots follow the image size
         io = capi.FrameIO()
         io.rectify = int(bool(rectify))
+        io.rows, io.cols = rows, cols
+        if Cimg is not None:
+            io.color_left = Cimg.ctypes.data
+            io.color_encoding = capi.COLOR_RGB8 if color_encoding == "rgb8" else capi.COLOR_BGR8
         out = {}
         spec = dict(rect_left=(capi.OUT_RECT_L, (rows, cols), np.uint8), rect_right=(capi.OUT_RECT_R, (rows, cols), np.uint8),
                     disparity16=(capi.OUT_DISPARITY16, (rows, cols), np.int16), disparity32f=(capi.OUT_DISPARITY32F, (rows, cols), np.float32),
-                    pointcloud2=(capi.OUT_POINTCLOUD2, (rows, cols, 32), np.uint8), points_xyz=(capi.OUT_POINTS_XYZ, (rows, cols, 3), np.float32))
+                    pointcloud2=(capi.OUT_POINTCLOUD2, (rows, cols, 32), np.uint8), points_xyz=(capi.OUT_POINTS_XYZ, (rows, cols, 3), np.float32),
+                    rect_color_left=(capi.OUT_RECT_COLOR_L, (rows, cols, 3), np.uint8))
         for name in want:
             bit, shape, dt = spec[name]
             io.want |= bit
             out[name] = np.empty(shape, dt)
             setattr(io, name, out[name].ctypes.data)
-        self.processPairAsync(0, L.ctypes.data, R.ctypes.data, io)
+        self.processPairAsync(0, None if L is None else L.ctypes.data, R.ctypes.data, io)
         self.waitSlot(0)
         return out
 

@@ -4,6 +4,7 @@
 //   in.bin  = left raw (W*H u8) followed by right raw;  out.bin = rectL, rectR (u8), disparity (s16), pointcloud2 (32 B/px)
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "b200_gpuimageproc/GpuStereoProcessor.hpp"
@@ -37,20 +38,32 @@ int main(int argc, char **argv)
         proc.rectifyImage(GPU_MAT_SRC_R_MONO, GPU_MAT_SRC_R_RECT_MONO);
         proc.computeDisparity(GPU_MAT_SRC_L_RECT_MONO, GPU_MAT_SRC_R_RECT_MONO, GPU_MAT_SRC_L_DISPARITY);
         proc.filterSpeckles(GPU_MAT_SRC_L_DISPARITY);
-        proc.projectDisparityTo3DPoints(GPU_MAT_SRC_L_DISPARITY, GPU_MAT_SRC_L_POINTS2);
-        PointCloud2Payload pc = proc.enqueueSendPoints(GPU_MAT_SRC_L_DISPARITY, GPU_MAT_SRC_L_RECT_MONO);
-        proc.waitForAllStreams();
+        // the reference's exact ids (test/UTest.cpp:378-382, src/StereoProcessor.cpp:272-281): DISPARITY_32F into
+        // projectDisparityTo3DPoints, POINTS2 into enqueueSendPoints
+        proc.projectDisparityTo3DPoints(GPU_MAT_SRC_L_DISPARITY_32F, GPU_MAT_SRC_L_POINTS2);
+        int published = 0;
+        GPUSenderPc2Ptr snd = proc.enqueueSendPoints(GPU_MAT_SRC_L_POINTS2, GPU_MAT_SRC_L_RECT_MONO,
+                                                     [&published](const PointCloud2Payload &m) { published += m.meta.point_step; });
+        GPUSenderDisparityPtr dsnd = proc.enqueueSendDisparity(GPU_MAT_SRC_L_DISPARITY);
+        GPUSenderImagePtr isnd = proc.enqueueSendImage(GPU_MAT_SRC_L_RECT_MONO, "mono8");
+        proc.waitForAllStreams();      // the senders complete from stream callbacks (src/GpuSenderIfc.cpp:13-26)
+        if (!snd->wasDataSent() || !dsnd->wasDataSent() || !isnd->wasDataSent() || published != 32) return 7;
+        const PointCloud2Payload &pc = snd->payload;
         Mat rl, rr, d;
         proc.downloadMat(GPU_MAT_SRC_L_RECT_MONO, rl);
         proc.downloadMat(GPU_MAT_SRC_R_RECT_MONO, rr);
         proc.downloadMat(GPU_MAT_SRC_L_DISPARITY, d);
         if (pc.meta.point_step != 32 || pc.meta.width != W || d.type != B200S_16SC1) return 6;
+        if (std::memcmp(isnd->payload.data, rl.data.data(), rl.data.size()) != 0 || dsnd->payload.meta.width != W) return 8;
+        proc.convertColor(GPU_MAT_SRC_L_RECT_MONO, GPU_MAT_SRC_L_RECT_COLOR, "mono8", "bgr8");
+        proc.printStats("Disparity", GPU_MAT_SRC_L_DISPARITY);
         FILE *o = std::fopen(argv[4], "wb");
         std::fwrite(rl.data.data(), 1, rl.data.size(), o);
         std::fwrite(rr.data.data(), 1, rr.data.size(), o);
         std::fwrite(d.data.data(), 1, d.data.size(), o);
-        std::fwrite(pc.data.data(), 1, pc.data.size(), o);
+        std::fwrite(pc.data, 1, pc.size, o);
         std::fclose(o);
+        proc.cleanSenders();
         std::printf("facade ok\n");
         return 0;
     } catch (const Error &e) {

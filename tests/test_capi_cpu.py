@@ -33,7 +33,7 @@ def test_struct_layouts_match_header(capi):
     assert C.sizeof(capi.Params) == 12 * 4
     assert C.sizeof(capi.CamInfo) == 8 + 9 * 8 + 8 * 8 + 8 + 9 * 8 + 12 * 8
     assert C.sizeof(capi.Pc2Meta) == 40 and C.sizeof(capi.DisparityMeta) == 48
-    assert C.sizeof(capi.FrameIO) == 16 + 6 * 8
+    assert C.sizeof(capi.FrameIO) == 16 + 6 * 8 + 8 + 4 * 4 + 8    # + color_left, color_encoding/rows/cols (+ pad), rect_color_left
 
 
 def test_default_params_are_cv_stereobm_defaults(capi):

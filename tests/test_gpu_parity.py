@@ -358,117 +358,331 @@ def test_graph_replay_gives_identical_frames():
     proc.close()
 
 
-class _DevMem(object):
-    """Raw device pointer as a __cuda_array_interface__ object (torch only moves the bytes)."""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = dict(shape=(int(nbytes),), typestr="|u1", data=(int(ptr), False), version=3)
-
-
-def _slot_product(proc, slot, which, dtype, shape):
-    import torch
-    ptr, nbytes = proc.slotDevicePtr(slot, which)
-    return torch.as_tensor(_DevMem(ptr, nbytes), device="cuda:0").cpu().numpy().view(dtype).reshape(shape)
-
-
-@pytest.mark.parametrize("name", ["C4", "C5", "C4r", "C2"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4", "C5", "C4r"])
 def test_bench_configuration_parity(name):
-    """Drives b200s_process_pair_async exactly like bench.py's timed legs (same config table, slot count, frames per
-    step, seeds, graph replay, device-resident inputs with products left in the slot buffers, then pinned host buffers)
+    """Drives the fused slot / batch path through bench.py's own ConfigRun (same config table, slot count, frames per
+    launch, seeds, graph replay; device-resident inputs with products left in the slot buffers, then pinned host buffers)
     and compares rect L/R, float disparity and the PointCloud2 bytes of EVERY frame of a replayed step with the real
-    OpenCV chain (tests/chain_ref.py; reference flow test/UTest.cpp:290-398)."""
+    OpenCV chain (reference flow test/UTest.cpp:290-398)."""
     import os
     import sys
     import torch
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
     import bench as B
-    from chain_ref import expected_chain, first_mismatch
+    c = B.CONFIGS[name]
+    run = B.ConfigRun(name, c, 0, 0, None)
+    chain = B.CpuChain(c, run.cal, os.cpu_count() or 1)
+    want = [chain.run(L, R) for (L, R) in run.frames]
+    assert np.mean([(w["disparity32f"] > 0).mean() for w in want]) > 0.3      # the synthetic pairs really match
+    H, W = run.H, run.W
+
+    def compare(leg, i, get):
+        for key, bit, es in run.products:
+            got = get(key, bit)
+            w = np.ascontiguousarray(want[i][key]).view(np.uint8).ravel()
+            assert got.shape == w.shape, (name, leg, i, key)
+            if not np.array_equal(got, w):
+                bad = np.nonzero(got != w)[0]
+                raise AssertionError("%s %s frame %d %s: %d bytes differ, first at pixel %d" % (name, leg, i, key, bad.size, bad[0] // es))
+
+    def dev_product(s, k, bit):
+        ptr, nbytes = run.proc.slotFrameDevicePtr(s, k, bit)
+        return torch.as_tensor(B._DevMem(ptr, nbytes), device="cuda:0").cpu().numpy()
+
+    # ---- device-resident leg: eager, capture, replay (unchecked, like the bench warm-up), then a checked replayed step
+    run.prepare_device()
+    r0 = run.proc.graphReplays()
+    run.proc.syncParams()
+    for _ in range(3):
+        run.step_device()
+    for s in range(run.S):
+        run.proc.waitSlot(s)
+    assert run.proc.graphReplays() - r0 >= len(run.groups)
+    for g0 in range(0, len(run.groups), run.S):          # S batches in flight, then every frame of them is checked
+        gs = list(range(g0, min(g0 + run.S, len(run.groups))))
+        for g in gs:
+            run.proc.processBatchRaw(g % run.S, run.dev_batches[g])
+        for g in gs:
+            run.proc.waitSlot(g % run.S)
+            for k, i in enumerate(run.groups[g]):
+                compare("device", i, lambda key, bit: dev_product(g % run.S, k, bit))
+    # ---- host leg (pinned buffers, H2D + D2H inside the chain)
+    run.prepare_host()
+    for _ in range(3):
+        run.step_host()
+    for s in range(run.S):
+        run.proc.waitSlot(s)
+    for g0 in range(0, len(run.groups), run.S):
+        gs = list(range(g0, min(g0 + run.S, len(run.groups))))
+        for g in gs:
+            run.proc.waitSlot(g % run.S)
+            run.proc.processBatchRaw(g % run.S, run.host_batches[g])
+        for g in gs:
+            run.proc.waitSlot(g % run.S)
+            for k, i in enumerate(run.groups[g]):
+                compare("host", i, lambda key, bit: run.host_views[g % run.S][k][key])
+    # ---- and the bench's own self-check on the same state
+    f, mm, bad = run.check("host", chain)
+    assert f == min(run.S, len(run.groups)) and mm == 0, bad
+    run.close()
+
+
+@pytest.mark.parametrize("direct", [0, 1])
+def test_batched_frames_equal_single_frames(direct):
+    """b200s_process_batch_async: a batch of frames through one launch per kernel gives the bytes of frame-by-frame calls
+    (which the other tests pin to the oracle), for every product, ragged batch sizes, the L/R-check + speckle state, and
+    both pack modes (copy engine / kernels storing straight into the pinned host buffers)."""
     m = _gpu()
     cap = m._capi
-    c = B.CONFIGS[name]
-    W, H, nd = c["W"], c["H"], c["nd"]
+    W, H, nd, b = 500, 263, 64, 9
+    frames = [synth.synth_raw_pair(W, H, nd, seed=6100 + i) for i in range(5)]
+    cal = frames[0][2]
     n = W * H
-    F, S = B.FRAMES_PER_STEP, B.N_SLOTS
-    frames, cal = B.make_frames(c, F, 1000 * c["idx"])
-    p = O.BMParams(numDisparities=nd, blockSize=c["block"], speckleWindowSize=c["speckle"][0], speckleRange=c["speckle"][1],
-                   preFilterType=c.get("pft", 1), preFilterSize=c.get("ps", 9), uniquenessRatio=c.get("uniq", 15),
-                   disp12MaxDiff=c.get("disp12", -1))
-    want = [expected_chain(L, R, cal, p, c["rectify"]) for (L, R) in frames]
-    assert np.mean([(w["disparity16"] != -16).mean() for w in want]) > 0.3
+    names = ("rect_left", "rect_right", "disparity16", "disparity32f", "pointcloud2", "points_xyz")
+    sizes = dict(rect_left=n, rect_right=n, disparity16=2 * n, disparity32f=4 * n, pointcloud2=32 * n, points_xyz=12 * n)
+    bits = dict(rect_left=cap.OUT_RECT_L, rect_right=cap.OUT_RECT_R, disparity16=cap.OUT_DISPARITY16, disparity32f=cap.OUT_DISPARITY32F,
+                pointcloud2=cap.OUT_POINTCLOUD2, points_xyz=cap.OUT_POINTS_XYZ)
+    for p in (O.BMParams(numDisparities=nd, blockSize=b),
+              O.BMParams(numDisparities=nd, blockSize=b, preFilterType=0, preFilterSize=5, uniquenessRatio=0, disp12MaxDiff=0,
+                         speckleWindowSize=60, speckleRange=32)):
+        single = m.GpuStereoProcessor(0)
+        single.initStereoModel(_caminfo(cal["left"], W, H), _caminfo(cal["right"], W, H))
+        _set(single, p)
+        want = [single.processPair(Lr, Rr, rectify=True, want=names) for (Lr, Rr, _) in frames]
+        single.close()
+        rl = O.rectify(frames[0][0], **cal["left"])
+        d0 = O.stereobm_compute(rl, O.rectify(frames[0][1], **cal["right"]), p)
+        assert np.array_equal(want[0]["disparity16"], d0)                      # the single-frame path itself is pinned
+        proc = m.GpuStereoProcessor(0)
+        proc.setPackMode(direct)
+        proc.initStereoModel(_caminfo(cal["left"], W, H), _caminfo(cal["right"], W, H))
+        _set(proc, p)
+        proc.configureSlots(2, H, W, frames_per_slot=4)
+        pins = []
+        hin = []
+        for (Lr, Rr, _) in frames:
+            a, pa = proc.hostAlloc(n); a[:] = np.ascontiguousarray(Lr).ravel()
+            c, pc = proc.hostAlloc(n); c[:] = np.ascontiguousarray(Rr).ravel()
+            pins += [pa, pc]
+            hin.append((pa, pc))
+        for nb, first in ((4, 0), (3, 1), (1, 4), (4, 1)):                    # full, ragged and single-frame batches
+            ios = (cap.FrameIO * nb)()
+            views = []
+            for k in range(nb):
+                ios[k].rectify, ios[k].rows, ios[k].cols = 1, H, W
+                v = {}
+                for name in names:
+                    ios[k].want |= bits[name]
+                    v[name], ptr = proc.hostAlloc(sizes[name])
+                    pins.append(ptr)
+                    setattr(ios[k], name, ptr)
+                views.append(v)
+            idx = [first + k for k in range(nb)]
+            for rep in range(3):                                               # eager, captured, replayed
+                for v in views:
+                    for a in v.values():
+                        a[:] = 0
+                proc.processBatchAsync(nb & 1, [hin[i][0] for i in idx], [hin[i][1] for i in idx], ios)
+                proc.waitSlot(nb & 1)
+                for k, i in enumerate(idx):
+                    for name in names:
+                        w = np.ascontiguousarray(want[i][name]).view(np.uint8).ravel()
+                        assert np.array_equal(views[k][name], w), (direct, nb, first, rep, k, name)
+        with pytest.raises(cap.B200StereoError) as e:                          # more frames than the slot holds
+            proc.processBatchAsync(0, [hin[0][0]] * 5, [hin[0][1]] * 5, (cap.FrameIO * 5)())
+        assert e.value.code == cap.EINVAL
+        for ptr in pins:
+            proc.hostFree(ptr)
+        proc.close()
 
+
+def test_fused_chain_colour_point_cloud():
+    """Colour camera in the fused path (src/StereoProcessor.cpp:201-217,239-256: the rectified colour image feeds
+    enqueueSendPoints): bgr8 / rgb8 colour input, with and without a separate mono image, against the oracle."""
+    import cv2
+    m = _gpu()
+    W, H, nd, b = 640, 360, 64, 11
+    Lraw, Rraw, cal = synth.synth_raw_pair(W, H, nd, seed=6200)
+    rng = np.random.default_rng(5)
+    tint = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    color = ((Lraw[..., None].astype(np.uint16) * 3 + tint) // 4).astype(np.uint8)     # BGR
+    p = O.BMParams(numDisparities=nd, blockSize=b)
     proc = m.GpuStereoProcessor(0)
-    B.setup_processor(proc, c, cal)
-    proc.configureSlots(S, H, W)
-    wbits = B.want_bits(c, cap)
-    products = [("rect_left", cap.OUT_RECT_L, np.uint8, (H, W)), ("rect_right", cap.OUT_RECT_R, np.uint8, (H, W)),
-                ("disparity32f", cap.OUT_DISPARITY32F, np.float32, (H, W)), ("pointcloud2", cap.OUT_POINTCLOUD2, np.uint8, (H, W, 32))]
-    products = [q for q in products if wbits & q[1]]
+    proc.initStereoModel(_caminfo(cal["left"], W, H), _caminfo(cal["right"], W, H))
+    _set(proc, p)
+    cxd = cal["left"]["P"][2] - cal["right"]["P"][2]
+    Q = O.stereo_Q(cal["left"]["P"], cal["right"]["P"])
+    rcol = O.rectify(color, **cal["left"])
+    rr = O.rectify(Rraw, **cal["right"])
+    # (a) separate mono image + bgr8 colour
+    out = proc.processPair(Lraw, Rraw, rectify=True, want=("rect_left", "disparity16", "pointcloud2", "rect_color_left"), color=color)
+    rl = O.rectify(Lraw, **cal["left"])
+    d = O.stereobm_compute(rl, rr, p)
+    assert np.array_equal(out["rect_left"], rl) and np.array_equal(out["disparity16"], d)
+    assert np.array_equal(out["rect_color_left"], rcol)
+    pc = O.pack_pointcloud2(O.reproject(O.disparity_to_float(d, cxd), Q), rcol)
+    assert np.array_equal(out["pointcloud2"], pc)
+    assert (out["pointcloud2"][..., 16] != out["pointcloud2"][..., 18]).mean() > 0.5       # really coloured
+    # (b) colour camera only, rgb8: the grey image is cv::cvtColor(BGR2GRAY) of the colour image (convertRawToMono)
+    out2 = proc.processPair(None, Rraw, rectify=True, want=("rect_left", "disparity16", "pointcloud2"),
+                            color=np.ascontiguousarray(color[..., ::-1]), color_encoding="rgb8")
+    gray = cv2.cvtColor(color, cv2.COLOR_BGR2GRAY)
+    rl2 = O.rectify(gray, **cal["left"])
+    d2 = O.stereobm_compute(rl2, rr, p)
+    assert np.array_equal(out2["rect_left"], rl2) and np.array_equal(out2["disparity16"], d2)
+    assert np.array_equal(out2["pointcloud2"], O.pack_pointcloud2(O.reproject(O.disparity_to_float(d2, cxd), Q), rcol))
+    # (c) already rectified inputs: the colour image is used as it is
+    out3 = proc.processPair(rl, rr, rectify=False, want=("disparity16", "pointcloud2"), color=rcol)
+    assert np.array_equal(out3["disparity16"], d) and np.array_equal(out3["pointcloud2"], pc)
+    proc.close()
 
-    def compare(i, get):
-        for key, bit, dt, shape in products:
-            got = get(key, bit, dt, shape)
-            msg = first_mismatch(got.view(np.uint32) if dt == np.float32 else got,
-                                 want[i][key].view(np.uint32) if dt == np.float32 else want[i][key])
-            assert not msg, "%s frame %d %s: %s" % (name, i, key, msg)
 
-    # ---- device-resident leg ----
-    dL = [torch.from_numpy(f[0]).cuda(0) for f in frames]
-    dR = [torch.from_numpy(f[1]).cuda(0) for f in frames]
+def test_process_pair_follows_the_image_size():
+    """A later processPair with another image size reconfigures the slots instead of reading / writing past the buffers;
+    the C entry point rejects a frame whose declared size differs from the slot size."""
+    m = _gpu()
+    cap = m._capi
+    proc = m.GpuStereoProcessor(0)
+    p = O.BMParams(numDisparities=32, blockSize=9)
+    _set(proc, p)
+    for (W, H) in ((400, 300), (320, 200), (640, 480)):
+        L, R = synth.synth_pair(W, H, 32, seed=W)
+        out = proc.processPair(L, R, rectify=False, want=("disparity16",))
+        assert np.array_equal(out["disparity16"], O.stereobm_compute(L, R, p)), (W, H)
     io = cap.FrameIO()
-    io.want, io.rectify, io.inputs_on_device, io.outputs_on_device = wbits, int(c["rectify"]), 1, 1
-    r0 = proc.graphReplays()
-    for step in range(3):                      # eager, capture, replay -- unchecked, like the warm-up of the bench
-        for i in range(F):
-            proc.processPairAsync(i % S, dL[i].data_ptr(), dR[i].data_ptr(), io)
-    for s in range(S):
-        proc.waitSlot(s)
-    assert proc.graphReplays() - r0 >= F
-    for g in range(0, F, S):                   # a replayed step, checked frame by frame (S frames in flight)
-        for i in range(g, min(g + S, F)):
-            proc.processPairAsync(i % S, dL[i].data_ptr(), dR[i].data_ptr(), io)
-        for i in range(g, min(g + S, F)):
-            proc.waitSlot(i % S)
-            compare(i, lambda key, bit, dt, shape: _slot_product(proc, i % S, bit, dt, shape))
+    io.want, io.rows, io.cols = cap.OUT_DISPARITY16, 100, 100
+    small = np.zeros((100, 100), np.uint8)
+    with pytest.raises(cap.B200StereoError) as e:
+        proc.processPairAsync(0, small.ctypes.data, small.ctypes.data, io)
+    assert e.value.code == cap.EINVAL
+    proc.close()
 
-    # ---- host leg (pinned buffers, H2D + D2H inside the chain) ----
-    pins, ios, views = [], [], []
-    def pinned(nbytes):
-        a, ptr = proc.hostAlloc(nbytes)
-        pins.append(ptr)
-        return a, ptr
-    hin = []
-    for (L, R) in frames:
-        a, pa = pinned(n); a[:] = L.ravel()
-        b, pb = pinned(n); b[:] = R.ravel()
-        hin.append((pa, pb))
-    for s in range(S):
-        hio = cap.FrameIO()
-        hio.want, hio.rectify = wbits, int(c["rectify"])
-        v = {}
-        v["disparity32f"], hio.disparity32f = pinned(n * 4)
-        v["pointcloud2"], hio.pointcloud2 = pinned(n * 32)
-        if c["rectify"]:
-            v["rect_left"], hio.rect_left = pinned(n)
-            v["rect_right"], hio.rect_right = pinned(n)
-        ios.append(hio)
-        views.append(v)
-    for step in range(3):
-        for i in range(F):
-            if i >= S or step > 0:
-                proc.waitSlot(i % S)
-            proc.processPairAsync(i % S, hin[i][0], hin[i][1], ios[i % S])
-    for s in range(S):
-        proc.waitSlot(s)
-    for g in range(0, F, S):
-        for i in range(g, min(g + S, F)):
-            proc.processPairAsync(i % S, hin[i][0], hin[i][1], ios[i % S])
-        for i in range(g, min(g + S, F)):
-            proc.waitSlot(i % S)
-            compare(i, lambda key, bit, dt, shape: views[i % S][key].view(dt).reshape(shape))
-    for ptr in pins:
+
+def test_asynchronous_senders_publish_from_the_stream_callback(proc, fixtures, calib):
+    """enqueueSend*(asynchronous=True) = the reference's senders (src/GpuSenderIfc.cpp:13-26): the call only enqueues, the
+    publisher runs on the stream-callback thread, the payload equals the synchronous one; the reference's ids are accepted
+    (POINTS2 into enqueueSendPoints, DISPARITY_32F into projectDisparityTo3DPoints, test/UTest.cpp:378-382)."""
+    import threading
+    m = _gpu()
+    proc.initStereoModel(_caminfo(calib["left"], 752, 480), _caminfo(calib["right"], 752, 480))
+    p = O.BMParams(numDisparities=64, blockSize=15)
+    _set(proc, p)
+    L, R = fixtures["left_rect"], fixtures["right_rect"]
+    proc.uploadMat(m.SRC_RECT_MONO | m.SIDE_L, L, "mono8")
+    proc.uploadMat(m.SRC_RECT_MONO | m.SIDE_R, R, "mono8")
+    proc.computeDisparity(m.SRC_RECT_MONO | m.SIDE_L, m.SRC_RECT_MONO | m.SIDE_R, m.SRC_DISPARITY | m.SIDE_L)
+    proc.projectDisparityTo3DPoints(m.SRC_DISPARITY_32F | m.SIDE_L, m.SRC_POINTS2 | m.SIDE_L)
+    sync_pc = proc.enqueueSendPoints(m.SRC_POINTS2 | m.SIDE_L, m.SRC_RECT_MONO | m.SIDE_L).message["data"].copy()
+    sync_d = proc.enqueueSendDisparity(m.SRC_DISPARITY | m.SIDE_L).message
+    got, threads = {}, set()
+
+    def pub(kind):
+        def f(msg):
+            threads.add(threading.get_ident())
+            got[kind] = msg
+        return f
+    s1 = proc.enqueueSendPoints(m.SRC_POINTS2 | m.SIDE_L, m.SRC_RECT_MONO | m.SIDE_L, pub=pub("pc"), asynchronous=True)
+    s2 = proc.enqueueSendDisparity(m.SRC_DISPARITY | m.SIDE_L, pub=pub("disp"), asynchronous=True)
+    s3 = proc.enqueueSendImage(m.SRC_RECT_MONO | m.SIDE_L, encoding="mono8", pub=pub("img"), asynchronous=True)
+    proc.waitForAllStreams()
+    assert s1.wasDataSent() and s2.wasDataSent() and s3.wasDataSent() and set(got) == {"pc", "disp", "img"}
+    assert threading.get_ident() not in threads                       # published from the CUDA callback thread
+    assert np.array_equal(got["pc"]["data"], sync_pc) and got["pc"]["point_step"] == 32
+    assert np.array_equal(got["disp"]["image"]["data"], sync_d["image"]["data"]) and got["disp"]["valid_window"] == sync_d["valid_window"]
+    assert np.array_equal(got["img"]["data"].reshape(480, 752), L)
+    proc.cleanSenders()
+    proc.convertColor(m.SRC_RECT_MONO | m.SIDE_L, m.SRC_RECT_COLOR | m.SIDE_L, "mono8", "bgr8")
+    assert np.array_equal(proc.downloadMat(m.SRC_RECT_COLOR | m.SIDE_L), np.repeat(L[..., None], 3, axis=2))
+    st = proc.matStats(m.SRC_RECT_MONO | m.SIDE_L)
+    assert st[0][0] == L.min() and st[0][1] == L.max() and abs(st[0][2] - L.mean()) < 1e-9
+    assert len(proc.printStats("rect", m.SRC_RECT_COLOR | m.SIDE_L)) == 3
+
+
+def test_graph_cache_keeps_alternating_destinations_replaying():
+    """A caller that alternates two destination buffers on one slot (double-buffered message memory) still gets graph
+    replays: a slot caches a few captured chains."""
+    m = _gpu()
+    cap = m._capi
+    W, H, nd = 480, 270, 32
+    Lr, Rr, cal = synth.synth_raw_pair(W, H, nd, seed=6300)
+    proc = m.GpuStereoProcessor(0)
+    proc.initStereoModel(_caminfo(cal["left"], W, H), _caminfo(cal["right"], W, H))
+    p = O.BMParams(numDisparities=nd, blockSize=9)
+    _set(proc, p)
+    proc.configureSlots(1, H, W)
+    want = O.stereobm_compute(O.rectify(Lr, **cal["left"]), O.rectify(Rr, **cal["right"]), p)
+    bufs = [proc.hostAlloc(W * H * 2) for _ in range(2)]
+    ios = []
+    for a, ptr in bufs:
+        io = cap.FrameIO()
+        io.want, io.rectify, io.disparity16 = cap.OUT_DISPARITY16, 1, ptr
+        ios.append(io)
+    Lc, Rc = np.ascontiguousarray(Lr), np.ascontiguousarray(Rr)
+    r0 = proc.graphReplays()
+    for it in range(10):
+        a, ptr = bufs[it & 1]
+        a[:] = 0
+        proc.processPairAsync(0, Lc.ctypes.data, Rc.ctypes.data, ios[it & 1])
+        proc.waitSlot(0)
+        assert np.array_equal(a.view(np.int16).reshape(H, W), want), it
+    assert proc.graphReplays() - r0 >= 6
+    for a, ptr in bufs:
         proc.hostFree(ptr)
     proc.close()
+
+
+def test_rectification_map_formats(proc):
+    """The cached map is a 4 B/px table of int16 deltas; a calibration whose shifts exceed +-1024 px falls back to the
+    8 B/px absolute table.  Both equal the oracle (and the on-the-fly evaluation)."""
+    m = _gpu()
+    W, H = 2600, 120
+    cal = synth.scaled_calibration(752, 480)
+    c = {k: np.array(v, np.float64).copy() for k, v in cal["left"].items()}
+    K = c["K"].reshape(3, 3)
+    P = c["P"].reshape(3, 4)
+    K[0, 0] = K[1, 1] = P[0, 0] = P[1, 1] = 500.0
+    K[0, 2], P[0, 2] = 2400.0, 1200.0          # principal points 1200 px apart -> shifts beyond the int16 delta range
+    K[1, 2] = P[1, 2] = 60.0
+    c["D"] = np.zeros(5)
+    c = {k: v.ravel().tolist() for k, v in c.items()}
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    want = O.rectify(img, **c)
+    assert want.any()
+    proc.initStereoModel(_caminfo(c, W, H), _caminfo(c, W, H))
+    for fly in (False, True):
+        proc.setRectifyOnTheFly(fly)
+        got = proc.rectifyImageLeft(img)
+        assert np.array_equal(got, want), fly
+    proc.setRectifyOnTheFly(False)
+
+
+def test_disparity_vis_matches_hsv_colouring(proc):
+    """disparity_vis (computeDisparityImage, src/GPUStereoProcessor.cpp:323-330 = cv::cuda::drawColorDisp) pinned against an
+    independent computation: hue H = (nd - d) * 240 / nd (integer), S = V = 1, through OpenCV's own float HSV -> BGR
+    conversion (cv2.cvtColor), truncated to 8 bits like the upstream kernel; alpha = 255."""
+    import cv2
+    m = _gpu()
+    nd = 128
+    rng = np.random.default_rng(11)
+    d16 = (rng.integers(-1, nd, (97, 256)) * 16 + rng.integers(0, 16, (97, 256))).astype(np.int16)
+    d16[0, :nd] = np.arange(nd) * 16                        # every integer disparity at least once
+    proc.setParams(numDisparities=nd)
+    proc.uploadMat(m.SRC_DISPARITY | m.SIDE_L, d16)
+    proc.computeDisparityImage(m.SRC_DISPARITY | m.SIDE_L, m.SRC_DISPARITY_IMG | m.SIDE_L)
+    vis = proc.downloadMat(m.SRC_DISPARITY_IMG | m.SIDE_L)
+    d = np.clip(d16.astype(np.int32) >> 4, 0, 255)
+    hue = ((nd - d) * 240 // nd).astype(np.float32)
+    hsv = np.stack([hue, np.ones_like(hue), np.ones_like(hue)], axis=2)
+    bgr = cv2.cvtColor(hsv, cv2.COLOR_HSV2BGR)              # float image: H in degrees, S, V in [0, 1]
+    # cv2's float conversion and the upstream kernel's formula can differ in the last float bit, i.e. by one 8-bit level
+    # where channel * 255 sits on an integer: tolerance 1 level, exact on every pure channel
+    want = np.clip(bgr * 255.0, 0, 255)
+    diff = np.abs(vis[..., :3].astype(np.float64) - np.floor(want + 1e-3))
+    assert diff.max() <= 1 and (diff > 0).mean() < 0.05, (diff.max(), (diff > 0).mean())
+    assert (vis[..., 3] == 255).all()
+    assert np.array_equal(vis, O.draw_color_disp(d16, nd))
 
 
 def test_multi_gpu_pool_shards_frames():

@@ -195,3 +195,24 @@ def test_rectify_matches_cv2_random_calibrations():
         img = rng.integers(0, 256, (H, W), dtype=np.uint8)
         m1, m2 = CV.rect_maps(K, D, R, P, W, H)
         assert np.array_equal(O.rectify(img, K=K, D=D, R=R, P=P), cv2.remap(img, m1, m2, cv2.INTER_LINEAR)), case
+
+
+def test_disparity_vis_restatement_against_opencv_hsv():
+    """The oracle's drawColorDisp restatement against an independent computation: hue (nd - d) * 240 / nd,
+    S = V = 1 through OpenCV's float HSV -> BGR conversion.  The upstream kernel divides H by 60 where cv2 multiplies by
+    1/60, so a channel may differ by one 8-bit level where its value sits on an integer: tolerance 1 level."""
+    import cv2
+    for nd in (128, 256):
+        rng = np.random.default_rng(nd)
+        d16 = (rng.integers(-1, nd, (64, 300)) * 16 + rng.integers(0, 16, (64, 300))).astype(np.int16)
+        vis = O.draw_color_disp(d16, nd)
+        d = np.clip(d16.astype(np.int32) >> 4, 0, 255)
+        hue = ((nd - d) * 240 // nd).astype(np.float32)
+        bgr = cv2.cvtColor(np.stack([hue, np.ones_like(hue), np.ones_like(hue)], axis=2), cv2.COLOR_HSV2BGR)
+        diff = np.abs(vis[..., :3].astype(np.float64) - np.floor(np.clip(bgr * 255.0, 0, 255) + 1e-3))
+        assert diff.max() <= 1 and (diff > 0).mean() < 0.05
+        assert (vis[..., 3] == 255).all()
+        # pure hues are exact: d = nd (hue 0 = red), d = nd / 2 (hue 120 = green), invalid d <= 0 (hue 240 = blue)
+        probe = np.array([[nd * 16 if nd < 256 else 255 * 16, (nd // 2) * 16, -16, 0]], np.int16)
+        v = O.draw_color_disp(probe, nd)
+        assert tuple(v[0, 1, :3]) == (0, 255, 0) and tuple(v[0, 2, :3]) == (255, 0, 0) and tuple(v[0, 3, :3]) == (255, 0, 0)
