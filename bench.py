@@ -7,7 +7,7 @@
 Headline workload (config.workload): BASELINE.json configs[3] = C4 -- 1920x1080 mono8 raw pair, camera_info rectification,
 x-Sobel prefilter, StereoBM 256 disparities / block 11 / texture 10 / uniqueness 15, DisparityImage float payload and
 PointCloud2 payload: the full rectify -> disparity -> pc2 chain.  One "step" = one pass of that chain over a batch of
-frames_per_step frames per GPU (PASSES passes over FRAMES_DISTINCT distinct synthetic frames).
+FRAMES_PER_STEP frames per GPU (passes over the config's distinct synthetic frames).
 
   value  frames/s with the raw frames and every output resident in HBM (CUDA events on the slot streams)
   e2e    frames/s through the C ABI with pinned HOST buffers: H2D of the raw pair and D2H of the rectified pair,
@@ -38,9 +38,10 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {
     # name: W, H, nd, block, rectify, speckle(win, range); batch = frames per launch (slot depth), slots = batches in flight
-    "C1": dict(W=752, H=480, nd=64, block=21, rectify=False, speckle=(0, 0), idx=1, batch=16, slots=4),
-    "C2": dict(W=1242, H=375, nd=128, block=15, rectify=False, speckle=(100, 4), idx=2, batch=16, slots=4),
-    "C3": dict(W=1280, H=720, nd=128, block=15, rectify=True, speckle=(0, 0), idx=3, batch=8, slots=4),
+    # frames = distinct synthetic frames per GPU (enough for `slots` batches in flight)
+    "C1": dict(W=752, H=480, nd=64, block=21, rectify=False, speckle=(0, 0), idx=1, batch=16, slots=4, frames=64),
+    "C2": dict(W=1242, H=375, nd=128, block=15, rectify=False, speckle=(100, 4), idx=2, batch=16, slots=4, frames=64),
+    "C3": dict(W=1280, H=720, nd=128, block=15, rectify=True, speckle=(0, 0), idx=3, batch=8, slots=4, frames=32),
     "C4": dict(W=1920, H=1080, nd=256, block=11, rectify=True, speckle=(0, 0), idx=4, batch=1, slots=4),
     "C5": dict(W=3840, H=2160, nd=256, block=11, rectify=True, speckle=(0, 0), idx=5, batch=1, slots=4),
     # not a BASELINE config: C4 with the reference's default speckle filter on (GPU.cfg max_speckle_size 800,
@@ -51,9 +52,7 @@ CONFIGS = {
     # from the cuda matcher's getters, src/GPUStereoProcessor.cpp:22-38, speckle filter 800 / 5 disparities)
     "C4r": dict(W=1920, H=1080, nd=256, block=11, rectify=True, speckle=(800, 80), idx=4, pft=0, ps=5, uniq=0, disp12=0, batch=1, slots=4),
 }
-FRAMES_DISTINCT = 16      # distinct synthetic frames per GPU
-PASSES = 4                # passes over them per step of the headline config
-FRAMES_PER_STEP = FRAMES_DISTINCT * PASSES
+FRAMES_PER_STEP = 64      # frames per GPU and step: passes over the config's distinct frames (16 unless the config says otherwise)
 N_SLOTS = int(os.environ.get("B200S_BENCH_SLOTS", "0"))       # 0 = per config
 BATCH = int(os.environ.get("B200S_BENCH_BATCH", "0"))         # 0 = per config
 THEORETICAL_TOPS = 37.2   # 148 SMs x 128 int32 lanes x 1.965 GHz
@@ -63,8 +62,16 @@ def slots_of(c):
     return N_SLOTS or c.get("slots", 4)
 
 
+def frames_of(c):
+    return int(os.environ.get("B200S_BENCH_FRAMES", c.get("frames", 16)))
+
+
+def passes_of(c):
+    return max(1, FRAMES_PER_STEP // frames_of(c))
+
+
 def batch_of(c):
-    return max(1, min(BATCH or c.get("batch", 1), FRAMES_DISTINCT))
+    return max(1, min(BATCH or c.get("batch", 1), frames_of(c)))
 
 
 def workload_name(c, name):
@@ -78,10 +85,10 @@ def workload_name(c, name):
 def config_dict(c, name, frames_per_step):
     """The `config` object of the JSON line -- identical in both arms (ours / reference) for the same workload."""
     n = c["W"] * c["H"]
-    return dict(workload=workload_name(c, name), frames_per_step_per_gpu=frames_per_step, distinct_frames_per_gpu=FRAMES_DISTINCT,
+    return dict(workload=workload_name(c, name), frames_per_step_per_gpu=frames_per_step, distinct_frames_per_gpu=frames_of(c),
                 sharding="independent frames per GPU, no collective",
                 l2="no flush: each step cycles %d distinct frames; working set (inputs %.0f MB + products of the frames in flight) exceeds the 126 MB L2 for C3-C5"
-                   % (FRAMES_DISTINCT, 2 * n * FRAMES_DISTINCT / 1e6))
+                   % (frames_of(c), 2 * n * frames_of(c) / 1e6))
 
 
 def evals_per_frame(c):
@@ -286,14 +293,15 @@ class ConfigRun(object):
         self.torch, self.capi, self.name, self.c, self.rank, self.dev, self.dist = torch, capi, name, c, rank, dev, dist
         self.W, self.H, self.n = c["W"], c["H"], c["W"] * c["H"]
         self.S, self.B = slots_of(c), batch_of(c)
-        self.frames, self.cal = make_frames(c, FRAMES_DISTINCT, 1000 * c["idx"] + rank * FRAMES_DISTINCT)
+        self.nframes = frames_of(c)
+        self.frames, self.cal = make_frames(c, self.nframes, 1000 * c["idx"] + rank * self.nframes)
         self.proc = m.GpuStereoProcessor(dev)
         setup_processor(self.proc, c, self.cal)
         self.proc.configureSlots(self.S, self.H, self.W, self.B)
         self.want = want_bits(c, capi)
         self.products = [(k, getattr(capi, bit), es) for k, bit, es in self.PRODUCTS if self.want & getattr(capi, bit)]
         self.pins = []
-        self.groups = [list(range(g, min(g + self.B, FRAMES_DISTINCT))) for g in range(0, FRAMES_DISTINCT, self.B)]
+        self.groups = [list(range(g, min(g + self.B, self.nframes))) for g in range(0, self.nframes, self.B)]
         self._dev_ready = self._host_ready = False
 
     # ---- device-resident leg: inputs in HBM (torch only owns the memory), products stay in the slot buffers ----
@@ -376,10 +384,9 @@ class ConfigRun(object):
         ms = self.proc.batchEnd()
         l1 = self.proc.kernelLaunches()
         self.barrier()
-        if self.dist is not None:
-            t = self.torch.tensor([ms], device="cuda:%d" % self.dev)
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-            ms = float(t.item())
+        # whole-job span = the slowest rank's device-timed span (MAX over ranks)
+        from ros_gpu_stereo_processor_b200 import sharding
+        _, ms = sharding.aggregate_throughput(1, ms, self.dist, "cuda:%d" % self.dev)
         return ms, l1 - l0
 
     # ---- parity self-check: the frames the last step left behind, one frame per slot, against the OpenCV chain ----
@@ -471,7 +478,7 @@ def measure_config(name, c, args, rank, world, dev, dist, steps, warmup, passes,
     out = dict(workload=workload_name(c, name), batch=run.B, slots=run.S)
     run.prepare_device()
     ms_dev, launches = run.timed(run.step_device, steps, warmup, passes)
-    frames_total = FRAMES_DISTINCT * passes * steps * world
+    frames_total = run.nframes * passes * steps * world
     fps_dev = frames_total / (ms_dev * 1e-3)
     chain = None
     checks = dict(frames=0, mismatches=0, failures=[])
@@ -519,7 +526,7 @@ def run_ours(args, rank, world, local_rank):
 
     sampler = ClockSampler(dev)
     sampler.start()
-    main = measure_config(name, c, args, rank, world, dev, dist, args.steps, args.warmup, PASSES, True, all_cpus)
+    main = measure_config(name, c, args, rank, world, dev, dist, args.steps, args.warmup, passes_of(c), True, all_cpus)
     clocks = sampler.stop()
     run = main.pop("_run")
     nominal, eff = evals_per_frame(c)
@@ -585,7 +592,7 @@ def run_ours(args, rank, world, local_rank):
     for tname in [t for t in args.table.split(",") if t and t != name]:
         tc = CONFIGS[tname]
         tsteps = max(2, min(args.steps, 6))
-        res = measure_config(tname, tc, args, rank, world, dev, dist, tsteps, 3, 1 if tname == "C5" else PASSES, True, all_cpus)
+        res = measure_config(tname, tc, args, rank, world, dev, dist, tsteps, 3, 1 if tname == "C5" else passes_of(tc), True, all_cpus)
         res.pop("_run").close()
         table[tname] = {k: v for k, v in res.items() if not k.startswith("_")}
         table[tname]["steps"] = tsteps

@@ -271,7 +271,8 @@ int ensure_pre_planes(b200s_handle* h, Work& w, int rows, int cols, int nf)
 
 // prefilter + match + post-filters on rectified device planes; disp must hold rows*cols int16 per frame
 int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, bool already_prefiltered, int rows,
-                  int cols, int16_t* disp, cudaStream_t st, int nf, size_t src_stride, size_t disp_stride)
+                  int cols, int16_t* disp, cudaStream_t st, int nf, size_t src_stride, size_t disp_stride, const uint8_t* const* tabL,
+                  const uint8_t* const* tabR)
 {
     const b200s_params& p = h->prm;
     int rc = validate_params(h, p);
@@ -291,16 +292,19 @@ int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, 
         if (p.pre_filter_type == 1) {
             // tiled x-Sobel of both sides (and all frames) in one launch: the fused kernel with the identity map
             h->launches += launch_rectify_xsobel_pair(L, R, cols, rows, MAP_NONE, nullptr, nullptr, h->cam[0].cm, h->cam[1].cm, nullptr,
-                                                      nullptr, pl, pr, pitch, cols, rows, p.pre_filter_cap, st, nf, src_stride, 0, pstride);
+                                                      nullptr, pl, pr, pitch, cols, rows, p.pre_filter_cap, st, nf, src_stride, 0, pstride, tabL, tabR);
         } else {
             const int one = launch_norm_prefilter_pair(L, R, cols, rows, MAP_NONE, nullptr, nullptr, h->cam[0].cm, h->cam[1].cm, nullptr, nullptr,
-                                                       pl, pr, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, st, nf, src_stride, 0, pstride);
+                                                       pl, pr, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, st, nf, src_stride, 0, pstride, tabL, tabR);
             h->launches += one;
             if (!one) {     // preFilterSize > 21: two passes through a scratch plane, frame by frame
                 if (w.normtmp.ensure(n * sizeof(int))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (prefilter scratch)");
                 for (int f = 0; f < nf; ++f) {
-                    h->launches += launch_prefilter_norm(L + f * src_stride, pl + f * pstride, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, (int*)w.normtmp.p, st);
-                    h->launches += launch_prefilter_norm(R + f * src_stride, pr + f * pstride, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, (int*)w.normtmp.p, st);
+                    // sources named by the slot's address table: its host copy tells where frame f is
+                    const uint8_t* lf = tabL ? (const uint8_t*)w.in_tab[f] : L + f * src_stride;
+                    const uint8_t* rf = tabR ? (const uint8_t*)w.in_tab[MAX_BATCH + f] : R + f * src_stride;
+                    h->launches += launch_prefilter_norm(lf, pl + f * pstride, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, (int*)w.normtmp.p, st);
+                    h->launches += launch_prefilter_norm(rf, pr + f * pstride, pitch, cols, rows, p.pre_filter_size, p.pre_filter_cap, (int*)w.normtmp.p, st);
                 }
             }
         }
@@ -344,7 +348,7 @@ int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, 
 
 int ensure_misc(b200s_handle* h, Work& w)
 {
-    if (w.misc.ensure(256)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (misc)");
+    if (w.misc.ensure(2048)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (misc)");
     return B200S_OK;
 }
 

@@ -80,6 +80,8 @@ struct Work {
     std::vector<std::string> warm_keys;   // allocation signatures this slot has already run eagerly
     std::vector<GraphEntry> graphs;
     uint64_t use_counter = 0;
+    std::string tab_cache;        // last input-address table written to the device (slots.cu)
+    const void* in_tab[3 * MAX_BATCH] = {nullptr};   // host copy of that table: L[32], R[32], colour[32]
     void drop_graphs()
     {
         for (GraphEntry& g : graphs)
@@ -188,7 +190,8 @@ int ensure_misc(b200s_handle* h, Work& w);
 // prefilter + match + post-filters on rectified device planes (a batch of nf frames: sources src_stride bytes apart,
 // prefiltered planes plane_stride(cols, rows) apart, disparity planes disp_stride apart)
 int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, bool already_prefiltered, int rows, int cols,
-                  int16_t* disp, cudaStream_t st, int nf = 1, size_t src_stride = 0, size_t disp_stride = 0);
+                  int16_t* disp, cudaStream_t st, int nf = 1, size_t src_stride = 0, size_t disp_stride = 0,
+                  const uint8_t* const* tabL = nullptr, const uint8_t* const* tabR = nullptr);
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 inline size_t plane_stride(int cols, int rows) { return align256(plane_bytes(cols, rows)); }
 // Device-side alias of a pinned (page-locked, mapped) host buffer, or nullptr when `p` is pageable / not host memory

@@ -20,6 +20,9 @@ struct BMConfig {          // cv::StereoBM state actually used by the matcher
 // ---- batches ----------------------------------------------------------------------------------------
 // Several equally sized frames can go through one launch (frame index = a grid dimension): frame f of a plane starts
 // `stride` BYTES after frame f - 1.  nf = 1 with zero strides is the single-frame case of the named-buffer API.
+// Input planes may instead be named by a device-resident table of per-frame addresses (`tab*`): the caller's own
+// device images are read in place, and a captured CUDA graph stays valid when the addresses change (only the table
+// is rewritten).
 constexpr int MAX_BATCH = 32;
 struct PtrList {           // per-frame destinations that are not one strided buffer (caller-owned pinned host memory)
     void* p[MAX_BATCH];
@@ -37,18 +40,21 @@ enum MapMode { MAP_NONE = 0, MAP_ABS32 = 1, MAP_FLY = 2, MAP_DELTA16 = 3 };
 int launch_build_map(const CamModel& cm, int W, int H, void* map, MapMode mode, int* overflow, cudaStream_t st);
 // cv::remap INTER_LINEAR / BORDER_CONSTANT(0); ch = 1, 3 or 4 interleaved
 int launch_remap(const uint8_t* src, int sW, int sH, int ch, const void* map, MapMode mode, const CamModel& cm,
-                 uint8_t* dst, int W, int H, cudaStream_t st, int nf = 1, size_t src_stride = 0, size_t dst_stride = 0);
+                 uint8_t* dst, int W, int H, cudaStream_t st, int nf = 1, size_t src_stride = 0, size_t dst_stride = 0,
+                 const uint8_t* const* src_tab = nullptr);
 // fused (rectify +) x-Sobel prefilter: writes the rectified plane (mode != MAP_NONE) and the prefiltered plane of both
 // sides in one launch (blockIdx.z = 2 * frame + side)
 int launch_rectify_xsobel_pair(const uint8_t* srcL, const uint8_t* srcR, int sW, int sH, MapMode mode, const void* mapL,
                                const void* mapR, const CamModel& cmL, const CamModel& cmR, uint8_t* rectL, uint8_t* rectR,
                                uint8_t* preL, uint8_t* preR, size_t pre_pitch, int W, int H, int cap, cudaStream_t st,
-                               int nf = 1, size_t src_stride = 0, size_t rect_stride = 0, size_t pre_stride = 0);
+                               int nf = 1, size_t src_stride = 0, size_t rect_stride = 0, size_t pre_stride = 0,
+                               const uint8_t* const* tabL = nullptr, const uint8_t* const* tabR = nullptr);
 // (rectify +) normalised-response prefilter of both sides in one tiled kernel (preFilterSize <= 21; returns 0 otherwise)
 int launch_norm_prefilter_pair(const uint8_t* srcL, const uint8_t* srcR, int sW, int sH, MapMode mode, const void* mapL,
                                const void* mapR, const CamModel& cmL, const CamModel& cmR, uint8_t* rectL, uint8_t* rectR,
                                uint8_t* preL, uint8_t* preR, size_t pre_pitch, int W, int H, int ps, int cap, cudaStream_t st,
-                               int nf = 1, size_t src_stride = 0, size_t rect_stride = 0, size_t pre_stride = 0);
+                               int nf = 1, size_t src_stride = 0, size_t rect_stride = 0, size_t pre_stride = 0,
+                               const uint8_t* const* tabL = nullptr, const uint8_t* const* tabR = nullptr);
 int launch_remap_nearest(const uint8_t* src, int sW, int sH, int ch, const CamModel& cm, uint8_t* dst, int W, int H,
                          cudaStream_t st);
 
@@ -108,10 +114,20 @@ int launch_disparity_to_float(const int16_t* d16, float* df, int n, double cxd, 
 // xyz (f32 x3, optional) and pc2 (32 B records, optional); color: ch = 1 (mono replicated) or 3 (BGR)
 // qmask: bit (4*r + c) set when Q[r][c] != 0 (zero terms are skipped; the result is bit-identical)
 // pc2_list (optional) overrides pc2 with one destination per frame ("pack straight into pinned host buffers").
+// min_d16 == nullptr: the missing value is the constant dmin_const (a plane that comes out of the matcher always holds
+// FILTERED = (minD - 1) * 16 as its minimum: the border columns), no reduction pass needed.
+// df / df_list (optional): also write the float disparity plane (convertTo) from the same pass over d16.
+struct ReprojectExtras {
+    int dmin_const = 0;
+    float* df = nullptr;
+    size_t df_stride = 0;
+    const PtrList* df_list = nullptr;
+    const uint8_t* const* color_tab = nullptr;      // per-frame colour planes (see `tab*` above)
+};
 int launch_reproject_pack(const int16_t* d16, int W, int H, double cxd, const double* Q, unsigned qmask, const int* min_d16,
                           const uint8_t* color, int ch, float* xyz, uint8_t* pc2, cudaStream_t st, int nf = 1,
                           size_t d_stride = 0, size_t color_stride = 0, size_t xyz_stride = 0, size_t pc2_stride = 0,
-                          const PtrList* pc2_list = nullptr);
+                          const PtrList* pc2_list = nullptr, const ReprojectExtras* extra = nullptr);
 int launch_disparity_color(const int16_t* d16, uint8_t* bgra, int n, int nd, cudaStream_t st);
 
 // ---- intpeak.cu -------------------------------------------------------------------------------------

@@ -89,11 +89,12 @@ __device__ __forceinline__ int2 map_at(const void* __restrict__ map, const CamMo
 template <int MODE, int CH>
 __global__ void __launch_bounds__(256) remap_kernel(const uint8_t* __restrict__ src, int sW, int sH,
                                                     const void* __restrict__ map, CamModel cm,
-                                                    uint8_t* __restrict__ dst, int W, int H, size_t src_stride, size_t dst_stride)
+                                                    uint8_t* __restrict__ dst, int W, int H, size_t src_stride, size_t dst_stride,
+                                                    const uint8_t* const* __restrict__ src_tab)
 {
     int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= W || y >= H) return;
-    src += blockIdx.z * src_stride;
+    src = src_tab ? src_tab[blockIdx.z] : src + blockIdx.z * src_stride;
     dst += blockIdx.z * dst_stride;
     const int2 m = map_at<MODE>(map, cm, x, y, W);
 #pragma unroll
@@ -130,7 +131,16 @@ struct RectSide {
 };
 struct BatchStrides {      // bytes between consecutive frames of a batch (blockIdx.z = 2 * frame + side)
     size_t src, rect, pre;
+    // optional device-resident tables of per-frame source addresses (frames that are not one strided buffer, e.g. the
+    // caller's own device images): tabL[f] / tabR[f] replace src + f * stride
+    const uint8_t* const* tabL;
+    const uint8_t* const* tabR;
 };
+__device__ __forceinline__ const uint8_t* frame_src(const RectSide& S, const BatchStrides& bs, int side, int frame)
+{
+    const uint8_t* const* tab = side ? bs.tabR : bs.tabL;
+    return tab ? tab[frame] : S.src + frame * bs.src;
+}
 
 // blockIdx.z selects frame and side, so that one launch rectifies and prefilters the left and the right images of a
 // whole batch.  Each thread first fetches (or evaluates) the map entries of its FT_PER tile pixels, then issues all
@@ -143,7 +153,7 @@ __global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSi
     __shared__ __align__(16) uint8_t tile[FTY + 2][FTX + 2 + 2];
     const RectSide& S = (blockIdx.z & 1) ? sr : sl;
     const int frame = blockIdx.z >> 1;
-    const uint8_t* __restrict__ src = S.src + frame * bs.src;
+    const uint8_t* __restrict__ src = frame_src(S, bs, blockIdx.z & 1, frame);
     const int x0 = blockIdx.x * FTX, y0 = blockIdx.y * FTY;
     int2 m[FT_PER];
     bool ok[FT_PER];
@@ -252,7 +262,7 @@ __global__ void __launch_bounds__(256) norm_prefilter_kernel(RectSide sl, RectSi
     __shared__ __align__(16) uint16_t vs[NTY][NTW];
     const RectSide& S = (blockIdx.z & 1) ? sr : sl;
     const int frame = blockIdx.z >> 1;
-    const uint8_t* __restrict__ src = S.src + frame * bs.src;
+    const uint8_t* __restrict__ src = frame_src(S, bs, blockIdx.z & 1, frame);
     const int x0 = blockIdx.x * NTX, y0 = blockIdx.y * NTY;
     const int tw = NTX + 2 * p2, th = NTY + 2 * p2, tn = tw * th;
     for (int i0 = threadIdx.x; i0 < tn; i0 += 4 * 256) {
@@ -332,7 +342,8 @@ static inline dim3 grid2d(int W, int H, int nf = 1) { return dim3((W + 31) / 32,
 int launch_norm_prefilter_pair(const uint8_t* srcL, const uint8_t* srcR, int sW, int sH, MapMode mode, const void* mapL,
                                const void* mapR, const CamModel& cmL, const CamModel& cmR, uint8_t* rectL, uint8_t* rectR,
                                uint8_t* preL, uint8_t* preR, size_t pre_pitch, int W, int H, int ps, int cap, cudaStream_t st,
-                               int nf, size_t src_stride, size_t rect_stride, size_t pre_stride)
+                               int nf, size_t src_stride, size_t rect_stride, size_t pre_stride, const uint8_t* const* tabL,
+                               const uint8_t* const* tabR)
 {
     const int p2 = ps / 2;
     if (p2 > NP2MAX) return 0;
@@ -340,7 +351,7 @@ int launch_norm_prefilter_pair(const uint8_t* srcL, const uint8_t* srcR, int sW,
     scale_g *= scale_s;
     dim3 g((W + NTX - 1) / NTX, (H + NTY - 1) / NTY, 2 * nf);
     RectSide l{srcL, mapL, rectL, preL, cmL}, r{srcR, mapR, rectR, preR, cmR};
-    BatchStrides bs{src_stride, rect_stride, pre_stride};
+    BatchStrides bs{src_stride, rect_stride, pre_stride, tabL, tabR};
     switch (mode) {
     case MAP_NONE: norm_prefilter_kernel<MAP_NONE><<<g, 256, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, p2, scale_g, scale_s, cap); break;
     case MAP_ABS32: norm_prefilter_kernel<MAP_ABS32><<<g, 256, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, p2, scale_g, scale_s, cap); break;
@@ -363,23 +374,23 @@ int launch_build_map(const CamModel& cm, int W, int H, void* map, MapMode mode, 
 
 template <int CH>
 static void launch_remap_ch(const uint8_t* src, int sW, int sH, const void* map, MapMode mode, const CamModel& cm, uint8_t* dst,
-                            int W, int H, cudaStream_t st, int nf, size_t ss, size_t ds)
+                            int W, int H, cudaStream_t st, int nf, size_t ss, size_t ds, const uint8_t* const* tab)
 {
     const dim3 g = grid2d(W, H, nf);
     switch (mode) {
-    case MAP_ABS32: remap_kernel<MAP_ABS32, CH><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H, ss, ds); break;
-    case MAP_DELTA16: remap_kernel<MAP_DELTA16, CH><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H, ss, ds); break;
-    default: remap_kernel<MAP_FLY, CH><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H, ss, ds); break;
+    case MAP_ABS32: remap_kernel<MAP_ABS32, CH><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H, ss, ds, tab); break;
+    case MAP_DELTA16: remap_kernel<MAP_DELTA16, CH><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H, ss, ds, tab); break;
+    default: remap_kernel<MAP_FLY, CH><<<g, 256, 0, st>>>(src, sW, sH, map, cm, dst, W, H, ss, ds, tab); break;
     }
 }
 
 int launch_remap(const uint8_t* src, int sW, int sH, int ch, const void* map, MapMode mode, const CamModel& cm, uint8_t* dst,
-                 int W, int H, cudaStream_t st, int nf, size_t src_stride, size_t dst_stride)
+                 int W, int H, cudaStream_t st, int nf, size_t src_stride, size_t dst_stride, const uint8_t* const* src_tab)
 {
     if (!map) mode = MAP_FLY;
-    if (ch == 1) launch_remap_ch<1>(src, sW, sH, map, mode, cm, dst, W, H, st, nf, src_stride, dst_stride);
-    else if (ch == 3) launch_remap_ch<3>(src, sW, sH, map, mode, cm, dst, W, H, st, nf, src_stride, dst_stride);
-    else if (ch == 4) launch_remap_ch<4>(src, sW, sH, map, mode, cm, dst, W, H, st, nf, src_stride, dst_stride);
+    if (ch == 1) launch_remap_ch<1>(src, sW, sH, map, mode, cm, dst, W, H, st, nf, src_stride, dst_stride, src_tab);
+    else if (ch == 3) launch_remap_ch<3>(src, sW, sH, map, mode, cm, dst, W, H, st, nf, src_stride, dst_stride, src_tab);
+    else if (ch == 4) launch_remap_ch<4>(src, sW, sH, map, mode, cm, dst, W, H, st, nf, src_stride, dst_stride, src_tab);
     else return -1;
     return 1;
 }
@@ -394,11 +405,12 @@ int launch_remap_nearest(const uint8_t* src, int sW, int sH, int ch, const CamMo
 int launch_rectify_xsobel_pair(const uint8_t* srcL, const uint8_t* srcR, int sW, int sH, MapMode mode, const void* mapL,
                                const void* mapR, const CamModel& cmL, const CamModel& cmR, uint8_t* rectL, uint8_t* rectR,
                                uint8_t* preL, uint8_t* preR, size_t pre_pitch, int W, int H, int cap, cudaStream_t st,
-                               int nf, size_t src_stride, size_t rect_stride, size_t pre_stride)
+                               int nf, size_t src_stride, size_t rect_stride, size_t pre_stride, const uint8_t* const* tabL,
+                               const uint8_t* const* tabR)
 {
     dim3 g((W + FTX - 1) / FTX, (H + FTY - 1) / FTY, 2 * nf);
     RectSide l{srcL, mapL, rectL, preL, cmL}, r{srcR, mapR, rectR, preR, cmR};
-    BatchStrides bs{src_stride, rect_stride, pre_stride};
+    BatchStrides bs{src_stride, rect_stride, pre_stride, tabL, tabR};
     switch (mode) {
     case MAP_NONE: rectify_xsobel_kernel<MAP_NONE><<<g, 256, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
     case MAP_ABS32: rectify_xsobel_kernel<MAP_ABS32><<<g, 256, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;

@@ -70,17 +70,22 @@ __global__ void __launch_bounds__(256) reproject_pack_kernel(const int16_t* __re
                                                              const double* __restrict__ Q, const int* __restrict__ min_d16,
                                                              const uint8_t* __restrict__ color, int ch,
                                                              float* __restrict__ xyz, uint8_t* __restrict__ pc2, unsigned qmask,
-                                                             size_t d_stride, size_t color_stride, size_t xyz_stride, const FrameDst fd)
+                                                             size_t d_stride, size_t color_stride, size_t xyz_stride, const FrameDst fd,
+                                                             int dmin_const, float* __restrict__ df, const FrameDst fdf,
+                                                             const uint8_t* const* __restrict__ color_tab)
 {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     {
         const int f = blockIdx.z;          // frame of the batch
         d16 = (const int16_t*)((const uint8_t*)d16 + f * d_stride);
-        if (color) color += f * color_stride;
+        if (color_tab) color = color_tab[f];
+        else if (color) color += f * color_stride;
         if (xyz) xyz = (float*)((uint8_t*)xyz + f * xyz_stride);
         if (fd.use_list) pc2 = (uint8_t*)fd.list.p[f];
         else if (pc2) pc2 += f * fd.stride;
-        min_d16 += f;
+        if (fdf.use_list) df = (float*)fdf.list.p[f];
+        else if (df) df = (float*)((uint8_t*)df + f * fdf.stride);
+        if (min_d16) min_d16 += f;
     }
     // One PointCloud2 record = 32 bytes = two 16-byte halves, [x y z 0] and [bgr 0 0 0].  The 32 records of a warp are
     // 1 KiB contiguous; lanes exchange halves so that each of the two store instructions of the warp writes 512
@@ -91,7 +96,8 @@ __global__ void __launch_bounds__(256) reproject_pack_kernel(const int16_t* __re
     float p[3] = {0.f, 0.f, 0.f};
     const bool inside = x < W && y < H;
     const size_t i = inside ? (size_t)y * W + x : 0;
-    const int dv = inside ? (int)d16[i] : 0, dmin = *min_d16;
+    const int dv = inside ? (int)d16[i] : 0, dmin = min_d16 ? *min_d16 : dmin_const;
+    if (df && inside) df[i] = disp_to_float(dv, cxd);      // the DisparityImage payload from the same pass (convertTo)
     // missing value (d == min over the image): cv::reprojectImageTo3D sets Z = 10000, which isValidPoint rejects, so the
     // record is NaN xyz + colour whatever X and Y were; no arithmetic needed unless the xyz plane is wanted too
     if (inside && (xyz || dv != dmin)) {
@@ -193,12 +199,15 @@ int launch_disparity_to_float(const int16_t* d16, float* df, int n, double cxd, 
 
 int launch_reproject_pack(const int16_t* d16, int W, int H, double cxd, const double* Q, unsigned qmask, const int* min_d16,
                           const uint8_t* color, int ch, float* xyz, uint8_t* pc2, cudaStream_t st, int nf, size_t d_stride,
-                          size_t color_stride, size_t xyz_stride, size_t pc2_stride, const PtrList* pc2_list)
+                          size_t color_stride, size_t xyz_stride, size_t pc2_stride, const PtrList* pc2_list, const ReprojectExtras* extra)
 {
     dim3 g((W + 31) / 32, (H + 7) / 8, nf);
     if (pc2_list && !pc2) pc2 = (uint8_t*)pc2_list->p[0];     // the kernel tests pc2 for "records wanted"
+    ReprojectExtras ex;
+    if (extra) ex = *extra;
     reproject_pack_kernel<<<g, 256, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask, d_stride, color_stride,
-                                             xyz_stride, frame_dst(pc2_stride, pc2_list));
+                                             xyz_stride, frame_dst(pc2_stride, pc2_list), ex.dmin_const, ex.df,
+                                             frame_dst(ex.df_stride, ex.df_list), ex.color_tab);
     return 1;
 }
 

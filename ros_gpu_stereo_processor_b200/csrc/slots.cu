@@ -28,20 +28,29 @@ void stage_mark(b200s_handle* h, Work& w, int i, cudaStream_t st)
     cudaEventRecord(w.ev_stage[i], st);
 }
 
-// everything of a batch after the inputs are on the device: rectify -> disparity -> float / reproject+pack -> outputs.
-// L / R / C: first frame of the input planes, frames `in_stride` (`c_stride`) bytes apart.
-int run_frame_chain(b200s_handle* h, Work& w, int nf, const b200s_frame_io* ios, const uint8_t* L, const uint8_t* R,
-                    size_t in_stride, const uint8_t* Craw, size_t c_stride, cudaStream_t st)
+// Per-frame input addresses live in a small device table inside w.misc (after the per-frame minima): the kernels of the
+// chain read tab[frame], so the caller's own device images are used in place and a captured graph does not depend on
+// where the inputs are -- only the table is rewritten (one small H2D copy) when the addresses change.
+constexpr size_t MISC_TAB_OFFSET = 256, MISC_BYTES = MISC_TAB_OFFSET + 3 * MAX_BATCH * sizeof(void*);
+const uint8_t* const* tab_of(const Work& w, int which /*0 L, 1 R, 2 colour*/)
+{
+    return (const uint8_t* const*)((const uint8_t*)w.misc.p + MISC_TAB_OFFSET) + which * MAX_BATCH;
+}
+
+// everything of a batch after the input table is set: rectify -> disparity -> float / reproject+pack -> outputs
+int run_frame_chain(b200s_handle* h, Work& w, int nf, const b200s_frame_io* ios, bool have_color, cudaStream_t st)
 {
     const b200s_frame_io* io = &ios[0];
     const int rows = h->slot_rows, cols = h->slot_cols;
     const size_t n = (size_t)rows * cols;
     const SlotLayout& lay = h->lay;
     const size_t pstride = plane_stride(cols, rows);
-    const bool have_color = Craw != nullptr;
     bool prefiltered = false;
-    const uint8_t *rl = L, *rr = R, *rc_color = Craw;
-    size_t rect_stride = in_stride, rcol_stride = c_stride;
+    const uint8_t* const* tabL = tab_of(w, 0);
+    const uint8_t* const* tabR = tab_of(w, 1);
+    const uint8_t* const* tabC = have_color ? tab_of(w, 2) : nullptr;
+    const uint8_t *rl = nullptr, *rr = nullptr, *rc_color = nullptr;
+    size_t rect_stride = 0, rcol_stride = 0;
     stage_mark(h, w, 0, st);
     if (io->rectify) {
         if (w.rectL.ensure(lay.raw * w.depth) || w.rectR.ensure(lay.raw * w.depth)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (rectified planes)");
@@ -57,22 +66,22 @@ int run_frame_chain(b200s_handle* h, Work& w, int nf, const b200s_frame_io* ios,
         uint8_t* pl = (uint8_t*)w.preL.p + PLANE_LEAD;
         uint8_t* pr = (uint8_t*)w.preR.p + PLANE_LEAD;
         if (same_mode && h->prm.pre_filter_type == 1) {
-            h->launches += launch_rectify_xsobel_pair(L, R, cols, rows, mode, mapL, mapR, h->cam[0].cm, h->cam[1].cm, (uint8_t*)w.rectL.p,
-                                                      (uint8_t*)w.rectR.p, pl, pr, plane_pitch(cols), cols, rows, h->prm.pre_filter_cap,
-                                                      st, nf, in_stride, lay.raw, pstride);
+            h->launches += launch_rectify_xsobel_pair(nullptr, nullptr, cols, rows, mode, mapL, mapR, h->cam[0].cm, h->cam[1].cm,
+                                                      (uint8_t*)w.rectL.p, (uint8_t*)w.rectR.p, pl, pr, plane_pitch(cols), cols, rows,
+                                                      h->prm.pre_filter_cap, st, nf, 0, lay.raw, pstride, tabL, tabR);
             prefiltered = true;
         } else {
             int one = 0;
             if (same_mode && h->prm.pre_filter_type == 0 && h->prm.pre_filter_size <= 21)
-                one = launch_norm_prefilter_pair(L, R, cols, rows, mode, mapL, mapR, h->cam[0].cm, h->cam[1].cm, (uint8_t*)w.rectL.p,
-                                                 (uint8_t*)w.rectR.p, pl, pr, plane_pitch(cols), cols, rows, h->prm.pre_filter_size,
-                                                 h->prm.pre_filter_cap, st, nf, in_stride, lay.raw, pstride);
+                one = launch_norm_prefilter_pair(nullptr, nullptr, cols, rows, mode, mapL, mapR, h->cam[0].cm, h->cam[1].cm,
+                                                 (uint8_t*)w.rectL.p, (uint8_t*)w.rectR.p, pl, pr, plane_pitch(cols), cols, rows,
+                                                 h->prm.pre_filter_size, h->prm.pre_filter_cap, st, nf, 0, lay.raw, pstride, tabL, tabR);
             if (one) {
                 h->launches += one;
                 prefiltered = true;
             } else {
-                h->launches += launch_remap(L, cols, rows, 1, mapL, mode, h->cam[0].cm, (uint8_t*)w.rectL.p, cols, rows, st, nf, in_stride, lay.raw);
-                h->launches += launch_remap(R, cols, rows, 1, mapR, modeR, h->cam[1].cm, (uint8_t*)w.rectR.p, cols, rows, st, nf, in_stride, lay.raw);
+                h->launches += launch_remap(nullptr, cols, rows, 1, mapL, mode, h->cam[0].cm, (uint8_t*)w.rectL.p, cols, rows, st, nf, 0, lay.raw, tabL);
+                h->launches += launch_remap(nullptr, cols, rows, 1, mapR, modeR, h->cam[1].cm, (uint8_t*)w.rectR.p, cols, rows, st, nf, 0, lay.raw, tabR);
             }
         }
         rl = (const uint8_t*)w.rectL.p;
@@ -81,13 +90,14 @@ int run_frame_chain(b200s_handle* h, Work& w, int nf, const b200s_frame_io* ios,
         if (have_color) {
             // the colour image feeds the point cloud (src/StereoProcessor.cpp:201-217: L_RECT_COLOR -> enqueueSendPoints)
             if (w.rectC.ensure(lay.rawc * w.depth)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (rectified colour plane)");
-            h->launches += launch_remap(Craw, cols, rows, 3, mapL, mode, h->cam[0].cm, (uint8_t*)w.rectC.p, cols, rows, st, nf, c_stride, lay.rawc);
+            h->launches += launch_remap(nullptr, cols, rows, 3, mapL, mode, h->cam[0].cm, (uint8_t*)w.rectC.p, cols, rows, st, nf, 0, lay.rawc, tabC);
             rc_color = (const uint8_t*)w.rectC.p;
             rcol_stride = lay.rawc;
         }
     }
     if (w.disp.ensure(lay.disp * w.depth)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (disparity plane)");
-    int rc = run_disparity(h, w, rl, rr, prefiltered, rows, cols, (int16_t*)w.disp.p, st, nf, rect_stride, lay.disp);
+    int rc = run_disparity(h, w, rl, rr, prefiltered, rows, cols, (int16_t*)w.disp.p, st, nf, rect_stride, lay.disp, rl ? nullptr : tabL,
+                           rr ? nullptr : tabR);
     if (rc) return rc;
     h->stats_frames += nf - 1;
     stage_mark(h, w, 3, st);
@@ -106,25 +116,38 @@ int run_frame_chain(b200s_handle* h, Work& w, int nf, const b200s_frame_io* ios,
         pc_direct = pc_direct && pc_list.p[f];
     }
     for (int f = nf; f < MAX_BATCH; ++f) df_list.p[f] = pc_list.p[f] = nullptr;
-    if (want_df || want_pc || want_xyz) {
-        rc = ensure_misc(h, w);
-        if (rc) return rc;
-        if (want_df && !df_direct && w.df.ensure(lay.df * w.depth)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (float disparity)");
-        h->launches += launch_disparity_to_float((const int16_t*)w.disp.p, want_df && !df_direct ? (float*)w.df.p : nullptr, (int)n,
+    // The float disparity plane (DisparityImage payload) comes out of the reproject + pack pass over d16; the missing value
+    // of cv::reprojectImageTo3D (= the minimum of the plane) is FILTERED for every plane this chain produces, because the
+    // border columns always hold it -- no reduction pass.  Only a lone float plane still uses the conversion kernel.
+    const int filtered = (h->prm.min_disparity - 1) * 16;
+    if (want_df && !df_direct && w.df.ensure(lay.df * w.depth)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (float disparity)");
+    if (want_df && !(want_pc || want_xyz))
+        h->launches += launch_disparity_to_float((const int16_t*)w.disp.p, !df_direct ? (float*)w.df.p : nullptr, (int)n,
                                                  h->model_ok ? h->cxd : 0.0, (int*)w.misc.p, st, nf, lay.disp, lay.df,
                                                  df_direct ? &df_list : nullptr);
-    }
     stage_mark(h, w, 4, st);
     if (want_pc || want_xyz) {
         if (want_pc && !pc_direct && w.pc2.ensure(lay.pc2 * w.depth)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (point cloud)");
         if (want_xyz && w.xyz.ensure(lay.xyz * w.depth)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (points)");
+        ReprojectExtras ex;
+        ex.dmin_const = filtered;
+        if (want_df) {
+            ex.df = df_direct ? nullptr : (float*)w.df.p;
+            ex.df_stride = lay.df;
+            ex.df_list = df_direct ? &df_list : nullptr;
+        }
+        // colour of the records: the rectified colour image, else the rectified grey image, else (rectify = 0) the inputs
         const uint8_t* col = have_color ? rc_color : rl;
+        size_t col_stride = have_color ? rcol_stride : rect_stride;
+        if (!col) ex.color_tab = have_color ? tabC : tabL;
         h->launches += launch_reproject_pack((const int16_t*)w.disp.p, cols, rows, h->cxd, (const double*)h->Qdev.p, h->qmask,
-                                             (const int*)w.misc.p, col, have_color ? 3 : 1, want_xyz ? (float*)w.xyz.p : nullptr,
-                                             want_pc && !pc_direct ? (uint8_t*)w.pc2.p : nullptr, st, nf, lay.disp,
-                                             have_color ? rcol_stride : rect_stride, lay.xyz, lay.pc2, pc_direct ? &pc_list : nullptr);
+                                             nullptr, col, have_color ? 3 : 1, want_xyz ? (float*)w.xyz.p : nullptr,
+                                             want_pc && !pc_direct ? (uint8_t*)w.pc2.p : nullptr, st, nf, lay.disp, col_stride, lay.xyz,
+                                             lay.pc2, pc_direct ? &pc_list : nullptr, &ex);
     }
     stage_mark(h, w, 5, st);
+    rc = ensure_misc(h, w);
+    if (rc) return rc;
     rc = check_kernels(h, "process_pair");
     if (rc) return rc;
     for (int f = 0; f < nf; ++f) {
@@ -242,39 +265,54 @@ int b200s_process_batch_async(b200s_handle* h, int slot, int n_frames, const voi
     if (io->rectify && (h->cam[0].info.width != cols || h->cam[0].info.height != rows))
         return fail(h, B200S_EINVAL, "slot size differs from the calibration size");
     const bool graphs = h->use_graphs && !h->timing;
-    // inputs: host frames always go through the slot's raw planes; batches and graph replay put device frames there
-    // too, so that the kernels see one strided buffer at fixed addresses
-    const uint8_t *L = (const uint8_t*)left[0], *R = (const uint8_t*)right[0], *Craw = (const uint8_t*)io->color_left;
-    size_t in_stride = 0, c_stride = 0;
-    const bool stage_inputs = !io->inputs_on_device || graphs || nf > 1 || (with_color && (!left[0] || io->color_encoding == B200S_COLOR_RGB8));
-    if (stage_inputs) {
-        const SlotLayout& lay = h->lay;
-        if (w.rawL.ensure(lay.raw * w.depth) || w.rawR.ensure(lay.raw * w.depth)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (input planes)");
-        if (with_color && w.rawC.ensure(lay.rawc * w.depth)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (colour input planes)");
-        const cudaMemcpyKind kind = io->inputs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-        for (int f = 0; f < nf; ++f) {
-            if (left[f]) CUDA_OK(h, cudaMemcpyAsync((uint8_t*)w.rawL.p + f * lay.raw, left[f], n, kind, st));
-            CUDA_OK(h, cudaMemcpyAsync((uint8_t*)w.rawR.p + f * lay.raw, right[f], n, kind, st));
-            if (with_color) CUDA_OK(h, cudaMemcpyAsync((uint8_t*)w.rawC.p + f * lay.rawc, ios[f].color_left, 3 * n, kind, st));
-        }
-        if (with_color) {
-            // convertRawToColor / convertRawToMono of a colour camera (src/GPUStereoProcessor.cpp:65-88): the slot keeps BGR,
-            // the matcher's grey image comes from it when no separate mono image was given
-            for (int f = 0; f < nf; ++f) {
-                uint8_t* cf = (uint8_t*)w.rawC.p + f * lay.rawc;
-                if (io->color_encoding == B200S_COLOR_RGB8) h->launches += launch_swap_rb(cf, cf, (int)n, st);
-                if (!left[f]) h->launches += launch_bgr_to_gray(cf, (uint8_t*)w.rawL.p + f * lay.raw, (int)n, 0, st);
-            }
-            Craw = (const uint8_t*)w.rawC.p;
-            c_stride = lay.rawc;
-        }
-        L = (const uint8_t*)w.rawL.p;
-        R = (const uint8_t*)w.rawR.p;
-        in_stride = lay.raw;
+    // Inputs.  Host frames are copied into the slot's raw planes; device frames are read where they are.  Either way the
+    // kernels get the addresses from the slot's device table, which is rewritten only when it changes.
+    const SlotLayout& lay = h->lay;
+    if (w.misc.ensure(MISC_BYTES)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (misc)");
+    const void* tab[3 * MAX_BATCH];
+    memset(tab, 0, sizeof tab);
+    const bool host_in = !io->inputs_on_device;
+    if (host_in || with_color) {
+        if ((host_in || !left[0]) && (w.rawL.ensure(lay.raw * w.depth))) return fail(h, B200S_ENOMEM, "cudaMalloc failed (input planes)");
+        if (host_in && w.rawR.ensure(lay.raw * w.depth)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (input planes)");
+        if (with_color && (host_in || io->color_encoding == B200S_COLOR_RGB8) && w.rawC.ensure(lay.rawc * w.depth))
+            return fail(h, B200S_ENOMEM, "cudaMalloc failed (colour input planes)");
     }
+    for (int f = 0; f < nf; ++f) {
+        const void *l = left[f], *r = right[f], *c = with_color ? ios[f].color_left : nullptr;
+        if (host_in) {
+            if (l) CUDA_OK(h, cudaMemcpyAsync((uint8_t*)w.rawL.p + f * lay.raw, l, n, cudaMemcpyHostToDevice, st));
+            CUDA_OK(h, cudaMemcpyAsync((uint8_t*)w.rawR.p + f * lay.raw, r, n, cudaMemcpyHostToDevice, st));
+            if (c) CUDA_OK(h, cudaMemcpyAsync((uint8_t*)w.rawC.p + f * lay.rawc, c, 3 * n, cudaMemcpyHostToDevice, st));
+            if (l) l = (uint8_t*)w.rawL.p + f * lay.raw;
+            r = (uint8_t*)w.rawR.p + f * lay.raw;
+            if (c) c = (uint8_t*)w.rawC.p + f * lay.rawc;
+        }
+        if (c && io->color_encoding == B200S_COLOR_RGB8) {
+            // convertRawToColor of a colour camera (src/GPUStereoProcessor.cpp:65-88): the slot keeps BGR
+            uint8_t* cf = (uint8_t*)w.rawC.p + f * lay.rawc;
+            h->launches += launch_swap_rb((const uint8_t*)c, cf, (int)n, st);
+            c = cf;
+        }
+        if (c && !l) {
+            // convertRawToMono: the matcher's grey image comes from the colour image when no mono image was given
+            uint8_t* lf = (uint8_t*)w.rawL.p + f * lay.raw;
+            h->launches += launch_bgr_to_gray((const uint8_t*)c, lf, (int)n, 0, st);
+            l = lf;
+        }
+        tab[f] = l;
+        tab[MAX_BATCH + f] = r;
+        tab[2 * MAX_BATCH + f] = c;
+    }
+    if (w.tab_cache.size() != sizeof tab || memcmp(w.tab_cache.data(), tab, sizeof tab) != 0) {
+        // pageable source: the driver stages small host->device copies before cudaMemcpyAsync returns
+        CUDA_OK(h, cudaMemcpyAsync((uint8_t*)w.misc.p + MISC_TAB_OFFSET, tab, sizeof tab, cudaMemcpyHostToDevice, st));
+        w.tab_cache.assign((const char*)tab, sizeof tab);
+    }
+    memcpy(w.in_tab, tab, sizeof tab);
     int rc = B200S_OK;
     if (!graphs) {
-        rc = run_frame_chain(h, w, nf, ios, L, R, in_stride, Craw, c_stride, st);
+        rc = run_frame_chain(h, w, nf, ios, with_color, st);
     } else {
         const std::string key = frame_graph_key(h, nf, ios, with_color, true);
         GraphEntry* hit = nullptr;
@@ -294,7 +332,7 @@ int b200s_process_batch_async(b200s_handle* h, int slot, int n_frames, const voi
             if (!warm) {
                 // first frame of this kind on the slot: run eagerly (allocations, map build).  Slot buffers have fixed
                 // sizes and are never reallocated, so graphs captured earlier stay valid.
-                rc = run_frame_chain(h, w, nf, ios, L, R, in_stride, Craw, c_stride, st);
+                rc = run_frame_chain(h, w, nf, ios, with_color, st);
                 if (rc == B200S_OK) {
                     if (w.warm_keys.size() >= 8) w.warm_keys.erase(w.warm_keys.begin());
                     w.warm_keys.push_back(akey);
@@ -306,7 +344,7 @@ int b200s_process_batch_async(b200s_handle* h, int slot, int n_frames, const voi
                 cudaGraphExec_t exec = nullptr;
                 cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
                 if (e == cudaSuccess) {
-                    rc = run_frame_chain(h, w, nf, ios, L, R, in_stride, Craw, c_stride, st);
+                    rc = run_frame_chain(h, w, nf, ios, with_color, st);
                     e = cudaStreamEndCapture(st, &graph);
                     if (rc == B200S_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
                     if (graph) cudaGraphDestroy(graph);
@@ -319,7 +357,7 @@ int b200s_process_batch_async(b200s_handle* h, int slot, int n_frames, const voi
                     h->use_graphs = 0;
                     h->launches = l0;
                     h->stats_frames = f0;
-                    rc = run_frame_chain(h, w, nf, ios, L, R, in_stride, Craw, c_stride, st);
+                    rc = run_frame_chain(h, w, nf, ios, with_color, st);
                 } else {
                     if ((int)w.graphs.size() >= MAX_GRAPHS_PER_SLOT) {       // evict the least recently used graph
                         size_t lru = 0;

@@ -77,3 +77,35 @@ def test_product_never_touches_the_oracle():
                 assert "cv2" not in txt or f.endswith(".cu"), os.path.join(dirpath, f)
     out = subprocess.run(["ldd", os.path.join(pkg, "libb200stereo.so")], capture_output=True, text=True).stdout
     assert "liboracle" not in out and "opencv" not in out
+
+
+def test_ros_glue_compiles_against_stub_headers():
+    """The ROS 1 glue (ros/src: StereoProcessor, node, nodelet) and the cv::Mat adapters of the C++ facade pass a syntax
+    check against minimal stand-ins of the ROS / boost / OpenCV headers (tests/cpp/ros_stubs); ROS itself is absent here."""
+    inc = ["-I" + os.path.join(ROOT, "tests", "cpp", "ros_stubs"), "-I" + os.path.join(ROOT, "ros", "include"), "-I" + os.path.join(ROOT, "include")]
+    for src in ("ros/src/StereoProcessor.cpp", "ros/src/StereoProcessorNode.cpp", "ros/src/StereoProcessorNodelet.cpp"):
+        out = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror"] + inc + [os.path.join(ROOT, src)], capture_output=True, text=True)
+        assert out.returncode == 0, src + "\n" + out.stderr
+    out = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-DB200S_WITH_OPENCV"] + inc +
+                         [os.path.join(ROOT, "tests", "cpp", "opencv_adapters_check.cpp")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    # the topic and parameter surface of the reference (src/StereoProcessor.cpp:29-101) is all there
+    txt = open(os.path.join(ROOT, "ros", "src", "StereoProcessor.cpp")).read()
+    for name in ("left/image_mono", "right/image_mono", "left/image_color", "right/image_color", "left/rect_mono", "right/rect_mono",
+                 "left/rect_color", "right/rect_color", "disparity", "disparity_vis", "pointcloud", "queue_size", "approximate_sync",
+                 "camera_info_file_left", "camera_info_file_right", "publisher_queue_size"):
+        assert '"%s"' % name in txt, name
+
+
+def test_gpu_cfg_keeps_the_reference_parameters():
+    """cfg/GPU.cfg: every parameter of the reference's cfg/GPU.cfg:12-35 with the same name, type and default."""
+    txt = open(os.path.join(ROOT, "cfg", "GPU.cfg")).read()
+    ref = {"xsobel": ("bool_t", "False"), "refine_disparity": ("bool_t", "False"), "correlation_window_size": ("int_t", "15"),
+           "disparity_min": ("int_t", "0"), "disparity_range": ("int_t", "128"), "bilateral_filter": ("bool_t", "False"),
+           "filter_ndisp": ("int_t", "64"), "filter_radius": ("int_t", "3"), "filter_iters": ("int_t", "1"),
+           "filter_edge_threshold": ("double_t", "0.1"), "filter_max_disc_threshold": ("double_t", "0.2"), "filter_sigma_range": ("double_t", "10"),
+           "texture_threshold": ("double_t", "10"), "max_speckle_size": ("int_t", "800"), "max_speckle_diff": ("double_t", "5")}
+    for name, (typ, default) in ref.items():
+        m = re.search(r'gen\.add\("%s",\s*(\w+),\s*0,\s*"[^"]*",\s*([^,\)]+)' % name, txt)
+        assert m, name
+        assert m.group(1) == typ and m.group(2).strip() == default, (name, m.groups())
