@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200stereo.so")
-SOURCES = ["api.cu", "slots.cu", "rectify.cu", "prefilter.cu", "bm_sad.cu", "bm_ws.cu", "bm_vh.cu", "bm_cuda_compat.cu", "post.cu", "reproject.cu", "intpeak.cu"]
+SOURCES = ["api.cu", "slots.cu", "rectify.cu", "prefilter.cu", "bm_sad.cu", "bm_ws.cu", "bm_vh.cu", "bm_strip.cu", "bm_cuda_compat.cu", "post.cu", "reproject.cu", "intpeak.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-cudart", "static"]

@@ -348,7 +348,7 @@ int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, 
 
 int ensure_misc(b200s_handle* h, Work& w)
 {
-    if (w.misc.ensure(2048)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (misc)");
+    if (w.misc.ensure(MISC_BYTES)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (misc)");
     return B200S_OK;
 }
 

@@ -23,6 +23,9 @@ int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
 int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg, int r, int lofs,
                  int XA, int XB, int YA, int YB, int16_t* disp, int16_t* cost, cudaStream_t st, int nf, size_t pre_stride,
                  size_t disp_stride);
+int launch_bm_strips(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg, int r, int lofs,
+                     int xa0, int xa1, int ya, int yb, int16_t* disp, int16_t* cost, cudaStream_t st, int nf, size_t pre_stride,
+                     size_t disp_stride);
 
 __global__ void fill_s16_kernel(int16_t* p, size_t n, int16_t v)
 {
@@ -789,9 +792,21 @@ static int block_match_impl(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, 
         if (rc < 0) return -1;
         ws_done = rc == 1;
     }
+    // the two r-wide border strips of the L/R-check path: one fused launch (bm_strip.cu) when it applies
+    bool strips_done = false;
+    if (ws_done && XA - outX0 == g.r && outX1 - XB == g.r && g.rofs == 0) {
+        static const int use_strips = getenv("B200S_STRIPS") ? atoi(getenv("B200S_STRIPS")) : 1;
+        if (use_strips) {
+            int rc = launch_bm_strips(Lp, Rp, pitch, W, H, cfg, g.r, g.lofs, outX0 - g.lofs, XB - g.lofs, g.roiY0, g.roiY1, disp, cost, st,
+                                      nf, pre_stride, disp_stride);
+            if (rc < 0) return -1;
+            strips_done = rc == 1;
+        }
+    }
+    if (strips_done) return launches + 2;
     if (nf > 1) {
-        // a batch needs bm_vh (the border fill above is harmless to repeat frame by frame otherwise); the border strips
-        // of the L/R-check path go through the generic kernels frame by frame
+        // a batch needs bm_vh (the border fill above is harmless to repeat frame by frame otherwise); strips the fused
+        // kernel does not handle go through the generic kernels frame by frame
         if (!ws_done) return NOT_BATCHABLE;
         ++launches;
         for (int f = 0; f < nf; ++f) {

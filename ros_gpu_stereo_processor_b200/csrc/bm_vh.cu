@@ -458,6 +458,65 @@ static cudaError_t launch_vh2(const VhParams& P, dim3 grid, int nt, size_t smem,
     return cudaGetLastError();
 }
 
+// registers per thread of an instantiation (decides how many blocks share an SM), asked from the runtime once
+template <int R, int ND>
+static int vh_regs2()
+{
+    static int regs = 0;
+    if (!regs) {
+        cudaFuncAttributes a;
+        regs = cudaFuncGetAttributes(&a, bm_vh_kernel<R, ND>) == cudaSuccess && a.numRegs > 0 ? a.numRegs : 80;
+    }
+    return regs;
+}
+template <int R>
+static int vh_regs1(int nd)
+{
+    if (nd == 256) return vh_regs2<R, 256>();
+    if (nd == 128) return vh_regs2<R, 128>();
+    if (nd == 64) return vh_regs2<R, 64>();
+    return vh_regs2<R, 0>();
+}
+static int vh_regs(int r, int nd)
+{
+    switch (r) {
+    case 2: return vh_regs1<2>(nd);
+    case 3: return vh_regs1<3>(nd);
+    case 4: return vh_regs1<4>(nd);
+    case 5: return vh_regs1<5>(nd);
+    case 6: return vh_regs1<6>(nd);
+    case 7: return vh_regs1<7>(nd);
+    case 8: return vh_regs1<8>(nd);
+    case 9: return vh_regs1<9>(nd);
+    case 10: return vh_regs1<10>(nd);
+    default: return 80;
+    }
+}
+
+struct DeviceShape {       // what the planner needs to know about the GPU it launches on
+    int sms = 148, regs_per_sm = 65536, smem_per_sm = 228 * 1024, smem_per_block = 227 * 1024, threads_per_sm = 2048;
+};
+static const DeviceShape& device_shape()
+{
+    static DeviceShape shapes[64];
+    static bool known[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!known[dev]) {
+        DeviceShape d;
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) d.sms = v;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxRegistersPerMultiprocessor, dev) == cudaSuccess && v > 0) d.regs_per_sm = v;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) == cudaSuccess && v > 0) d.smem_per_sm = v;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && v > 0) d.smem_per_block = v;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxThreadsPerMultiProcessor, dev) == cudaSuccess && v > 0) d.threads_per_sm = v;
+        shapes[dev] = d;
+        known[dev] = true;
+    }
+    return shapes[dev];
+}
+
 template <int R>
 static cudaError_t launch_vh(const VhParams& P, dim3 grid, int nt, size_t smem, cudaStream_t st)
 {
@@ -478,11 +537,14 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
     const int G4 = nd / 4;
     static const int max_warps = getenv("B200S_VH_WARPS") ? atoi(getenv("B200S_VH_WARPS")) : 24;
     static const int stagers_env = getenv("B200S_STAGERS") ? atoi(getenv("B200S_STAGERS")) : 2;
-    static const int n_sm = getenv("B200S_WS_BLOCKS") ? atoi(getenv("B200S_WS_BLOCKS")) : 148;
+    const DeviceShape& gpu = device_shape();
+    static const int n_sm_env = getenv("B200S_WS_BLOCKS") ? atoi(getenv("B200S_WS_BLOCKS")) : 0;
+    const int n_sm = n_sm_env > 0 ? n_sm_env : gpu.sms;
+    const int regs = vh_regs(r, nd);
     static const int ncb_env = getenv("B200S_VH_NCB") ? atoi(getenv("B200S_VH_NCB")) : 0;
     static const int bands_env = getenv("B200S_VH_BANDS") ? atoi(getenv("B200S_VH_BANDS")) : 0;
     static const int verbose = getenv("B200S_VH_VERBOSE") ? atoi(getenv("B200S_VH_VERBOSE")) : 0;
-    const size_t smem_max = 227 * 1024 - 1024;
+    const size_t smem_max = (size_t)gpu.smem_per_block - 1024;
     const int X0base = XA - ((XA - r - lofs) & 3);
     const int need = XB - X0base;
     const int rows = YB - YA;
@@ -517,9 +579,9 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
         P.nVw = nVw; P.nWw = nWw; P.nSw = nSw;
         const int tilesX = (need + TW - 1) / TW;
         const int max_bands = std::max(1, rows / (2 * r + 4));
-        // Blocks that fit an SM together (80 registers per thread, shared memory incl. the 1 KiB system reservation).
+        // Blocks that fit an SM together (registers of this instantiation, shared memory incl. the 1 KiB system reservation).
         const int nthr = 32 * (nVw + nWw + nSw);
-        const int occ = std::max(1, std::min(std::min(65536 / (80 * nthr), (int)((228 * 1024) / (o + 1024))), 2048 / nthr));
+        const int occ = std::max(1, std::min(std::min(gpu.regs_per_sm / (regs * nthr), (int)(gpu.smem_per_sm / (o + 1024))), gpu.threads_per_sm / nthr));
         for (int bands = 1; bands <= max_bands; ++bands) {
             if (bands_env > 0 && bands != std::min(bands_env, max_bands)) continue;
             const int BH = (rows + bands - 1) / bands;

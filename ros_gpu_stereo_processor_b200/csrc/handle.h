@@ -192,6 +192,7 @@ int ensure_misc(b200s_handle* h, Work& w);
 int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, bool already_prefiltered, int rows, int cols,
                   int16_t* disp, cudaStream_t st, int nf = 1, size_t src_stride = 0, size_t disp_stride = 0,
                   const uint8_t* const* tabL = nullptr, const uint8_t* const* tabR = nullptr);
+constexpr size_t MISC_BYTES = 2048;   // per-frame minima (ints) + the per-frame input address table of the slot
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 inline size_t plane_stride(int cols, int rows) { return align256(plane_bytes(cols, rows)); }
 // Device-side alias of a pinned (page-locked, mapped) host buffer, or nullptr when `p` is pageable / not host memory

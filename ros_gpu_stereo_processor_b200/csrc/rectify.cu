@@ -5,6 +5,9 @@
 // (test/UTest.cpp:247-256).  Algorithm: SURVEY.md A.1.
 #include "kernels.h"
 
+#include <climits>
+#include <cstdint>
+
 namespace b200s {
 
 // (sx, sy) = (rint(float(u)*32), rint(float(v)*32)); every double op is an explicit round-to-nearest
@@ -121,6 +124,7 @@ __global__ void __launch_bounds__(256) remap_nearest_kernel(const uint8_t* __res
 constexpr int FTX = 64, FTY = 16;
 constexpr int FT_N = (FTX + 2) * (FTY + 2);          // tile + halo pixels
 constexpr int FT_PER = (FT_N + 255) / 256;           // pixels per thread
+constexpr int RECT_WIN_BYTES = 10240;                // shared-memory window of the source image per tile (e.g. 128 x 80)
 
 struct RectSide {
     const uint8_t* src;
@@ -151,6 +155,8 @@ __global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSi
                                                              size_t ppitch, int W, int H, int cap)
 {
     __shared__ __align__(16) uint8_t tile[FTY + 2][FTX + 2 + 2];
+    __shared__ __align__(16) uint8_t win[MODE != MAP_NONE ? RECT_WIN_BYTES : 16];
+    __shared__ int bbox[4];
     const RectSide& S = (blockIdx.z & 1) ? sr : sl;
     const int frame = blockIdx.z >> 1;
     const uint8_t* __restrict__ src = frame_src(S, bs, blockIdx.z & 1, frame);
@@ -168,6 +174,61 @@ __global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSi
         m[k] = make_int2(0, 0);
         if (ok[k]) m[k] = map_at<MODE>(S.map, S.cm, x, ys, W);
     }
+    // Source window of the tile: the 2x2 footprints of all tile pixels lie in a small bounding box of the source image
+    // (a smooth map moves a 66x18 tile to roughly 70x22 source pixels).  The block finds that box (min / max of the
+    // integer map parts), copies it into shared memory with coalesced 16-byte loads -- zeros outside the image, which is
+    // cv::remap's BORDER_CONSTANT -- and gathers the taps from there: 4 byte-LDS per pixel instead of 4 scattered global
+    // loads whose latency the kernel could not hide.  Boxes that do not fit (extreme maps) keep the global gathers.
+    bool staged = false;
+    int wx0 = 0, wy0 = 0, wpitch = 0;
+    if (MODE != MAP_NONE) {
+        int xmn = INT_MAX, xmx = INT_MIN, ymn = INT_MAX, ymx = INT_MIN;
+#pragma unroll
+        for (int k = 0; k < FT_PER; ++k)
+            if (ok[k]) {
+                const int X0 = sat16(m[k].x >> 5), Y0 = sat16(m[k].y >> 5);
+                xmn = min(xmn, X0); xmx = max(xmx, X0); ymn = min(ymn, Y0); ymx = max(ymx, Y0);
+            }
+        xmn = __reduce_min_sync(0xffffffffu, xmn); xmx = __reduce_max_sync(0xffffffffu, xmx);
+        ymn = __reduce_min_sync(0xffffffffu, ymn); ymx = __reduce_max_sync(0xffffffffu, ymx);
+        if (threadIdx.x == 0) { bbox[0] = INT_MAX; bbox[1] = INT_MIN; bbox[2] = INT_MAX; bbox[3] = INT_MIN; }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&bbox[0], xmn); atomicMax(&bbox[1], xmx); atomicMin(&bbox[2], ymn); atomicMax(&bbox[3], ymx);
+        }
+        __syncthreads();
+        xmn = bbox[0]; xmx = bbox[1]; ymn = bbox[2]; ymx = bbox[3];
+        if (xmn <= xmx) {
+            wx0 = xmn & ~15;                                   // floor to a multiple of 16 (also for negative x)
+            wy0 = ymn;
+            wpitch = (xmx + 2 - wx0 + 15) & ~15;
+            const int wh = ymx + 2 - ymn;
+            staged = (long long)wpitch * wh <= RECT_WIN_BYTES;
+            if (staged) {
+                const int upr = wpitch >> 4, nunits = upr * wh;
+                const bool vec = ((sW & 15) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+                for (int u = threadIdx.x; u < nunits; u += 256) {
+                    const int row = u / upr, cx = u - row * upr;
+                    const int y = wy0 + row, x = wx0 + 16 * cx;
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if ((unsigned)y < (unsigned)sH) {
+                        const uint8_t* p = src + (size_t)y * sW + x;
+                        if (vec && x >= 0 && x + 16 <= sW) {
+                            v = __ldg((const uint4*)p);
+                        } else {
+                            uint32_t w4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if ((unsigned)(x + j) < (unsigned)sW) w4[j >> 2] |= (uint32_t)__ldg(p + j) << (8 * (j & 3));
+                            v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                        }
+                    }
+                    *(uint4*)(win + (size_t)row * wpitch + 16 * cx) = v;
+                }
+            }
+        }
+        __syncthreads();
+    }
     int s00[FT_PER], s01[FT_PER], s10[FT_PER], s11[FT_PER];
 #pragma unroll
     for (int k = 0; k < FT_PER; ++k) {
@@ -176,7 +237,10 @@ __global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSi
         if (MODE == MAP_NONE) {
             if (ok[k]) s00[k] = __ldg(src + (size_t)Y0 * sW + X0);      // identity map: a = b = 0, only s00 counts
         } else if (ok[k]) {
-            if ((unsigned)X0 < (unsigned)(sW - 1) && (unsigned)Y0 < (unsigned)(sH - 1)) {
+            if (staged) {
+                const uint8_t* p = win + (Y0 - wy0) * wpitch + (X0 - wx0);
+                s00[k] = p[0]; s01[k] = p[1]; s10[k] = p[wpitch]; s11[k] = p[wpitch + 1];
+            } else if ((unsigned)X0 < (unsigned)(sW - 1) && (unsigned)Y0 < (unsigned)(sH - 1)) {
                 // the whole 2x2 footprint is inside the source image (the common case): no per-tap border test
                 const uint8_t* p = src + (size_t)Y0 * sW + X0;
                 s00[k] = __ldg(p); s01[k] = __ldg(p + 1); s10[k] = __ldg(p + sW); s11[k] = __ldg(p + sW + 1);

@@ -115,8 +115,24 @@ __global__ void __launch_bounds__(256) reproject_pack_kernel(const int16_t* __re
             if ((qmask >> (r * 4 + 3)) & 1u) s = __dadd_rn(s, __ldg(Q + r * 4 + 3));
             h[r] = s;
         }
+        // float(a / w) for the three coordinates, a = (double)(float)h[r].  The correctly rounded FP64 division is a long
+        // instruction sequence; all three share the divisor, so one correctly rounded reciprocal and a multiplication give a
+        // quotient within 2 ulp (FP64) of a / w, and rounding THAT to float gives the same float as rounding the exact
+        // quotient unless it lies within a few FP64 ulps of a float rounding boundary (29 dropped bits = 0x10000000).  Those
+        // rare lanes, and non-finite or tiny quotients, take the exact division: the result is bit-identical always.
+        {
+            const double rw = __drcp_rn(h[3]);
 #pragma unroll
-        for (int r = 0; r < 3; ++r) p[r] = __double2float_rn(__ddiv_rn((double)__double2float_rn(h[r]), h[3]));
+            for (int r = 0; r < 3; ++r) {
+                const double a = (double)__double2float_rn(h[r]);
+                const double q = __dmul_rn(a, rw);
+                const unsigned lo = (unsigned)__double2loint(q) & 0x1FFFFFFFu;
+                const unsigned hi = (unsigned)__double2hiint(q) & 0x7FFFFFFFu;
+                // |q| in [2^-100, 2^100] (finite, far from float denormals / overflow) and away from the rounding boundary
+                const bool safe = hi > 0x39B00000u && hi < 0x46300000u && (lo - 0x0FFFFFF0u) > 0x20u;
+                p[r] = __double2float_rn(safe ? q : __ddiv_rn(a, h[3]));
+            }
+        }
         if (fabs(__dadd_rn(d, -minDisp)) <= (double)1.1920928955078125e-07f) p[2] = 10000.0f;
         if (xyz) {
             xyz[i * 3] = p[0]; xyz[i * 3 + 1] = p[1]; xyz[i * 3 + 2] = p[2];

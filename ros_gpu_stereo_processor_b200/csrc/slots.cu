@@ -31,7 +31,8 @@ void stage_mark(b200s_handle* h, Work& w, int i, cudaStream_t st)
 // Per-frame input addresses live in a small device table inside w.misc (after the per-frame minima): the kernels of the
 // chain read tab[frame], so the caller's own device images are used in place and a captured graph does not depend on
 // where the inputs are -- only the table is rewritten (one small H2D copy) when the addresses change.
-constexpr size_t MISC_TAB_OFFSET = 256, MISC_BYTES = MISC_TAB_OFFSET + 3 * MAX_BATCH * sizeof(void*);
+constexpr size_t MISC_TAB_OFFSET = 256;      // after the per-frame minima; ensure_misc() sizes the buffer (MISC_BYTES, handle.h)
+static_assert(MISC_TAB_OFFSET + 3 * MAX_BATCH * sizeof(void*) <= MISC_BYTES, "misc buffer too small for the address table");
 const uint8_t* const* tab_of(const Work& w, int which /*0 L, 1 R, 2 colour*/)
 {
     return (const uint8_t* const*)((const uint8_t*)w.misc.p + MISC_TAB_OFFSET) + which * MAX_BATCH;
@@ -268,7 +269,10 @@ int b200s_process_batch_async(b200s_handle* h, int slot, int n_frames, const voi
     // Inputs.  Host frames are copied into the slot's raw planes; device frames are read where they are.  Either way the
     // kernels get the addresses from the slot's device table, which is rewritten only when it changes.
     const SlotLayout& lay = h->lay;
-    if (w.misc.ensure(MISC_BYTES)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (misc)");
+    {
+        int rcm = ensure_misc(h, w);      // one fixed size for the life of the slot: the table must never move
+        if (rcm) return rcm;
+    }
     const void* tab[3 * MAX_BATCH];
     memset(tab, 0, sizeof tab);
     const bool host_in = !io->inputs_on_device;
