@@ -324,8 +324,9 @@ class ConfigRun(object):
             self.proc.processBatchRaw(g % self.S, b)
 
     # ---- end-to-end leg: pinned host inputs and outputs, H2D + D2H inside the chain ----
-    def pinned(self, nbytes):
-        a, ptr = self.proc.hostAlloc(nbytes)
+    def pinned(self, nbytes, out=False):
+        # B200S_BENCH_WC=1: output buffers write-combined (experiment; CPU reads of such memory are slow)
+        a, ptr = self.proc.hostAlloc(nbytes, write_combined=out and os.environ.get("B200S_BENCH_WC") == "1")
         self.pins.append(ptr)
         return a, ptr
 
@@ -346,7 +347,7 @@ class ConfigRun(object):
                 ios[k].want, ios[k].rectify = self.want, int(self.c["rectify"])
                 ios[k].rows, ios[k].cols = self.H, self.W
                 for key, bit, es in self.products:
-                    v[key], ptr = self.pinned(n * es)
+                    v[key], ptr = self.pinned(n * es, out=True)
                     setattr(ios[k], key, ptr)
                 views.append(v)
             self.host_views.append(views)

@@ -289,8 +289,16 @@ int b200s_last_stage_times(b200s_handle* h, int slot, float* ms /* [B200S_STAGE_
 /* printStats (src/GPUStereoProcessor.cpp:421-435): per-channel min / max / mean of a named buffer, reduced on the GPU.
  * mn / mx / mean receive one value per channel (up to 4); *channels the channel count.  Syncs that side's stream. */
 int b200s_mat_stats(b200s_handle* h, int mat_id, double* mn, double* mx, double* mean, int* channels);
+/* Bare copy probe (no kernels): streams device->host copies of `bytes` round-robin into four page-locked host buffers on
+ * two streams for about `seconds` and returns the achieved GB/s -- the ceiling of the end-to-end path on this host, per
+ * GPU; run it from one process per GPU at the same time for the aggregate (tools/d2h_probe.py).  host_mode: 0 =
+ * cudaHostAlloc default, 1 = cudaHostAllocWriteCombined, 2 = malloc + cudaHostRegister.  with_h2d also streams a
+ * 4 MB host->device copy per D2H copy (the raw pair going in). */
+int b200s_copy_probe(int device, size_t bytes, double seconds, int host_mode, int with_h2d, double* d2h_gbs);
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA runtime of their own */
 int b200s_host_alloc(void** p, size_t bytes);
+/* mode 0 = cudaHostAllocDefault, 1 = cudaHostAllocWriteCombined (device writes bypass the CPU caches; CPU reads are slow) */
+int b200s_host_alloc_mode(void** p, size_t bytes, int mode);
 int b200s_host_free(void* p);
 /* integer-ALU micro-benchmark used for the roofline denominator: runs `which` (0 IADD3, 1 VABSDIFF4, 2 VIADD.16x2,
  * 3 VIMNMX.U16x2, 4 IMAD, 5 PRMT, 6 LOP3, 7 IADD3+IMAD mixed) and returns lane-ops per second */

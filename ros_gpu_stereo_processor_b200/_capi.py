@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200stereo.so")
+# B200S_LIB_SUFFIX selects an experimental build variant (ros_gpu_stereo_processor_b200/build.py); the product is the plain name
+LIB_PATH = os.path.join(HERE, "libb200stereo%s.so" % os.environ.get("B200S_LIB_SUFFIX", ""))
 
 # error codes (b200s_error)
 OK, EINVAL, ENOTINIT, ECUDA, ENOMEM, EUNSUPPORTED, EIO, ENOBUF = 0, -1, -2, -3, -4, -5, -6, -7
@@ -126,6 +127,8 @@ SYMBOLS = {
     "b200s_process_batch_async": (C.c_int, [H, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(FrameIO)]),
     "b200s_slot_frame_device_ptr": (C.c_int, [H, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "b200s_last_stage_times": (C.c_int, [H, C.c_int, C.POINTER(C.c_float)]),
+    "b200s_host_alloc_mode": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]),
+    "b200s_copy_probe": (C.c_int, [C.c_int, C.c_size_t, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "b200s_mat_stats": (C.c_int, [H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
 }
 

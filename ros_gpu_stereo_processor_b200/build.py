@@ -10,11 +10,13 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libb200stereo.so")
+# experiments: B200S_NVCC_DEFS="-DB200S_RECT_FTY=8 ..." with B200S_LIB_SUFFIX=_x builds libb200stereo_x.so beside the product
+SUFFIX = os.environ.get("B200S_LIB_SUFFIX", "")
+LIB = os.path.join(HERE, "libb200stereo%s.so" % SUFFIX)
 SOURCES = ["api.cu", "slots.cu", "rectify.cu", "prefilter.cu", "bm_sad.cu", "bm_ws.cu", "bm_vh.cu", "bm_strip.cu", "bm_cuda_compat.cu", "post.cu", "reproject.cu", "intpeak.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
-         "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-cudart", "static"]
+         "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-cudart", "static"] + os.environ.get("B200S_NVCC_DEFS", "").split()
 
 
 def _stale(target, deps):
@@ -25,7 +27,7 @@ def _stale(target, deps):
 
 
 def build_library(force=False, verbose=False):
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + SUFFIX)
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, "kernels.h"), os.path.join(CSRC, "handle.h"), os.path.join(CSRC, "bm_common.cuh"), os.path.join(HERE, "..", "include", "b200_stereo.h")]
     objs = []

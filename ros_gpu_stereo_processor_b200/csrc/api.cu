@@ -1047,6 +1047,12 @@ int b200s_host_alloc(void** p, size_t bytes)
     return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? B200S_OK : B200S_ENOMEM;
 }
 
+int b200s_host_alloc_mode(void** p, size_t bytes, int mode)
+{
+    if (!p) return B200S_EINVAL;
+    return cudaHostAlloc(p, bytes, mode == 1 ? cudaHostAllocWriteCombined : cudaHostAllocDefault) == cudaSuccess ? B200S_OK : B200S_ENOMEM;
+}
+
 int b200s_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? B200S_OK : B200S_ECUDA; }
 
 int b200s_int_peak(b200s_handle* h, int which, double* lane_ops_per_s, double* sm_clock_mhz)

@@ -85,8 +85,11 @@ constexpr int NC = 16;               // output columns per VH thread
 
 }  // namespace vh
 
+#ifndef B200S_VH_MAXT
+#define B200S_VH_MAXT 768     // register budget of the matcher = 65536 / this (rounded down to a multiple of 8)
+#endif
 template <int R, int ND>
-__global__ void __launch_bounds__(768, 1) bm_vh_kernel(const VhParams P)
+__global__ void __launch_bounds__(B200S_VH_MAXT, 1) bm_vh_kernel(const VhParams P)
 {
     using namespace vh;
     extern __shared__ __align__(16) uint8_t smem[];

@@ -121,9 +121,14 @@ __global__ void __launch_bounds__(256) remap_nearest_kernel(const uint8_t* __res
 // Tile of TX x TY output pixels; the block rectifies the tile plus a 1-pixel halo into shared memory,
 // writes the interior to `rect`, then applies OpenCV's prefilterXSobel border rules:
 // 3x3 Sobel-x with rows mirrored (reflect-101), columns 0 and W-1 = cap, odd-height last row = cap.
-constexpr int FTX = 64, FTY = 16;
+#ifndef B200S_RECT_FTY
+#define B200S_RECT_FTY 16
+#endif
+constexpr int FTX = 64, FTY = B200S_RECT_FTY;        // 16 tile rows = 256 threads; 8 rows = 128 threads (small enough in
+                                                     // registers to share an SM with a resident matcher block)
+constexpr int FT_THREADS = 16 * FTY;                 // the Sobel phase gives each thread 4 adjacent pixels of a row
 constexpr int FT_N = (FTX + 2) * (FTY + 2);          // tile + halo pixels
-constexpr int FT_PER = (FT_N + 255) / 256;           // pixels per thread
+constexpr int FT_PER = (FT_N + FT_THREADS - 1) / FT_THREADS;   // pixels per thread
 constexpr int RECT_WIN_BYTES = 10240;                // shared-memory window of the source image per tile (e.g. 128 x 80)
 
 struct RectSide {
@@ -151,7 +156,7 @@ __device__ __forceinline__ const uint8_t* frame_src(const RectSide& S, const Bat
 // 4*FT_PER gathers, then blends: the dependent global loads of different pixels overlap.
 // MODE = MAP_NONE: the source is already rectified (tile = source pixels, no rectified plane is written).
 template <int MODE>
-__global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSide sr, BatchStrides bs, int sW, int sH,
+__global__ void __launch_bounds__(FT_THREADS) rectify_xsobel_kernel(RectSide sl, RectSide sr, BatchStrides bs, int sW, int sH,
                                                              size_t ppitch, int W, int H, int cap)
 {
     __shared__ __align__(16) uint8_t tile[FTY + 2][FTX + 2 + 2];
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSi
     bool ok[FT_PER];
 #pragma unroll
     for (int k = 0; k < FT_PER; ++k) {
-        const int i = threadIdx.x + 256 * k;
+        const int i = threadIdx.x + FT_THREADS * k;
         const int ty = i / (FTX + 2), tx = i - ty * (FTX + 2);
         const int x = x0 + tx - 1, y = y0 + ty - 1;
         // rows are mirrored for the Sobel taps: the halo row above row 0 is row 1, below row H-1 is row H-2
@@ -207,7 +212,7 @@ __global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSi
             if (staged) {
                 const int upr = wpitch >> 4, nunits = upr * wh;
                 const bool vec = ((sW & 15) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-                for (int u = threadIdx.x; u < nunits; u += 256) {
+                for (int u = threadIdx.x; u < nunits; u += FT_THREADS) {
                     const int row = u / upr, cx = u - row * upr;
                     const int y = wy0 + row, x = wx0 + 16 * cx;
                     uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(256) rectify_xsobel_kernel(RectSide sl, RectSi
     }
 #pragma unroll
     for (int k = 0; k < FT_PER; ++k) {
-        const int i = threadIdx.x + 256 * k;
+        const int i = threadIdx.x + FT_THREADS * k;
         if (i >= FT_N) continue;
         const int ty = i / (FTX + 2), tx = i - ty * (FTX + 2);
         const int a = m[k].x & 31, b = m[k].y & 31;
@@ -476,10 +481,10 @@ int launch_rectify_xsobel_pair(const uint8_t* srcL, const uint8_t* srcR, int sW,
     RectSide l{srcL, mapL, rectL, preL, cmL}, r{srcR, mapR, rectR, preR, cmR};
     BatchStrides bs{src_stride, rect_stride, pre_stride, tabL, tabR};
     switch (mode) {
-    case MAP_NONE: rectify_xsobel_kernel<MAP_NONE><<<g, 256, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
-    case MAP_ABS32: rectify_xsobel_kernel<MAP_ABS32><<<g, 256, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
-    case MAP_DELTA16: rectify_xsobel_kernel<MAP_DELTA16><<<g, 256, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
-    default: rectify_xsobel_kernel<MAP_FLY><<<g, 256, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
+    case MAP_NONE: rectify_xsobel_kernel<MAP_NONE><<<g, FT_THREADS, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
+    case MAP_ABS32: rectify_xsobel_kernel<MAP_ABS32><<<g, FT_THREADS, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
+    case MAP_DELTA16: rectify_xsobel_kernel<MAP_DELTA16><<<g, FT_THREADS, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
+    default: rectify_xsobel_kernel<MAP_FLY><<<g, FT_THREADS, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
     }
     return 1;
 }

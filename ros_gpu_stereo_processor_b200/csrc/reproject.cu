@@ -66,7 +66,12 @@ __global__ void __launch_bounds__(256) disparity_to_float_kernel(const int16_t* 
     }
 }
 
-__global__ void __launch_bounds__(256) reproject_pack_kernel(const int16_t* __restrict__ d16, int W, int H, double cxd,
+#ifndef B200S_PACK_ROWS
+#define B200S_PACK_ROWS 8
+#endif
+constexpr int RP_ROWS = B200S_PACK_ROWS;      // block = 32 columns x RP_ROWS rows (one warp per row)
+
+__global__ void __launch_bounds__(32 * RP_ROWS) reproject_pack_kernel(const int16_t* __restrict__ d16, int W, int H, double cxd,
                                                              const double* __restrict__ Q, const int* __restrict__ min_d16,
                                                              const uint8_t* __restrict__ color, int ch,
                                                              float* __restrict__ xyz, uint8_t* __restrict__ pc2, unsigned qmask,
@@ -74,7 +79,7 @@ __global__ void __launch_bounds__(256) reproject_pack_kernel(const int16_t* __re
                                                              int dmin_const, float* __restrict__ df, const FrameDst fdf,
                                                              const uint8_t* const* __restrict__ color_tab)
 {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * RP_ROWS + (threadIdx.x >> 5);
     {
         const int f = blockIdx.z;          // frame of the batch
         d16 = (const int16_t*)((const uint8_t*)d16 + f * d_stride);
@@ -217,11 +222,11 @@ int launch_reproject_pack(const int16_t* d16, int W, int H, double cxd, const do
                           const uint8_t* color, int ch, float* xyz, uint8_t* pc2, cudaStream_t st, int nf, size_t d_stride,
                           size_t color_stride, size_t xyz_stride, size_t pc2_stride, const PtrList* pc2_list, const ReprojectExtras* extra)
 {
-    dim3 g((W + 31) / 32, (H + 7) / 8, nf);
+    dim3 g((W + 31) / 32, (H + RP_ROWS - 1) / RP_ROWS, nf);
     if (pc2_list && !pc2) pc2 = (uint8_t*)pc2_list->p[0];     // the kernel tests pc2 for "records wanted"
     ReprojectExtras ex;
     if (extra) ex = *extra;
-    reproject_pack_kernel<<<g, 256, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask, d_stride, color_stride,
+    reproject_pack_kernel<<<g, 32 * RP_ROWS, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask, d_stride, color_stride,
                                              xyz_stride, frame_dst(pc2_stride, pc2_list), ex.dmin_const, ex.df,
                                              frame_dst(ex.df_stride, ex.df_list), ex.color_tab);
     return 1;

@@ -596,6 +596,87 @@ int b200s_pool_wait_all(b200s_pool* p)
     });
 }
 
+// ---- bare copy probe: what the host side of PCIe absorbs with no kernels at all -----------------------------------
+int b200s_copy_probe(int device, size_t bytes, double seconds, int host_mode, int with_h2d, double* d2h_gbs)
+{
+    if (!d2h_gbs || bytes == 0 || seconds <= 0) return B200S_EINVAL;
+    DeviceGuard g(device);
+    void* dev = nullptr;
+    void* din = nullptr;
+    void* hin = nullptr;
+    void* host[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t st[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t e0 = nullptr, e1[2] = {nullptr, nullptr};
+    const size_t in_bytes = 4u << 20;
+    int rc = B200S_OK;
+    auto cleanup = [&]() {
+        for (void* p : host)
+            if (p) {
+                if (host_mode == 2) { cudaHostUnregister(p); free(p); }
+                else cudaFreeHost(p);
+            }
+        if (hin) cudaFreeHost(hin);
+        if (dev) cudaFree(dev);
+        if (din) cudaFree(din);
+        for (cudaStream_t s : st) if (s) cudaStreamDestroy(s);
+        if (e0) cudaEventDestroy(e0);
+        for (cudaEvent_t e : e1) if (e) cudaEventDestroy(e);
+    };
+    bool ok = cudaMalloc(&dev, bytes) == cudaSuccess && cudaMalloc(&din, in_bytes) == cudaSuccess &&
+              cudaHostAlloc(&hin, in_bytes, cudaHostAllocDefault) == cudaSuccess && cudaMemset(dev, 7, bytes) == cudaSuccess;
+    for (int i = 0; ok && i < 4; ++i) {
+        if (host_mode == 2) {
+            host[i] = aligned_alloc(4096, (bytes + 4095) & ~(size_t)4095);
+            ok = host[i] && cudaHostRegister(host[i], bytes, cudaHostRegisterDefault) == cudaSuccess;
+        } else {
+            ok = cudaHostAlloc(&host[i], bytes, host_mode == 1 ? cudaHostAllocWriteCombined : cudaHostAllocDefault) == cudaSuccess;
+        }
+        if (ok) memset(host[i], 0, bytes);      // touch the pages (placement follows the caller's memory policy)
+    }
+    for (int i = 0; ok && i < 3; ++i) ok = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1[0]) == cudaSuccess && cudaEventCreate(&e1[1]) == cudaSuccess;
+    if (!ok) { cleanup(); cudaGetLastError(); return B200S_ECUDA; }
+    for (int i = 0; i < 4; ++i) cudaMemcpyAsync(host[i], dev, bytes, cudaMemcpyDeviceToHost, st[i & 1]);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0, st[0]);
+    cudaStreamWaitEvent(st[1], e0, 0);
+    // fixed number of rounds sized from a short calibration, so that the timed region is pure copies
+    double gbs_guess = 20.0;
+    long rounds = (long)(seconds * gbs_guess * 1e9 / (4.0 * bytes)) + 1;
+    long copies = 0;
+    float ms = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        cudaDeviceSynchronize();
+        cudaEventRecord(e0, st[0]);
+        cudaStreamWaitEvent(st[1], e0, 0);
+        copies = 0;
+        for (long r = 0; r < rounds; ++r) {
+            for (int i = 0; i < 4; ++i) {
+                cudaMemcpyAsync(host[i], dev, bytes, cudaMemcpyDeviceToHost, st[i & 1]);
+                if (with_h2d) cudaMemcpyAsync(din, hin, in_bytes, cudaMemcpyHostToDevice, st[2]);
+                ++copies;
+            }
+            cudaStreamSynchronize(st[0]);       // at most four copies queued ahead
+        }
+        cudaEventRecord(e1[0], st[0]);
+        cudaEventRecord(e1[1], st[1]);
+        cudaDeviceSynchronize();
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, e0, e1[0]);
+        cudaEventElapsedTime(&b, e0, e1[1]);
+        ms = a > b ? a : b;
+        if (pass == 0) {        // calibration pass: rescale the number of rounds to the requested duration
+            const double gbs = copies * (double)bytes / (ms * 1e-3) / 1e9;
+            rounds = (long)(seconds * gbs * 1e9 / (4.0 * bytes)) + 1;
+        }
+    }
+    if (cudaGetLastError() != cudaSuccess || ms <= 0) rc = B200S_ECUDA;
+    else *d2h_gbs = copies * (double)bytes / (ms * 1e-3) / 1e9;
+    if (((volatile unsigned char*)host[0])[bytes / 2] != 7) rc = B200S_ECUDA;     // the copies really arrived
+    cleanup();
+    return rc;
+}
+
 // ---- batch timing: one start event all slot streams wait on, one end event per slot stream ----------------
 int b200s_batch_begin(b200s_handle* h)
 {

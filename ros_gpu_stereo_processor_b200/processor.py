@@ -480,10 +480,10 @@ class GpuStereoProcessor(object):
         self._ck(self._lib.b200s_batch_end(self._h, C.byref(ms)))
         return ms.value
 
-    def hostAlloc(self, nbytes):
+    def hostAlloc(self, nbytes, write_combined=False):
         """Pinned host buffer as a numpy uint8 array (cudaHostAlloc)."""
         p = C.c_void_p()
-        rc = self._lib.b200s_host_alloc(C.byref(p), int(nbytes))
+        rc = self._lib.b200s_host_alloc_mode(C.byref(p), int(nbytes), int(bool(write_combined)))
         if rc != 0:
             raise capi.B200StereoError(rc, "cudaHostAlloc failed")
         buf = (C.c_uint8 * int(nbytes)).from_address(p.value)
