@@ -564,7 +564,7 @@ def run_ours(args, rank, world, local_rank):
                     peak_source="measured: b200s_int_peak, IADD3 and IMAD dependent chains interleaved (ALU + IMAD pipes), all SMs, this run",
                     frac_vs_iadd3_peak=achieved / peak_tops, iadd3_peak=peak_tops,
                     frac_vs_theoretical_37p2=achieved / THEORETICAL_TOPS,
-                    issue_slot_util=(ncu_pipes or {}).get("issue_slots_busy_pct"),
+                    issue_slot_util=(ncu_pipes or {}).get("issue_active_pct"),
                     issue_slot_util_source="ncu capture committed under profiles/ (hardware counter; not measurable from CUDA events)",
                     note="packed instructions (VABSDIFF4, u16x2 adds/minima) execute 2-4 scalar-equivalent ops each, so the fraction of the "
                          "single-pipe IADD3 rate exceeds 1; ncu_pipes is the hardware view of the same kernel (profiles/, committed capture)",
