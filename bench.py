@@ -417,33 +417,16 @@ class ConfigRun(object):
         return frames, mismatches, bad
 
     # ---- bare D2H probe on this GPU (no kernels): the copy ceiling of the end-to-end leg ----
-    def copy_ceiling_fps(self, seconds=0.4):
-        torch = self.torch
-        nbytes = self.d2h_per_frame
-        devb = torch.empty(nbytes, dtype=torch.uint8, device="cuda:%d" % self.dev)
-        host = []
-        for _ in range(2):
-            a, ptr = self.pinned(nbytes)
-            host.append(torch.from_numpy(a))
-        streams = [torch.cuda.Stream(self.dev) for _ in range(2)]
+    def copy_ceiling_fps(self, seconds=0.5):
+        """b200s_copy_probe (the probe of tools/d2h_probe.py: cudaMemcpyAsync D2H of one frame's products, two streams,
+        four page-locked buffers) run by every rank at the same time; frames/s summed over the ranks."""
+        import ctypes as C
+        gbs = C.c_double()
         self.barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), [torch.cuda.Event(enable_timing=True) for _ in streams]
-        ev0.record(streams[0])
-        streams[1].wait_event(ev0)
-        t0, k = time.perf_counter(), 0
-        while time.perf_counter() - t0 < seconds:
-            for i in range(2):
-                with torch.cuda.stream(streams[i]):
-                    host[i].copy_(devb, non_blocking=True)
-                k += 1
-            streams[0].synchronize()
-        for s, e in zip(streams, ev1):
-            e.record(s)
-        torch.cuda.synchronize(self.dev)
-        ms = max(ev0.elapsed_time(e) for e in ev1)
-        fps = k / (ms * 1e-3)
+        rc = self.proc._lib.b200s_copy_probe(self.dev, int(self.d2h_per_frame), float(seconds), 0, 0, C.byref(gbs))
+        fps = gbs.value * 1e9 / self.d2h_per_frame if rc == 0 else float("nan")
         if self.dist is not None:
-            t = torch.tensor([fps], device="cuda:%d" % self.dev, dtype=torch.float64)
+            t = self.torch.tensor([fps], device="cuda:%d" % self.dev, dtype=self.torch.float64)
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
             fps = float(t.item())
         return fps
@@ -502,7 +485,7 @@ def measure_config(name, c, args, rank, world, dev, dist, steps, warmup, passes,
                mdisp_evals_per_s=fps_dev * nominal / 1e6, mdisp_evals_effective_per_s=fps_dev * eff / 1e6,
                e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_frame=run.h2d_per_frame, d2h_bytes_per_frame=run.d2h_per_frame,
                         copy_ceiling_frames_per_s=ceiling_fps, frac_of_copy_ceiling=fps_e2e / ceiling_fps,
-                        ceiling="bare cudaMemcpyAsync D2H of the same bytes per frame, pinned, no kernels, all ranks at once (this run)"),
+                        ceiling="b200s_copy_probe: bare cudaMemcpyAsync D2H of one frame's products, pinned, 2 streams / 4 buffers, no kernels, all ranks at once (this run)"),
                parity_checked=checks, _ms_dev=ms_dev, _ms_e2e=ms_e2e, _launches=launches)
     if want_roofline and rank == 0:
         t_bm, stages = run.stage_times()
@@ -564,7 +547,7 @@ def run_ours(args, rank, world, local_rank):
                     peak_source="measured: b200s_int_peak, IADD3 and IMAD dependent chains interleaved (ALU + IMAD pipes), all SMs, this run",
                     frac_vs_iadd3_peak=achieved / peak_tops, iadd3_peak=peak_tops,
                     frac_vs_theoretical_37p2=achieved / THEORETICAL_TOPS,
-                    issue_slot_util=(ncu_pipes or {}).get("issue_slots_busy_pct"),
+                    issue_slot_util=(ncu_pipes or {}).get("issue_active_pct"),
                     issue_slot_util_source="ncu capture committed under profiles/ (hardware counter; not measurable from CUDA events)",
                     note="packed instructions (VABSDIFF4, u16x2 adds/minima) execute 2-4 scalar-equivalent ops each, so the fraction of the "
                          "single-pipe IADD3 rate exceeds 1; ncu_pipes is the hardware view of the same kernel (profiles/, committed capture)",

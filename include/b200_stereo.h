@@ -295,6 +295,9 @@ int b200s_mat_stats(b200s_handle* h, int mat_id, double* mn, double* mx, double*
  * cudaHostAlloc default, 1 = cudaHostAllocWriteCombined, 2 = malloc + cudaHostRegister.  with_h2d also streams a
  * 4 MB host->device copy per D2H copy (the raw pair going in). */
 int b200s_copy_probe(int device, size_t bytes, double seconds, int host_mode, int with_h2d, double* d2h_gbs);
+/* same with n_streams (1..8) copy streams and n_buffers (1..16) host buffers instead of 2 and 4 */
+int b200s_copy_probe_ex(int device, size_t bytes, double seconds, int host_mode, int with_h2d, int n_streams, int n_buffers,
+                        double* d2h_gbs);
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA runtime of their own */
 int b200s_host_alloc(void** p, size_t bytes);
 /* mode 0 = cudaHostAllocDefault, 1 = cudaHostAllocWriteCombined (device writes bypass the CPU caches; CPU reads are slow) */

@@ -128,6 +128,7 @@ SYMBOLS = {
     "b200s_slot_frame_device_ptr": (C.c_int, [H, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "b200s_last_stage_times": (C.c_int, [H, C.c_int, C.POINTER(C.c_float)]),
     "b200s_host_alloc_mode": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]),
+    "b200s_copy_probe_ex": (C.c_int, [C.c_int, C.c_size_t, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "b200s_copy_probe": (C.c_int, [C.c_int, C.c_size_t, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "b200s_mat_stats": (C.c_int, [H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
 }

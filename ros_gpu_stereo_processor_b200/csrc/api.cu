@@ -272,7 +272,7 @@ int ensure_pre_planes(b200s_handle* h, Work& w, int rows, int cols, int nf)
 // prefilter + match + post-filters on rectified device planes; disp must hold rows*cols int16 per frame
 int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, bool already_prefiltered, int rows,
                   int cols, int16_t* disp, cudaStream_t st, int nf, size_t src_stride, size_t disp_stride, const uint8_t* const* tabL,
-                  const uint8_t* const* tabR)
+                  const uint8_t* const* tabR, bool keep_border)
 {
     const b200s_params& p = h->prm;
     int rc = validate_params(h, p);
@@ -323,7 +323,19 @@ int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, 
         if (!w.ev_bm0) { cudaEventCreate(&w.ev_bm0); cudaEventCreate(&w.ev_bm1); }
         cudaEventRecord(w.ev_bm0, st);
     }
-    int l = launch_block_match(Lp, Rp, pitch, cols, rows, cfg, disp, cost, &sc, st, &w.last_evals, nf, pstride, disp_stride);
+    // A slot's disparity planes keep the FILTERED border of the previous batch: the matcher and the post-filters only ever
+    // write FILTERED there, so the fill is needed again only when the geometry (or FILTERED itself) changes.
+    bool border_ok = false;
+    if (keep_border) {
+        std::string key;
+        const int kv[8] = {rows, cols, p.min_disparity, p.num_disparities, p.block_size, p.disp12_max_diff >= 0, nf > w.depth ? nf : w.depth, 0};
+        key.assign((const char*)kv, sizeof kv);
+        key.append((const char*)&disp, sizeof disp);
+        border_ok = key == w.border_key;
+        w.border_key = key;
+        if (nf < w.depth && !border_ok) w.border_key.clear();      // a partial batch fills only its own frames
+    }
+    int l = launch_block_match(Lp, Rp, pitch, cols, rows, cfg, disp, cost, &sc, st, &w.last_evals, nf, pstride, disp_stride, border_ok);
     w.last_evals *= nf;
     if (h->timing) { cudaEventRecord(w.ev_bm1, st); w.timed = true; }
     if (l < 0) return fail(h, B200S_ECUDA, "block matcher launch failed (code " + std::to_string(l) + "): " + cudaGetErrorString(cudaGetLastError()));

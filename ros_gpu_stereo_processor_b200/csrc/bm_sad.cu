@@ -676,7 +676,7 @@ static const int NOT_BATCHABLE = -1000;
 
 static int block_match_impl(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg,
                             int16_t* disp, int16_t* cost, BMScratch* sc, cudaStream_t st, double* evals, int nf,
-                            size_t pre_stride, size_t disp_stride)
+                            size_t pre_stride, size_t disp_stride, bool border_is_filled)
 {
     const Geom g = geom(W, H, cfg);
     const int16_t FILTERED = (int16_t)((cfg.minD - 1) * 16);
@@ -702,11 +702,11 @@ static int block_match_impl(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, 
     }
     {
         const long long nfill = (long long)(outX0 + (W - outX1)) * H + (long long)(outX1 - outX0) * (g.roiY0 + (H - g.roiY1));
-        if (nfill > 0)
+        if (nfill > 0 && !border_is_filled)
             fill_border_kernel<<<dim3((unsigned)((nfill + 255) / 256), nf), 256, 0, st>>>(disp, W, H, outX0, outX1, g.roiY0, g.roiY1,
                                                                                         FILTERED, disp_stride);
     }
-    ++launches;
+    if (!border_is_filled) ++launches;
     if (evals) {
         int ex0 = std::max(compX0, g.roiX0), ex1 = std::min(compX1, g.roiX1);
         *evals = ex1 > ex0 ? (double)(ex1 - ex0) * (g.roiY1 - g.roiY0) * cfg.nd : 0.0;
@@ -854,15 +854,15 @@ static int block_match_impl(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, 
 
 int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg,
                        int16_t* disp, int16_t* cost, BMScratch* sc, cudaStream_t st, double* evals, int nf, size_t pre_stride,
-                       size_t disp_stride)
+                       size_t disp_stride, bool border_is_filled)
 {
-    if (nf <= 1) return block_match_impl(Lp, Rp, pitch, W, H, cfg, disp, cost, sc, st, evals, 1, 0, 0);
-    int rc = block_match_impl(Lp, Rp, pitch, W, H, cfg, disp, cost, sc, st, evals, nf, pre_stride, disp_stride);
+    if (nf <= 1) return block_match_impl(Lp, Rp, pitch, W, H, cfg, disp, cost, sc, st, evals, 1, 0, 0, border_is_filled);
+    int rc = block_match_impl(Lp, Rp, pitch, W, H, cfg, disp, cost, sc, st, evals, nf, pre_stride, disp_stride, border_is_filled);
     if (rc != NOT_BATCHABLE) return rc;
     int total = 0;
     for (int f = 0; f < nf; ++f) {
         rc = block_match_impl(Lp + f * pre_stride, Rp + f * pre_stride, pitch, W, H, cfg, (int16_t*)((uint8_t*)disp + f * disp_stride),
-                              cost ? (int16_t*)((uint8_t*)cost + f * disp_stride) : nullptr, sc, st, evals, 1, 0, 0);
+                              cost ? (int16_t*)((uint8_t*)cost + f * disp_stride) : nullptr, sc, st, evals, 1, 0, 0, false);
         if (rc < 0) return rc;
         total += rc;
     }

@@ -81,6 +81,7 @@ struct Work {
     std::vector<GraphEntry> graphs;
     uint64_t use_counter = 0;
     std::string tab_cache;        // last input-address table written to the device (slots.cu)
+    std::string border_key;       // geometry + FILTERED value the border of the slot's disparity planes was last filled for
     const void* in_tab[3 * MAX_BATCH] = {nullptr};   // host copy of that table: L[32], R[32], colour[32]
     void drop_graphs()
     {
@@ -191,7 +192,7 @@ int ensure_misc(b200s_handle* h, Work& w);
 // prefiltered planes plane_stride(cols, rows) apart, disparity planes disp_stride apart)
 int run_disparity(b200s_handle* h, Work& w, const uint8_t* L, const uint8_t* R, bool already_prefiltered, int rows, int cols,
                   int16_t* disp, cudaStream_t st, int nf = 1, size_t src_stride = 0, size_t disp_stride = 0,
-                  const uint8_t* const* tabL = nullptr, const uint8_t* const* tabR = nullptr);
+                  const uint8_t* const* tabL = nullptr, const uint8_t* const* tabR = nullptr, bool keep_border = false);
 constexpr size_t MISC_BYTES = 2048;   // per-frame minima (ints) + the per-frame input address table of the slot
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 inline size_t plane_stride(int cols, int rows) { return align256(plane_bytes(cols, rows)); }

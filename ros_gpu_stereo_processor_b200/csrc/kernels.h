@@ -83,7 +83,9 @@ struct BMScratch {         // device scratch owned by the caller
 // nf > 1: a batch; prefiltered planes pre_stride bytes apart, disp / cost planes disp_stride bytes apart.  *evals is per frame.
 int launch_block_match(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg,
                        int16_t* disp, int16_t* cost, BMScratch* scratch, cudaStream_t st, double* evals,
-                       int nf = 1, size_t pre_stride = 0, size_t disp_stride = 0);
+                       int nf = 1, size_t pre_stride = 0, size_t disp_stride = 0, bool border_is_filled = false);
+// border_is_filled: the caller guarantees that everything outside the rectangle the matcher writes already holds FILTERED
+// (a slot's disparity planes keep their border from the previous frame with the same geometry), so the fill is skipped
 constexpr size_t PLANE_LEAD = 256, PLANE_TAIL = 4096;
 inline size_t plane_pitch(int W) { return ((size_t)W + 15) / 16 * 16; }
 inline size_t plane_bytes(int W, int H) { return PLANE_LEAD + plane_pitch(W) * H + PLANE_TAIL; }

@@ -69,8 +69,36 @@ __global__ void __launch_bounds__(256) disparity_to_float_kernel(const int16_t* 
 #ifndef B200S_PACK_ROWS
 #define B200S_PACK_ROWS 8
 #endif
-constexpr int RP_ROWS = B200S_PACK_ROWS;      // block = 32 columns x RP_ROWS rows (one warp per row)
+constexpr int RP_ROWS = B200S_PACK_ROWS;      // block = 32 columns x RP_ROWS warps
+constexpr int RP_RPW = 4;                     // consecutive image rows per warp (column-only terms are computed once)
 
+// bit (4 r + c) set = Q[r][c] != 0.  image_geometry's Q (StereoCameraModel::updateQ) has exactly these seven entries:
+//   X = Q00 x + Q03,  Y = Q11 y + Q13,  Z = Q23,  W = Q32 d + Q33
+constexpr unsigned QMASK_STEREO = (1u << 0) | (1u << 3) | (1u << 5) | (1u << 7) | (1u << 11) | (1u << 14) | (1u << 15);
+
+// float(a / w): one correctly rounded reciprocal shared by the three coordinates, see reproject_pack_kernel
+__device__ __forceinline__ float div_to_float(double a, double w, double rw)
+{
+    const double q = __dmul_rn(a, rw);
+    const unsigned lo = (unsigned)__double2loint(q) & 0x1FFFFFFFu;
+    const unsigned hi = (unsigned)__double2hiint(q) & 0x7FFFFFFFu;
+    // |q| in [2^-100, 2^100] (finite, far from float denormals / overflow) and away from the float rounding boundary
+    const bool safe = hi > 0x39B00000u && hi < 0x46300000u && (lo - 0x0FFFFFF0u) > 0x20u;
+    return __double2float_rn(safe ? q : __ddiv_rn(a, w));
+}
+
+// cv::reprojectImageTo3D(handleMissingValues = true) + PointCloud2 records (+ the float disparity plane) in one pass.
+// STDQ: Q has the sparsity of image_geometry's stereo model (the only Q the reference can produce); the terms that depend
+// on the column only are then computed once per thread and reused for the RP_RPW rows its warp walks.  The generic path
+// evaluates the full 4-term products with zero entries skipped.  Both give the bytes of the CPU code: every FP64
+// operation is an explicit round-to-nearest intrinsic in the CPU's order.
+//
+// float(a / w) for the three coordinates, a = (double)(float)h[r]: the correctly rounded FP64 division is a long
+// instruction sequence and all three share the divisor, so one correctly rounded reciprocal and a multiplication give a
+// quotient within 2 ulp (FP64) of a / w; rounding THAT to float gives the same float as rounding the exact quotient unless
+// it lies within a few FP64 ulps of a float rounding boundary (29 dropped bits = 0x10000000).  Those rare lanes, and
+// non-finite or tiny quotients, take the exact division: the result is bit-identical always.
+template <bool STDQ>
 __global__ void __launch_bounds__(32 * RP_ROWS) reproject_pack_kernel(const int16_t* __restrict__ d16, int W, int H, double cxd,
                                                              const double* __restrict__ Q, const int* __restrict__ min_d16,
                                                              const uint8_t* __restrict__ color, int ch,
@@ -79,7 +107,9 @@ __global__ void __launch_bounds__(32 * RP_ROWS) reproject_pack_kernel(const int1
                                                              int dmin_const, float* __restrict__ df, const FrameDst fdf,
                                                              const uint8_t* const* __restrict__ color_tab)
 {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * RP_ROWS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int x0 = blockIdx.x * 32, x = x0 + lane;
+    const int yw = (blockIdx.y * RP_ROWS + (threadIdx.x >> 5)) * RP_RPW;      // first row of this warp
     {
         const int f = blockIdx.z;          // frame of the batch
         d16 = (const int16_t*)((const uint8_t*)d16 + f * d_stride);
@@ -92,82 +122,89 @@ __global__ void __launch_bounds__(32 * RP_ROWS) reproject_pack_kernel(const int1
         else if (df) df = (float*)((uint8_t*)df + f * fdf.stride);
         if (min_d16) min_d16 += f;
     }
-    // One PointCloud2 record = 32 bytes = two 16-byte halves, [x y z 0] and [bgr 0 0 0].  The 32 records of a warp are
-    // 1 KiB contiguous; lanes exchange halves so that each of the two store instructions of the warp writes 512
-    // contiguous bytes (lane l: half (l & 1) of record (l >> 1) + 16 * instruction) -- full lines for HBM and for
-    // posted PCIe writes when pc2 is pinned host memory.  Rows are padded to whole warps by the launcher (W % 32 == 0)
-    // or fall back to per-thread stores.
-    uint32_t ux = 0x7fc00000u, uy = 0x7fc00000u, uz = 0x7fc00000u;
-    float p[3] = {0.f, 0.f, 0.f};
-    const bool inside = x < W && y < H;
-    const size_t i = inside ? (size_t)y * W + x : 0;
-    const int dv = inside ? (int)d16[i] : 0, dmin = min_d16 ? *min_d16 : dmin_const;
-    if (df && inside) df[i] = disp_to_float(dv, cxd);      // the DisparityImage payload from the same pass (convertTo)
-    // missing value (d == min over the image): cv::reprojectImageTo3D sets Z = 10000, which isValidPoint rejects, so the
-    // record is NaN xyz + colour whatever X and Y were; no arithmetic needed unless the xyz plane is wanted too
-    if (inside && (xyz || dv != dmin)) {
-        const float dfl = disp_to_float(dv, cxd);
-        const double d = (double)dfl;
-        const double minDisp = (double)disp_to_float(dmin, cxd);
-        double h[4];
+    if (yw >= H) return;
+    const int dmin = min_d16 ? *min_d16 : dmin_const;
+    const double minDisp = (double)disp_to_float(dmin, cxd);
+    // column-only and constant terms of the standard Q
+    double q11 = 0, q13 = 0, q32 = 0, q33 = 0, ax = 0, az = 0;
+    if (STDQ) {
+        ax = (double)__double2float_rn(__dadd_rn(__dmul_rn(__ldg(Q + 0), (double)x), __ldg(Q + 3)));
+        q11 = __ldg(Q + 5); q13 = __ldg(Q + 7);
+        az = (double)__double2float_rn(__dadd_rn(0.0, __ldg(Q + 11)));
+        q32 = __ldg(Q + 14); q33 = __ldg(Q + 15);
+    }
+    const bool xin = x < W;
+    const bool full_row = x0 + 32 <= W;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            // entries of Q that are exactly zero are skipped (qmask bit = entry is non-zero): 0 * v = +-0 and s + (+-0) = s,
-            // so the sum is bit-identical to the full 4-term product of cv::reprojectImageTo3D (finite v)
-            double s = (qmask >> (r * 4 + 0)) & 1u ? __dmul_rn(__ldg(Q + r * 4 + 0), (double)x) : 0.0;
-            if ((qmask >> (r * 4 + 1)) & 1u) s = __dadd_rn(s, __dmul_rn(__ldg(Q + r * 4 + 1), (double)y));
-            if ((qmask >> (r * 4 + 2)) & 1u) s = __dadd_rn(s, __dmul_rn(__ldg(Q + r * 4 + 2), d));
-            if ((qmask >> (r * 4 + 3)) & 1u) s = __dadd_rn(s, __ldg(Q + r * 4 + 3));
-            h[r] = s;
-        }
-        // float(a / w) for the three coordinates, a = (double)(float)h[r].  The correctly rounded FP64 division is a long
-        // instruction sequence; all three share the divisor, so one correctly rounded reciprocal and a multiplication give a
-        // quotient within 2 ulp (FP64) of a / w, and rounding THAT to float gives the same float as rounding the exact
-        // quotient unless it lies within a few FP64 ulps of a float rounding boundary (29 dropped bits = 0x10000000).  Those
-        // rare lanes, and non-finite or tiny quotients, take the exact division: the result is bit-identical always.
-        {
-            const double rw = __drcp_rn(h[3]);
+    for (int rr = 0; rr < RP_RPW; ++rr) {
+        const int y = yw + rr;
+        if (y >= H) break;                                   // warp-uniform
+        // One PointCloud2 record = 32 bytes = two 16-byte halves, [x y z 0] and [bgr 0 0 0].  The 32 records of a warp
+        // row are 1 KiB contiguous; lanes exchange halves so that each of the two store instructions of the warp writes
+        // 512 contiguous bytes (lane l: half (l & 1) of record (l >> 1) + 16 * instruction) -- full lines for HBM and
+        // for posted PCIe writes when pc2 is pinned host memory.  Partial warps at the right edge store per thread.
+        uint32_t ux = 0x7fc00000u, uy = 0x7fc00000u, uz = 0x7fc00000u;
+        const size_t i = xin ? (size_t)y * W + x : 0;
+        const int dv = xin ? (int)d16[i] : 0;
+        if (df && xin) df[i] = disp_to_float(dv, cxd);       // the DisparityImage payload from the same pass (convertTo)
+        // missing value (d == min over the image): cv::reprojectImageTo3D sets Z = 10000, which isValidPoint rejects, so
+        // the record is NaN xyz + colour whatever X and Y were; no arithmetic needed unless the xyz plane is wanted too
+        if (xin && (xyz || dv != dmin)) {
+            const double d = (double)disp_to_float(dv, cxd);
+            double a[3], w;
+            if (STDQ) {
+                a[0] = ax;
+                a[1] = (double)__double2float_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(q11, (double)y)), q13));
+                a[2] = az;
+                w = __dadd_rn(__dadd_rn(0.0, __dmul_rn(q32, d)), q33);
+            } else {
+                double h[4];
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const double a = (double)__double2float_rn(h[r]);
-                const double q = __dmul_rn(a, rw);
-                const unsigned lo = (unsigned)__double2loint(q) & 0x1FFFFFFFu;
-                const unsigned hi = (unsigned)__double2hiint(q) & 0x7FFFFFFFu;
-                // |q| in [2^-100, 2^100] (finite, far from float denormals / overflow) and away from the rounding boundary
-                const bool safe = hi > 0x39B00000u && hi < 0x46300000u && (lo - 0x0FFFFFF0u) > 0x20u;
-                p[r] = __double2float_rn(safe ? q : __ddiv_rn(a, h[3]));
+                for (int r = 0; r < 4; ++r) {
+                    // entries of Q that are exactly zero are skipped (qmask bit = entry is non-zero): 0 * v = +-0 and
+                    // s + (+-0) = s, so the sum is bit-identical to the full 4-term product (finite v)
+                    double s2 = (qmask >> (r * 4 + 0)) & 1u ? __dmul_rn(__ldg(Q + r * 4 + 0), (double)x) : 0.0;
+                    if ((qmask >> (r * 4 + 1)) & 1u) s2 = __dadd_rn(s2, __dmul_rn(__ldg(Q + r * 4 + 1), (double)y));
+                    if ((qmask >> (r * 4 + 2)) & 1u) s2 = __dadd_rn(s2, __dmul_rn(__ldg(Q + r * 4 + 2), d));
+                    if ((qmask >> (r * 4 + 3)) & 1u) s2 = __dadd_rn(s2, __ldg(Q + r * 4 + 3));
+                    h[r] = s2;
+                }
+                a[0] = (double)__double2float_rn(h[0]); a[1] = (double)__double2float_rn(h[1]); a[2] = (double)__double2float_rn(h[2]);
+                w = h[3];
+            }
+            const double rw = __drcp_rn(w);
+            float p[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) p[r] = div_to_float(a[r], w, rw);
+            if (fabs(__dadd_rn(d, -minDisp)) <= (double)1.1920928955078125e-07f) p[2] = 10000.0f;
+            if (xyz) {
+                xyz[i * 3] = p[0]; xyz[i * 3 + 1] = p[1]; xyz[i * 3 + 2] = p[2];
+            }
+            // isValidPoint (src/GpuSenderPc2.cpp:84-89): z != MISSING_Z and not inf; invalid -> quiet NaN
+            if ((p[2] != 10000.0f) && !isinf(p[2])) {
+                ux = __float_as_uint(p[0]); uy = __float_as_uint(p[1]); uz = __float_as_uint(p[2]);
             }
         }
-        if (fabs(__dadd_rn(d, -minDisp)) <= (double)1.1920928955078125e-07f) p[2] = 10000.0f;
-        if (xyz) {
-            xyz[i * 3] = p[0]; xyz[i * 3 + 1] = p[1]; xyz[i * 3 + 2] = p[2];
+        if (!pc2) continue;
+        uint32_t bgr = 0;
+        if (xin) {
+            if (ch == 3) bgr = (uint32_t)color[i * 3] | ((uint32_t)color[i * 3 + 1] << 8) | ((uint32_t)color[i * 3 + 2] << 16);
+            else { uint32_t g = color ? color[i] : 0; bgr = g | (g << 8) | (g << 16); }
         }
-        // isValidPoint (src/GpuSenderPc2.cpp:84-89): z != MISSING_Z and not inf; invalid -> quiet NaN
-        if ((p[2] != 10000.0f) && !isinf(p[2])) {
-            ux = __float_as_uint(p[0]); uy = __float_as_uint(p[1]); uz = __float_as_uint(p[2]);
-        }
-    }
-    if (!pc2) return;
-    uint32_t bgr = 0;
-    if (inside) {
-        if (ch == 3) bgr = (uint32_t)color[i * 3] | ((uint32_t)color[i * 3 + 1] << 8) | ((uint32_t)color[i * 3 + 2] << 16);
-        else { uint32_t g = color ? color[i] : 0; bgr = g | (g << 8) | (g << 16); }
-    }
-    const int lane = threadIdx.x & 31;
-    const int x0 = blockIdx.x * 32;
-    if (x0 + 32 <= W && y < H) {
-        uint4* row = (uint4*)(pc2 + ((size_t)y * W + x0) * 32);
+        if (full_row) {
+            uint4* row = (uint4*)(pc2 + ((size_t)y * W + x0) * 32);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int src = (lane >> 1) + 16 * k;
-            const uint32_t sx = __shfl_sync(0xffffffffu, ux, src), sy = __shfl_sync(0xffffffffu, uy, src);
-            const uint32_t sz = __shfl_sync(0xffffffffu, uz, src), sc = __shfl_sync(0xffffffffu, bgr, src);
-            row[32 * k + lane] = (lane & 1) ? make_uint4(sc, 0u, 0u, 0u) : make_uint4(sx, sy, sz, 0u);
+            for (int k = 0; k < 2; ++k) {
+                const int src = (lane >> 1) + 16 * k;
+                const uint32_t sx = __shfl_sync(0xffffffffu, ux, src), sy = __shfl_sync(0xffffffffu, uy, src);
+                const uint32_t sz = __shfl_sync(0xffffffffu, uz, src), sc = __shfl_sync(0xffffffffu, bgr, src);
+                row[32 * k + lane] = (lane & 1) ? make_uint4(sc, 0u, 0u, 0u) : make_uint4(sx, sy, sz, 0u);
+            }
+        } else if (xin) {
+            uint4* o = (uint4*)(pc2 + i * 32);
+            o[0] = make_uint4(ux, uy, uz, 0u);
+            o[1] = make_uint4(bgr, 0u, 0u, 0u);
         }
-    } else if (inside) {
-        uint4* o = (uint4*)(pc2 + i * 32);
-        o[0] = make_uint4(ux, uy, uz, 0u);
-        o[1] = make_uint4(bgr, 0u, 0u, 0u);
     }
 }
 
@@ -222,13 +259,18 @@ int launch_reproject_pack(const int16_t* d16, int W, int H, double cxd, const do
                           const uint8_t* color, int ch, float* xyz, uint8_t* pc2, cudaStream_t st, int nf, size_t d_stride,
                           size_t color_stride, size_t xyz_stride, size_t pc2_stride, const PtrList* pc2_list, const ReprojectExtras* extra)
 {
-    dim3 g((W + 31) / 32, (H + RP_ROWS - 1) / RP_ROWS, nf);
+    dim3 g((W + 31) / 32, (H + RP_ROWS * RP_RPW - 1) / (RP_ROWS * RP_RPW), nf);
     if (pc2_list && !pc2) pc2 = (uint8_t*)pc2_list->p[0];     // the kernel tests pc2 for "records wanted"
     ReprojectExtras ex;
     if (extra) ex = *extra;
-    reproject_pack_kernel<<<g, 32 * RP_ROWS, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask, d_stride, color_stride,
-                                             xyz_stride, frame_dst(pc2_stride, pc2_list), ex.dmin_const, ex.df,
-                                             frame_dst(ex.df_stride, ex.df_list), ex.color_tab);
+    if (qmask == QMASK_STEREO)
+        reproject_pack_kernel<true><<<g, 32 * RP_ROWS, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask, d_stride, color_stride,
+                                                         xyz_stride, frame_dst(pc2_stride, pc2_list), ex.dmin_const, ex.df,
+                                                         frame_dst(ex.df_stride, ex.df_list), ex.color_tab);
+    else
+        reproject_pack_kernel<false><<<g, 32 * RP_ROWS, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask, d_stride, color_stride,
+                                                          xyz_stride, frame_dst(pc2_stride, pc2_list), ex.dmin_const, ex.df,
+                                                          frame_dst(ex.df_stride, ex.df_list), ex.color_tab);
     return 1;
 }
 

@@ -98,7 +98,7 @@ int run_frame_chain(b200s_handle* h, Work& w, int nf, const b200s_frame_io* ios,
     }
     if (w.disp.ensure(lay.disp * w.depth)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (disparity plane)");
     int rc = run_disparity(h, w, rl, rr, prefiltered, rows, cols, (int16_t*)w.disp.p, st, nf, rect_stride, lay.disp, rl ? nullptr : tabL,
-                           rr ? nullptr : tabR);
+                           rr ? nullptr : tabR, true);
     if (rc) return rc;
     h->stats_frames += nf - 1;
     stage_mark(h, w, 3, st);
@@ -597,16 +597,17 @@ int b200s_pool_wait_all(b200s_pool* p)
 }
 
 // ---- bare copy probe: what the host side of PCIe absorbs with no kernels at all -----------------------------------
-int b200s_copy_probe(int device, size_t bytes, double seconds, int host_mode, int with_h2d, double* d2h_gbs)
+int b200s_copy_probe_ex(int device, size_t bytes, double seconds, int host_mode, int with_h2d, int n_streams, int n_buffers,
+                        double* d2h_gbs)
 {
-    if (!d2h_gbs || bytes == 0 || seconds <= 0) return B200S_EINVAL;
+    if (!d2h_gbs || bytes == 0 || seconds <= 0 || n_streams < 1 || n_streams > 8 || n_buffers < 1 || n_buffers > 16) return B200S_EINVAL;
     DeviceGuard g(device);
     void* dev = nullptr;
     void* din = nullptr;
     void* hin = nullptr;
-    void* host[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaStream_t st[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t e0 = nullptr, e1[2] = {nullptr, nullptr};
+    void* host[16] = {nullptr};
+    cudaStream_t st[9] = {nullptr};        // n_streams copy streams + one for the host->device side
+    cudaEvent_t e0 = nullptr, e1[8] = {nullptr};
     const size_t in_bytes = 4u << 20;
     int rc = B200S_OK;
     auto cleanup = [&]() {
@@ -624,7 +625,7 @@ int b200s_copy_probe(int device, size_t bytes, double seconds, int host_mode, in
     };
     bool ok = cudaMalloc(&dev, bytes) == cudaSuccess && cudaMalloc(&din, in_bytes) == cudaSuccess &&
               cudaHostAlloc(&hin, in_bytes, cudaHostAllocDefault) == cudaSuccess && cudaMemset(dev, 7, bytes) == cudaSuccess;
-    for (int i = 0; ok && i < 4; ++i) {
+    for (int i = 0; ok && i < n_buffers; ++i) {
         if (host_mode == 2) {
             host[i] = aligned_alloc(4096, (bytes + 4095) & ~(size_t)4095);
             ok = host[i] && cudaHostRegister(host[i], bytes, cudaHostRegisterDefault) == cudaSuccess;
@@ -633,41 +634,42 @@ int b200s_copy_probe(int device, size_t bytes, double seconds, int host_mode, in
         }
         if (ok) memset(host[i], 0, bytes);      // touch the pages (placement follows the caller's memory policy)
     }
-    for (int i = 0; ok && i < 3; ++i) ok = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1[0]) == cudaSuccess && cudaEventCreate(&e1[1]) == cudaSuccess;
+    for (int i = 0; ok && i <= n_streams; ++i) ok = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&e0) == cudaSuccess;
+    for (int i = 0; ok && i < n_streams; ++i) ok = cudaEventCreate(&e1[i]) == cudaSuccess;
     if (!ok) { cleanup(); cudaGetLastError(); return B200S_ECUDA; }
-    for (int i = 0; i < 4; ++i) cudaMemcpyAsync(host[i], dev, bytes, cudaMemcpyDeviceToHost, st[i & 1]);
+    for (int i = 0; i < n_buffers; ++i) cudaMemcpyAsync(host[i], dev, bytes, cudaMemcpyDeviceToHost, st[i % n_streams]);
     cudaDeviceSynchronize();
-    cudaEventRecord(e0, st[0]);
-    cudaStreamWaitEvent(st[1], e0, 0);
-    // fixed number of rounds sized from a short calibration, so that the timed region is pure copies
-    double gbs_guess = 20.0;
-    long rounds = (long)(seconds * gbs_guess * 1e9 / (4.0 * bytes)) + 1;
+    // number of rounds from a calibration pass, so that the timed pass is pure copies of about the requested duration
+    const int per_round = 2 * n_streams;         // two copies queued per stream
+    long rounds = (long)(0.2 * seconds * 20e9 / ((double)per_round * bytes)) + 1;
     long copies = 0;
     float ms = 0;
     for (int pass = 0; pass < 2; ++pass) {
         cudaDeviceSynchronize();
         cudaEventRecord(e0, st[0]);
-        cudaStreamWaitEvent(st[1], e0, 0);
+        for (int i = 1; i < n_streams; ++i) cudaStreamWaitEvent(st[i], e0, 0);
         copies = 0;
         for (long r = 0; r < rounds; ++r) {
-            for (int i = 0; i < 4; ++i) {
-                cudaMemcpyAsync(host[i], dev, bytes, cudaMemcpyDeviceToHost, st[i & 1]);
-                if (with_h2d) cudaMemcpyAsync(din, hin, in_bytes, cudaMemcpyHostToDevice, st[2]);
+            for (int i = 0; i < per_round; ++i) {
+                cudaMemcpyAsync(host[copies % n_buffers], dev, bytes, cudaMemcpyDeviceToHost, st[i % n_streams]);
+                if (with_h2d) cudaMemcpyAsync(din, hin, in_bytes, cudaMemcpyHostToDevice, st[n_streams]);
                 ++copies;
             }
-            cudaStreamSynchronize(st[0]);       // at most four copies queued ahead
+            cudaStreamSynchronize(st[0]);       // at most two rounds queued ahead
         }
-        cudaEventRecord(e1[0], st[0]);
-        cudaEventRecord(e1[1], st[1]);
+        float worst = 0;
+        for (int i = 0; i < n_streams; ++i) cudaEventRecord(e1[i], st[i]);
         cudaDeviceSynchronize();
-        float a = 0, b = 0;
-        cudaEventElapsedTime(&a, e0, e1[0]);
-        cudaEventElapsedTime(&b, e0, e1[1]);
-        ms = a > b ? a : b;
+        for (int i = 0; i < n_streams; ++i) {
+            float a = 0;
+            cudaEventElapsedTime(&a, e0, e1[i]);
+            worst = a > worst ? a : worst;
+        }
+        ms = worst;
         if (pass == 0) {        // calibration pass: rescale the number of rounds to the requested duration
             const double gbs = copies * (double)bytes / (ms * 1e-3) / 1e9;
-            rounds = (long)(seconds * gbs * 1e9 / (4.0 * bytes)) + 1;
+            rounds = (long)(seconds * gbs * 1e9 / ((double)per_round * bytes)) + 1;
         }
     }
     if (cudaGetLastError() != cudaSuccess || ms <= 0) rc = B200S_ECUDA;
@@ -675,6 +677,11 @@ int b200s_copy_probe(int device, size_t bytes, double seconds, int host_mode, in
     if (((volatile unsigned char*)host[0])[bytes / 2] != 7) rc = B200S_ECUDA;     // the copies really arrived
     cleanup();
     return rc;
+}
+
+int b200s_copy_probe(int device, size_t bytes, double seconds, int host_mode, int with_h2d, double* d2h_gbs)
+{
+    return b200s_copy_probe_ex(device, bytes, seconds, host_mode, with_h2d, 2, 4, d2h_gbs);
 }
 
 // ---- batch timing: one start event all slot streams wait on, one end event per slot stream ----------------

@@ -62,7 +62,8 @@ def worker(rank, args, barrier, q):
     # a very short first call creates the CUDA context before the barrier
     lib.b200s_copy_probe(rank, 1 << 20, 0.01, 0, 0, ctypes.byref(gbs))
     barrier.wait()
-    rc = lib.b200s_copy_probe(rank, int(args.chunk_mb * 1e6), args.seconds, MODES[args.mode], int(args.with_h2d), ctypes.byref(gbs))
+    rc = lib.b200s_copy_probe_ex(rank, int(args.chunk_mb * 1e6), args.seconds, MODES[args.mode], int(args.with_h2d), args.streams,
+                                 args.buffers, ctypes.byref(gbs))
     q.put(dict(rank=rank, rc=rc, gbs=gbs.value, numa=note, gpu_numa_node=node))
 
 
@@ -74,6 +75,8 @@ def main():
     ap.add_argument("--mode", default="pinned", choices=list(MODES))
     ap.add_argument("--numa", default="none", choices=["none", "local", "interleave"])
     ap.add_argument("--with-h2d", action="store_true", help="also stream a 4 MB host->device copy per D2H copy")
+    ap.add_argument("--streams", type=int, default=2, help="copy streams per GPU")
+    ap.add_argument("--buffers", type=int, default=4, help="page-locked host buffers per GPU")
     args = ap.parse_args()
     ctx = mp.get_context("spawn")
     try:
@@ -91,7 +94,7 @@ def main():
         res = sorted([q.get(timeout=300) for _ in procs], key=lambda d: d["rank"])
         for p in procs:
             p.join(timeout=60)
-        print(json.dumps(dict(n_gpus=n, mode=args.mode, numa=args.numa, with_h2d=args.with_h2d, chunk_mb=args.chunk_mb,
+        print(json.dumps(dict(n_gpus=n, mode=args.mode, numa=args.numa, with_h2d=args.with_h2d, chunk_mb=args.chunk_mb, streams=args.streams, buffers=args.buffers,
                               aggregate_gbs=sum(r["gbs"] for r in res), per_gpu_gbs=[round(r["gbs"], 2) for r in res],
                               all_ok=all(r["rc"] == 0 for r in res), numa_nodes=numa_nodes(),
                               gpu_numa_nodes=[r["gpu_numa_node"] for r in res], notes=sorted(set(r["numa"] for r in res)),
