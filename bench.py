@@ -419,17 +419,21 @@ class ConfigRun(object):
     # ---- bare D2H probe on this GPU (no kernels): the copy ceiling of the end-to-end leg ----
     def copy_ceiling_fps(self, seconds=0.5):
         """b200s_copy_probe (the probe of tools/d2h_probe.py: cudaMemcpyAsync D2H of one frame's products, two streams,
-        four page-locked buffers) run by every rank at the same time; frames/s summed over the ranks."""
+        four page-locked buffers) run by every rank at the same time.  Returns (sum over the ranks, N x the slowest rank) in
+        frames/s: the bench gives every rank the same number of frames, so the slowest PCIe path gates the job."""
         import ctypes as C
         gbs = C.c_double()
         self.barrier()
         rc = self.proc._lib.b200s_copy_probe(self.dev, int(self.d2h_per_frame), float(seconds), 0, 0, C.byref(gbs))
         fps = gbs.value * 1e9 / self.d2h_per_frame if rc == 0 else float("nan")
+        total, slowest, n = fps, fps, 1
         if self.dist is not None:
             t = self.torch.tensor([fps], device="cuda:%d" % self.dev, dtype=self.torch.float64)
+            tmin = t.clone()
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
-            fps = float(t.item())
-        return fps
+            self.dist.all_reduce(tmin, op=self.dist.ReduceOp.MIN)
+            total, slowest, n = float(t.item()), float(tmin.item()), self.dist.get_world_size()
+        return total, n * slowest
 
     def stage_times(self, reps=2):
         """Matcher alone + the other stages: one batch at a time on slot 0, CUDA events on its stream (graphs bypassed)."""
@@ -471,7 +475,7 @@ def measure_config(name, c, args, rank, world, dev, dist, steps, warmup, passes,
         f, mm, bad = run.check("device", chain)
         checks["frames"] += f; checks["mismatches"] += mm; checks["failures"] += bad
     run.prepare_host()
-    ceiling_fps = run.copy_ceiling_fps()
+    ceiling_fps, ceiling_balanced_fps = run.copy_ceiling_fps()
     ms_e2e, _ = run.timed(run.step_host, steps, max(1, warmup), passes)
     fps_e2e = frames_total / (ms_e2e * 1e-3)
     if chain is not None:
@@ -485,7 +489,9 @@ def measure_config(name, c, args, rank, world, dev, dist, steps, warmup, passes,
                mdisp_evals_per_s=fps_dev * nominal / 1e6, mdisp_evals_effective_per_s=fps_dev * eff / 1e6,
                e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_frame=run.h2d_per_frame, d2h_bytes_per_frame=run.d2h_per_frame,
                         copy_ceiling_frames_per_s=ceiling_fps, frac_of_copy_ceiling=fps_e2e / ceiling_fps,
-                        ceiling="b200s_copy_probe: bare cudaMemcpyAsync D2H of one frame's products, pinned, 2 streams / 4 buffers, no kernels, all ranks at once (this run)"),
+                        copy_ceiling_equal_shares_frames_per_s=ceiling_balanced_fps, frac_of_equal_shares_ceiling=fps_e2e / ceiling_balanced_fps,
+                        ceiling="b200s_copy_probe: bare cudaMemcpyAsync D2H of one frame's products, pinned, 2 streams / 4 buffers, no kernels, all ranks at once "
+                                "(this run); equal_shares = N x the slowest rank's rate, what a job with the same number of frames on every rank can reach"),
                parity_checked=checks, _ms_dev=ms_dev, _ms_e2e=ms_e2e, _launches=launches)
     if want_roofline and rank == 0:
         t_bm, stages = run.stage_times()

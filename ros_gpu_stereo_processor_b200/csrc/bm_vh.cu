@@ -88,7 +88,11 @@ constexpr int NC = 16;               // output columns per VH thread
 #ifndef B200S_VH_MAXT
 #define B200S_VH_MAXT 768     // register budget of the matcher = 65536 / this (rounded down to a multiple of 8)
 #endif
-template <int R, int ND>
+// WIDE: preFilterCap 32..63.  The staged bytes reach 126, so a byte lane can hold ONE biased E word (128 + e in [2, 254])
+// but neither a pair sum nor a difference of two: every E word is widened on its own (the +128 of the entering and of
+// the leaving word cancel, so no bias accumulates and the W role has nothing to subtract).  About a quarter more VH
+// instructions than the narrow form, still well ahead of the bm_ws fallback these parameters used to take.
+template <int R, int ND, bool WIDE>
 __global__ void __launch_bounds__(B200S_VH_MAXT, 1) bm_vh_kernel(const VhParams P)
 {
     using namespace vh;
@@ -187,7 +191,17 @@ __global__ void __launch_bounds__(B200S_VH_MAXT, 1) bm_vh_kernel(const VhParams 
 
             // horizontal window sum of the first pixel: byte-pair sums (<= 252), then widened
             uint32_t Re, Ro;
-            {
+            if (WIDE) {
+                uint32_t se = 0, so = 0;
+#pragma unroll
+                for (int m = 0; m < B; ++m) {
+                    const uint32_t p = E[m] + 0x80808080u;                        // bytes 128 + e in [2, 254]
+                    se += p & 0x00ff00ffu;
+                    so += __byte_perm(p, 0, 0x4341);
+                }
+                Re = se - (uint32_t)(128 * B) * 0x00010001u;
+                Ro = so - (uint32_t)(128 * B) * 0x00010001u;
+            } else {
                 uint32_t se = 0, so = 0;
 #pragma unroll
                 for (int m = 0; m < R; ++m) {
@@ -216,7 +230,12 @@ __global__ void __launch_bounds__(B200S_VH_MAXT, 1) bm_vh_kernel(const VhParams 
                     *(uint2*)(ps + i * SWb) = make_uint2(Se[i], So[i]);
                     *(uint32_t*)(pk + i * KWb) = m + (uint32_t)g4;
                 }
-                if (i + 1 < NC) {
+                if (i + 1 < NC && WIDE) {
+                    const uint32_t Dn = E[i + B] + 0x80808080u, Dl = E[i] + 0x80808080u;     // entering / leaving column
+                    const uint32_t Dno = __byte_perm(Dn, 0, 0x4341), Dlo = __byte_perm(Dl, 0, 0x4341);
+                    Re += (Dn - (Dno << 8)) - (Dl - (Dlo << 8));
+                    Ro += Dno - Dlo;
+                } else if (i + 1 < NC) {
                     if (!(i & 1)) {
                         const uint32_t D = E[i + B] + 0x80808080u - E[i];      // bytes 128 + d in [4, 252]
                         const uint32_t Do = __byte_perm(D, 0, 0x4341);
@@ -246,7 +265,7 @@ __global__ void __launch_bounds__(B200S_VH_MAXT, 1) bm_vh_kernel(const VhParams 
                 uint8_t* krow = smem + P.oK[cb] + px * KWb;
                 uint8_t* srow = smem + P.oS[cb] + px * SWb;
                 // odd columns of a VH thread carry 128 per accumulated input row on every window sum
-                const int bias = (px & 1) ? 128 * (o + 2 * r + 1) : 0;
+                const int bias = (!WIDE && (px & 1)) ? 128 * (o + 2 * r + 1) : 0;
                 uint32_t best = 0xFFFFFFFFu;
                 if (ND > 0) {
 #pragma unroll
@@ -449,49 +468,50 @@ __global__ void __launch_bounds__(B200S_VH_MAXT, 1) bm_vh_kernel(const VhParams 
     }
 }
 
-template <int R, int ND>
+template <int R, int ND, bool WIDE>
 static cudaError_t launch_vh2(const VhParams& P, dim3 grid, int nt, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(bm_vh_kernel<R, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(bm_vh_kernel<R, ND, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // small tiles rely on several blocks per SM: ask for the whole shared-memory carve-out (no L1 use in this kernel)
-    e = cudaFuncSetAttribute(bm_vh_kernel<R, ND>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(bm_vh_kernel<R, ND, WIDE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    bm_vh_kernel<R, ND><<<grid, nt, smem, st>>>(P);
+    bm_vh_kernel<R, ND, WIDE><<<grid, nt, smem, st>>>(P);
     return cudaGetLastError();
 }
 
 // registers per thread of an instantiation (decides how many blocks share an SM), asked from the runtime once
-template <int R, int ND>
+template <int R, int ND, bool WIDE>
 static int vh_regs2()
 {
     static int regs = 0;
     if (!regs) {
         cudaFuncAttributes a;
-        regs = cudaFuncGetAttributes(&a, bm_vh_kernel<R, ND>) == cudaSuccess && a.numRegs > 0 ? a.numRegs : 80;
+        regs = cudaFuncGetAttributes(&a, bm_vh_kernel<R, ND, WIDE>) == cudaSuccess && a.numRegs > 0 ? a.numRegs : 80;
     }
     return regs;
 }
 template <int R>
-static int vh_regs1(int nd)
+static int vh_regs1(int nd, bool wide)
 {
-    if (nd == 256) return vh_regs2<R, 256>();
-    if (nd == 128) return vh_regs2<R, 128>();
-    if (nd == 64) return vh_regs2<R, 64>();
-    return vh_regs2<R, 0>();
+    if (wide) return vh_regs2<R, 0, true>();       // the wide form is instantiated for the generic disparity loop only
+    if (nd == 256) return vh_regs2<R, 256, false>();
+    if (nd == 128) return vh_regs2<R, 128, false>();
+    if (nd == 64) return vh_regs2<R, 64, false>();
+    return vh_regs2<R, 0, false>();
 }
-static int vh_regs(int r, int nd)
+static int vh_regs(int r, int nd, bool wide)
 {
     switch (r) {
-    case 2: return vh_regs1<2>(nd);
-    case 3: return vh_regs1<3>(nd);
-    case 4: return vh_regs1<4>(nd);
-    case 5: return vh_regs1<5>(nd);
-    case 6: return vh_regs1<6>(nd);
-    case 7: return vh_regs1<7>(nd);
-    case 8: return vh_regs1<8>(nd);
-    case 9: return vh_regs1<9>(nd);
-    case 10: return vh_regs1<10>(nd);
+    case 2: return vh_regs1<2>(nd, wide);
+    case 3: return vh_regs1<3>(nd, wide);
+    case 4: return vh_regs1<4>(nd, wide);
+    case 5: return vh_regs1<5>(nd, wide);
+    case 6: return vh_regs1<6>(nd, wide);
+    case 7: return vh_regs1<7>(nd, wide);
+    case 8: return vh_regs1<8>(nd, wide);
+    case 9: return vh_regs1<9>(nd, wide);
+    case 10: return vh_regs1<10>(nd, wide);
     default: return 80;
     }
 }
@@ -523,10 +543,11 @@ static const DeviceShape& device_shape()
 template <int R>
 static cudaError_t launch_vh(const VhParams& P, dim3 grid, int nt, size_t smem, cudaStream_t st)
 {
-    if (P.nd == 256) return launch_vh2<R, 256>(P, grid, nt, smem, st);
-    if (P.nd == 128) return launch_vh2<R, 128>(P, grid, nt, smem, st);
-    if (P.nd == 64) return launch_vh2<R, 64>(P, grid, nt, smem, st);
-    return launch_vh2<R, 0>(P, grid, nt, smem, st);
+    if (P.cap > 31) return launch_vh2<R, 0, true>(P, grid, nt, smem, st);
+    if (P.nd == 256) return launch_vh2<R, 256, false>(P, grid, nt, smem, st);
+    if (P.nd == 128) return launch_vh2<R, 128, false>(P, grid, nt, smem, st);
+    if (P.nd == 64) return launch_vh2<R, 64, false>(P, grid, nt, smem, st);
+    return launch_vh2<R, 0, false>(P, grid, nt, smem, st);
 }
 
 // returns 1 when launched, 0 when this configuration is not handled (caller falls back), < 0 on CUDA errors
@@ -536,14 +557,15 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
 {
     using vh::NC;
     const int nd = cfg.nd;
-    if (cfg.cap > 31 || r < 2 || r > 10 || (nd & 15)) return 0;   // byte lanes of E need 2*cap <= 62; R is a template parameter
+    if (cfg.cap > 63 || r < 2 || r > 10 || (nd & 15)) return 0;   // R is a template parameter; cap > 31 takes the WIDE form
+    const bool wide = cfg.cap > 31;
     const int G4 = nd / 4;
     static const int max_warps = getenv("B200S_VH_WARPS") ? atoi(getenv("B200S_VH_WARPS")) : 24;
     static const int stagers_env = getenv("B200S_STAGERS") ? atoi(getenv("B200S_STAGERS")) : 2;
     const DeviceShape& gpu = device_shape();
     static const int n_sm_env = getenv("B200S_WS_BLOCKS") ? atoi(getenv("B200S_WS_BLOCKS")) : 0;
     const int n_sm = n_sm_env > 0 ? n_sm_env : gpu.sms;
-    const int regs = vh_regs(r, nd);
+    const int regs = vh_regs(r, nd, wide);
     static const int ncb_env = getenv("B200S_VH_NCB") ? atoi(getenv("B200S_VH_NCB")) : 0;
     static const int bands_env = getenv("B200S_VH_BANDS") ? atoi(getenv("B200S_VH_BANDS")) : 0;
     static const int verbose = getenv("B200S_VH_VERBOSE") ? atoi(getenv("B200S_VH_VERBOSE")) : 0;
@@ -588,7 +610,7 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
         for (int bands = 1; bands <= max_bands; ++bands) {
             if (bands_env > 0 && bands != std::min(bands_env, max_bands)) continue;
             const int BH = (rows + bands - 1) / bands;
-            if (128 * (BH + 2 * r + 1) + 2 * cfg.cap * (2 * r + 1) * (2 * r + 1) > 65535) continue;   // bias of the odd columns
+            if ((wide ? 0 : 128 * (BH + 2 * r + 1)) + 2 * cfg.cap * (2 * r + 1) * (2 * r + 1) > 65535) continue;   // bias of the odd columns
             const int nb = tilesX * ((rows + BH - 1) / BH) * nf;
             const int per_sm = (nb + n_sm - 1) / n_sm;
             const int conc = std::min(occ, per_sm), waves = (per_sm + occ - 1) / occ;

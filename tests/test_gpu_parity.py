@@ -875,7 +875,10 @@ def test_disparity_ragged_shapes(proc, case):
 
 # ---- bm_vh_kernel: every window radius the kernel is instantiated for, several disparity counts and caps -----------
 VH_CASES = [(b, nd, cap) for b in (5, 7, 9, 11, 13, 15, 17, 19, 21) for nd, cap in ((64, 31), (256, 15))] + [
-    (11, 16, 31), (11, 48, 1), (15, 128, 31), (21, 96, 31), (9, 176, 20), (23, 64, 31), (11, 64, 32)]   # last two: v4 fallback
+    (11, 16, 31), (11, 48, 1), (15, 128, 31), (21, 96, 31), (9, 176, 20), (23, 64, 31)] + [                 # last one: v4 fallback
+    # preFilterCap 32..63: the wide form of bm_vh (every window radius; 2 * 63 * 21^2 = 55 566 still fits 16 bits)
+    (b, nd, cap) for b, nd, cap in ((5, 64, 63), (7, 128, 40), (9, 256, 63), (11, 256, 32), (11, 64, 63), (13, 48, 50), (15, 128, 63),
+                                    (17, 64, 33), (19, 96, 63), (21, 64, 63), (21, 256, 47))]
 
 
 @pytest.mark.parametrize("case", VH_CASES)
@@ -890,9 +893,11 @@ def test_disparity_vh_kernel_instantiations(proc, case):
     assert np.array_equal(got, want), _describe(got, want)
 
 
-def test_disparity_tall_band_bias_limit(proc):
-    """bm_vh keeps 128 per accumulated row on the odd columns' sums: a tall, narrow image forces long bands."""
-    p = O.BMParams(numDisparities=16, blockSize=21, preFilterCap=31)
+@pytest.mark.parametrize("cap", [31, 63])
+def test_disparity_tall_band_bias_limit(proc, cap):
+    """bm_vh keeps 128 per accumulated row on the odd columns' sums (narrow form): a tall, narrow image forces long bands;
+    the wide form (cap 63) has no such bias and may take the whole height as one band."""
+    p = O.BMParams(numDisparities=16, blockSize=21, preFilterCap=cap)
     L, R = synth.synth_pair(120, 1500, 16, seed=99)
     _set(proc, p)
     got = proc.computeDisparityBare(L, R)

@@ -1,5 +1,5 @@
 """Times the block matcher alone on one config (device-resident), for tuning.
-usage: python tools/time_bm.py C4 [reps] [frames_per_launch]      (environment: B200S_VH_* planner overrides, UNIQ, DISP12)"""
+usage: python tools/time_bm.py C4 [reps] [frames_per_launch]      (environment: B200S_VH_* planner overrides, UNIQ, DISP12, CAP)"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,7 +18,7 @@ frames = [synth.synth_pair(W, H, nd, 1234 + i) for i in range(min(nf, 4))]
 dL = [torch.from_numpy(np.ascontiguousarray(f[0])).cuda() for f in frames]
 dR = [torch.from_numpy(np.ascontiguousarray(f[1])).cuda() for f in frames]
 proc = m.GpuStereoProcessor(0)
-proc.setParams(numDisparities=nd, blockSize=c["block"], minDisparity=0, preFilterType=1, preFilterSize=9, preFilterCap=31,
+proc.setParams(numDisparities=nd, blockSize=c["block"], minDisparity=0, preFilterType=1, preFilterSize=9, preFilterCap=int(os.environ.get("CAP", "31")),
                textureThreshold=10, uniquenessRatio=int(os.environ.get("UNIQ", "15")), speckleWindowSize=0, speckleRange=0,
                disp12MaxDiff=int(os.environ.get("DISP12", "-1")))
 proc.configureSlots(1, H, W, nf)
