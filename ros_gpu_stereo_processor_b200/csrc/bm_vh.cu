@@ -50,6 +50,7 @@ struct VhParams {
     int oTc;                         // [8][ncols] words: texture column sums (ring over output rows)
     int oS[2], oK[2];
     int oMbar;                       // 8 mbarriers
+    int oX;                          // halo exchange of the VH threads (HX): uint4 [2 buffers][2 sides][chunks][VH threads]
     size_t pre_stride, disp_stride;  // bytes between the frames of a batch (blockIdx.z = frame)
 };
 
@@ -88,11 +89,42 @@ constexpr int NC = 16;               // output columns per VH thread
 #ifndef B200S_VH_MAXT
 #define B200S_VH_MAXT 768     // register budget of the matcher = 65536 / this (rounded down to a multiple of 8)
 #endif
+// E words e in [LO, HI) of one VH thread for the current row pair: E = |L-R|(entering row) - |L-R|(leaving row) as one
+// 32-bit integer, byte lanes in [-2cap, 2cap] with borrows between them (every later use adds a constant that makes all
+// four lanes positive).  st: stage buffer; wn / wo: the thread's right-row words (entering / leaving row).
+template <int LO, int HI, int NWORDS, int NEALL>
+__device__ __forceinline__ void vh_e_words(const uint8_t* st, int loffs, int ncolsP, const uint32_t (&wn)[NWORDS],
+                                           const uint32_t (&wo)[NWORDS], uint32_t (&E)[NEALL])
+{
+#pragma unroll
+    for (int q = LO / 4; q < (HI + 3) / 4; ++q) {
+        const uint4 ln4 = *(const uint4*)(st + loffs + 16 * q);
+        const uint4 lo4 = *(const uint4*)(st + 4 * ncolsP + loffs + 16 * q);
+        const uint32_t ln[4] = {ln4.x, ln4.y, ln4.z, ln4.w};
+        const uint32_t lo[4] = {lo4.x, lo4.y, lo4.z, lo4.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int e = 4 * q + c;
+            if (e >= LO && e < HI) {
+                const uint32_t rn = c ? __funnelshift_r(wn[q], wn[q + 1], 8 * c) : wn[q];
+                const uint32_t ro = c ? __funnelshift_r(wo[q], wo[q + 1], 8 * c) : wo[q];
+                E[e] = __vabsdiffu4(ln[c], rn) - __vabsdiffu4(lo[c], ro);
+            }
+        }
+    }
+}
+
+// HX (halo exchange): instead of recomputing the r window columns on either side of its 16 own columns (20 of 36 E words
+// at block 21), a VH thread computes its own 16 E words, publishes the first and the last r of them in shared memory and
+// reads its halos from the neighbouring column blocks after one named barrier of the VH warps (the two outermost column
+// blocks of the tile still compute their outer halo).  Used when the exchange buffer fits beside the S / key buffers
+// (nd <= 128); bit-identical by construction, the same words are just computed once.
+//
 // WIDE: preFilterCap 32..63.  The staged bytes reach 126, so a byte lane can hold ONE biased E word (128 + e in [2, 254])
 // but neither a pair sum nor a difference of two: every E word is widened on its own (the +128 of the entering and of
 // the leaving word cancel, so no bias accumulates and the W role has nothing to subtract).  About a quarter more VH
 // instructions than the narrow form, still well ahead of the bm_ws fallback these parameters used to take.
-template <int R, int ND, bool WIDE>
+template <int R, int ND, bool WIDE, bool HX>
 __global__ void __launch_bounds__(B200S_VH_MAXT, 1) bm_vh_kernel(const VhParams P)
 {
     using namespace vh;
@@ -168,26 +200,52 @@ __global__ void __launch_bounds__(B200S_VH_MAXT, 1) bm_vh_kernel(const VhParams 
                     wn[4 * q] = a.x; wn[4 * q + 1] = a.y; wn[4 * q + 2] = a.z; wn[4 * q + 3] = a.w;
                     wo[4 * q] = o4.x; wo[4 * q + 1] = o4.y; wo[4 * q + 2] = o4.z; wo[4 * q + 3] = o4.w;
                 }
-#pragma unroll
-                for (int q = 0; q < NLQ; ++q) {
-                    const uint4 ln4 = *(const uint4*)(st + loffs + 16 * q);
-                    const uint4 lo4 = *(const uint4*)(st + 4 * P.ncolsP + loffs + 16 * q);
-                    const uint32_t ln[4] = {ln4.x, ln4.y, ln4.z, ln4.w};
-                    const uint32_t lo[4] = {lo4.x, lo4.y, lo4.z, lo4.w};
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int e = 4 * q + c;
-                        if (e < NE) {
-                            const uint32_t rn = c ? __funnelshift_r(wn[q], wn[q + 1], 8 * c) : wn[q];
-                            const uint32_t ro = c ? __funnelshift_r(wo[q], wo[q + 1], 8 * c) : wo[q];
-                            // E = |L-R|(entering) - |L-R|(leaving) as one 32-bit integer: byte lanes in [-62, 62] with
-                            // borrows between them; every use below adds a constant that makes all four lanes positive
-                            E[e] = __vabsdiffu4(ln[c], rn) - __vabsdiffu4(lo[c], ro);
-                        }
-                    }
+                if (!HX) {
+                    vh_e_words<0, NE>(st, loffs, P.ncolsP, wn, wo, E);
+                } else {
+                    vh_e_words<R, R + NC>(st, loffs, P.ncolsP, wn, wo, E);                 // the thread's own 16 columns
+                    if (cb == 0) vh_e_words<0, R>(st, loffs, P.ncolsP, wn, wo, E);         // outer halos of the tile
+                    if (cb == P.NCB - 1) vh_e_words<R + NC, NE>(st, loffs, P.ncolsP, wn, wo, E);
                 }
             }
             mbar_arrive(mb + 8 * (MB_EMPTY_STAGE + sb));   // the staged rows are in registers now
+            if (HX) {
+                constexpr int CH = (R + 3) / 4;                    // 16-byte chunks per side
+                uint4* xb = (uint4*)(smem + P.oX) + (size_t)(j & 1) * 2 * CH * NVt;
+#pragma unroll
+                for (int q = 0; q < CH; ++q) {
+                    uint32_t a[4], b2[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int i = 4 * q + c;
+                        a[c] = i < R ? E[R + i] : 0u;              // first r own words: the right halo of block cb - 1
+                        b2[c] = i < R ? E[NC + i] : 0u;            // last r own words: the left halo of block cb + 1
+                    }
+                    xb[(0 * CH + q) * NVt + tid] = make_uint4(a[0], a[1], a[2], a[3]);
+                    xb[(1 * CH + q) * NVt + tid] = make_uint4(b2[0], b2[1], b2[2], b2[3]);
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(NVt) : "memory");
+                if (cb > 0) {
+#pragma unroll
+                    for (int q = 0; q < CH; ++q) {
+                        const uint4 v = xb[(1 * CH + q) * NVt + tid - G4];
+                        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (4 * q + c < R) E[4 * q + c] = w4[c];
+                    }
+                }
+                if (cb < P.NCB - 1) {
+#pragma unroll
+                    for (int q = 0; q < CH; ++q) {
+                        const uint4 v = xb[(0 * CH + q) * NVt + tid + G4];
+                        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (4 * q + c < R) E[R + NC + 4 * q + c] = w4[c];
+                    }
+                }
+            }
 
             // horizontal window sum of the first pixel: byte-pair sums (<= 252), then widened
             uint32_t Re, Ro;
@@ -468,37 +526,39 @@ __global__ void __launch_bounds__(B200S_VH_MAXT, 1) bm_vh_kernel(const VhParams 
     }
 }
 
-template <int R, int ND, bool WIDE>
+template <int R, int ND, bool WIDE, bool HX>
 static cudaError_t launch_vh2(const VhParams& P, dim3 grid, int nt, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(bm_vh_kernel<R, ND, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(bm_vh_kernel<R, ND, WIDE, HX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // small tiles rely on several blocks per SM: ask for the whole shared-memory carve-out (no L1 use in this kernel)
-    e = cudaFuncSetAttribute(bm_vh_kernel<R, ND, WIDE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(bm_vh_kernel<R, ND, WIDE, HX>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    bm_vh_kernel<R, ND, WIDE><<<grid, nt, smem, st>>>(P);
+    bm_vh_kernel<R, ND, WIDE, HX><<<grid, nt, smem, st>>>(P);
     return cudaGetLastError();
 }
 
 // registers per thread of an instantiation (decides how many blocks share an SM), asked from the runtime once
-template <int R, int ND, bool WIDE>
+template <int R, int ND, bool WIDE, bool HX>
 static int vh_regs2()
 {
     static int regs = 0;
     if (!regs) {
         cudaFuncAttributes a;
-        regs = cudaFuncGetAttributes(&a, bm_vh_kernel<R, ND, WIDE>) == cudaSuccess && a.numRegs > 0 ? a.numRegs : 80;
+        regs = cudaFuncGetAttributes(&a, bm_vh_kernel<R, ND, WIDE, HX>) == cudaSuccess && a.numRegs > 0 ? a.numRegs : 80;
     }
     return regs;
 }
+// the halo exchange is instantiated where its buffer can fit: 64 and 128 disparities, narrow form
+static bool vh_hx_available(int nd, bool wide) { return !wide && (nd == 64 || nd == 128); }
 template <int R>
 static int vh_regs1(int nd, bool wide)
 {
-    if (wide) return vh_regs2<R, 0, true>();       // the wide form is instantiated for the generic disparity loop only
-    if (nd == 256) return vh_regs2<R, 256, false>();
-    if (nd == 128) return vh_regs2<R, 128, false>();
-    if (nd == 64) return vh_regs2<R, 64, false>();
-    return vh_regs2<R, 0, false>();
+    if (wide) return vh_regs2<R, 0, true, false>();       // the wide form is instantiated for the generic disparity loop only
+    if (nd == 256) return vh_regs2<R, 256, false, false>();
+    if (nd == 128) return vh_regs2<R, 128, false, true>();
+    if (nd == 64) return vh_regs2<R, 64, false, true>();
+    return vh_regs2<R, 0, false, false>();
 }
 static int vh_regs(int r, int nd, bool wide)
 {
@@ -543,11 +603,11 @@ static const DeviceShape& device_shape()
 template <int R>
 static cudaError_t launch_vh(const VhParams& P, dim3 grid, int nt, size_t smem, cudaStream_t st)
 {
-    if (P.cap > 31) return launch_vh2<R, 0, true>(P, grid, nt, smem, st);
-    if (P.nd == 256) return launch_vh2<R, 256, false>(P, grid, nt, smem, st);
-    if (P.nd == 128) return launch_vh2<R, 128, false>(P, grid, nt, smem, st);
-    if (P.nd == 64) return launch_vh2<R, 64, false>(P, grid, nt, smem, st);
-    return launch_vh2<R, 0, false>(P, grid, nt, smem, st);
+    if (P.cap > 31) return launch_vh2<R, 0, true, false>(P, grid, nt, smem, st);
+    if (P.nd == 256) return launch_vh2<R, 256, false, false>(P, grid, nt, smem, st);
+    if (P.nd == 128) return P.oX >= 0 ? launch_vh2<R, 128, false, true>(P, grid, nt, smem, st) : launch_vh2<R, 128, false, false>(P, grid, nt, smem, st);
+    if (P.nd == 64) return P.oX >= 0 ? launch_vh2<R, 64, false, true>(P, grid, nt, smem, st) : launch_vh2<R, 64, false, false>(P, grid, nt, smem, st);
+    return launch_vh2<R, 0, false, false>(P, grid, nt, smem, st);
 }
 
 // returns 1 when launched, 0 when this configuration is not handled (caller falls back), < 0 on CUDA errors
@@ -569,6 +629,7 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
     static const int ncb_env = getenv("B200S_VH_NCB") ? atoi(getenv("B200S_VH_NCB")) : 0;
     static const int bands_env = getenv("B200S_VH_BANDS") ? atoi(getenv("B200S_VH_BANDS")) : 0;
     static const int verbose = getenv("B200S_VH_VERBOSE") ? atoi(getenv("B200S_VH_VERBOSE")) : 0;
+    static const int use_hx = getenv("B200S_VH_HX") ? atoi(getenv("B200S_VH_HX")) : 1;
     const size_t smem_max = (size_t)gpu.smem_per_block - 1024;
     const int X0base = XA - ((XA - r - lofs) & 3);
     const int need = XB - X0base;
@@ -599,6 +660,12 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
         for (int s2 = 0; s2 < 2; ++s2) { P.oK[s2] = (int)o; o += (size_t)TW * P.KWb; }
         for (int s2 = 0; s2 < 2; ++s2) { P.oS[s2] = (int)o; o += (size_t)TW * P.SWb; }
         P.oMbar = (int)o; o += 8 * vh::MB_COUNT;
+        P.oX = -1;
+        if (use_hx && vh_hx_available(nd, wide) && NCB > 1) {
+            o = (o + 15) & ~(size_t)15;
+            const size_t xbytes = (size_t)2 * 2 * ((r + 3) / 4) * 16 * (size_t)(nVw * 32);
+            if (o + xbytes <= smem_max) { P.oX = (int)o; o += xbytes; }
+        }
         if (o > smem_max) continue;
         P.TW = TW; P.ncols = ncols; P.NCB = NCB; P.G4 = G4;
         P.nVw = nVw; P.nWw = nWw; P.nSw = nSw;
@@ -638,8 +705,8 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
     P.BH = (rows + best_bands - 1) / best_bands;
     dim3 grid(tilesX, (rows + P.BH - 1) / P.BH, nf);
     if (verbose)
-        fprintf(stderr, "bm_vh plan: NCB=%d TW=%d BH=%d grid=%dx%dx%d warps V/W/S=%d/%d/%d smem=%zu\n", P.NCB, P.TW, P.BH, grid.x, grid.y,
-                grid.z, P.nVw, P.nWw, P.nSw, smem);
+        fprintf(stderr, "bm_vh plan: NCB=%d TW=%d BH=%d grid=%dx%dx%d warps V/W/S=%d/%d/%d smem=%zu hx=%d\n", P.NCB, P.TW, P.BH, grid.x, grid.y,
+                grid.z, P.nVw, P.nWw, P.nSw, smem, P.oX >= 0);
     cudaError_t e;
     switch (r) {
     case 2: e = launch_vh<2>(P, grid, nt, smem, st); break;

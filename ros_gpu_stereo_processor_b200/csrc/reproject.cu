@@ -72,9 +72,10 @@ __global__ void __launch_bounds__(256) disparity_to_float_kernel(const int16_t* 
 constexpr int RP_ROWS = B200S_PACK_ROWS;      // block = 32 columns x RP_ROWS warps
 constexpr int RP_RPW = 4;                     // consecutive image rows per warp (column-only terms are computed once)
 
-// bit (4 r + c) set = Q[r][c] != 0.  image_geometry's Q (StereoCameraModel::updateQ) has exactly these seven entries:
-//   X = Q00 x + Q03,  Y = Q11 y + Q13,  Z = Q23,  W = Q32 d + Q33
-constexpr unsigned QMASK_STEREO = (1u << 0) | (1u << 3) | (1u << 5) | (1u << 7) | (1u << 11) | (1u << 14) | (1u << 15);
+// bit (4 r + c) set = Q[r][c] != 0.  image_geometry's Q (StereoCameraModel::updateQ) has exactly these entries:
+//   X = Q00 x + Q03,  Y = Q11 y + Q13,  Z = Q23,  W = Q32 d + Q33      (Q33 = fy (cx - cx') is zero for equal principal points)
+constexpr unsigned QMASK_STEREO0 = (1u << 0) | (1u << 3) | (1u << 5) | (1u << 7) | (1u << 11) | (1u << 14);
+constexpr unsigned QMASK_STEREO = QMASK_STEREO0 | (1u << 15);
 
 // float(a / w): one correctly rounded reciprocal shared by the three coordinates, see reproject_pack_kernel
 __device__ __forceinline__ float div_to_float(double a, double w, double rw)
@@ -88,9 +89,10 @@ __device__ __forceinline__ float div_to_float(double a, double w, double rw)
 }
 
 // cv::reprojectImageTo3D(handleMissingValues = true) + PointCloud2 records (+ the float disparity plane) in one pass.
-// STDQ: Q has the sparsity of image_geometry's stereo model (the only Q the reference can produce); the terms that depend
-// on the column only are then computed once per thread and reused for the RP_RPW rows its warp walks.  The generic path
-// evaluates the full 4-term products with zero entries skipped.  Both give the bytes of the CPU code: every FP64
+// STDQ (1: with Q33, 2: Q33 == 0, 0: any Q): Q has the sparsity of image_geometry's stereo model (the only Q the reference
+// can produce); the terms that depend on the column only are then computed once per thread and reused for the RP_RPW rows
+// its warp walks.  The generic path evaluates the full 4-term products with zero entries skipped.  The loads of all rows
+// of a warp are issued before the arithmetic of the first one.  Both give the bytes of the CPU code: every FP64
 // operation is an explicit round-to-nearest intrinsic in the CPU's order.
 //
 // float(a / w) for the three coordinates, a = (double)(float)h[r]: the correctly rounded FP64 division is a long
@@ -98,7 +100,7 @@ __device__ __forceinline__ float div_to_float(double a, double w, double rw)
 // quotient within 2 ulp (FP64) of a / w; rounding THAT to float gives the same float as rounding the exact quotient unless
 // it lies within a few FP64 ulps of a float rounding boundary (29 dropped bits = 0x10000000).  Those rare lanes, and
 // non-finite or tiny quotients, take the exact division: the result is bit-identical always.
-template <bool STDQ>
+template <int STDQ>
 __global__ void __launch_bounds__(32 * RP_ROWS) reproject_pack_kernel(const int16_t* __restrict__ d16, int W, int H, double cxd,
                                                              const double* __restrict__ Q, const int* __restrict__ min_d16,
                                                              const uint8_t* __restrict__ color, int ch,
@@ -135,6 +137,23 @@ __global__ void __launch_bounds__(32 * RP_ROWS) reproject_pack_kernel(const int1
     }
     const bool xin = x < W;
     const bool full_row = x0 + 32 <= W;
+    // all global loads of the warp's rows first (the kernel waited on one dependent load per row otherwise)
+    int dvs[RP_RPW];
+    uint32_t bgrs[RP_RPW];
+#pragma unroll
+    for (int rr = 0; rr < RP_RPW; ++rr) {
+        const int y = yw + rr;
+        dvs[rr] = 0;
+        bgrs[rr] = 0;
+        if (xin && y < H) {
+            const size_t i = (size_t)y * W + x;
+            dvs[rr] = (int)d16[i];
+            if (pc2) {
+                if (ch == 3) bgrs[rr] = (uint32_t)color[i * 3] | ((uint32_t)color[i * 3 + 1] << 8) | ((uint32_t)color[i * 3 + 2] << 16);
+                else { const uint32_t g = color ? color[i] : 0; bgrs[rr] = g | (g << 8) | (g << 16); }
+            }
+        }
+    }
 #pragma unroll
     for (int rr = 0; rr < RP_RPW; ++rr) {
         const int y = yw + rr;
@@ -145,7 +164,7 @@ __global__ void __launch_bounds__(32 * RP_ROWS) reproject_pack_kernel(const int1
         // for posted PCIe writes when pc2 is pinned host memory.  Partial warps at the right edge store per thread.
         uint32_t ux = 0x7fc00000u, uy = 0x7fc00000u, uz = 0x7fc00000u;
         const size_t i = xin ? (size_t)y * W + x : 0;
-        const int dv = xin ? (int)d16[i] : 0;
+        const int dv = dvs[rr];
         if (df && xin) df[i] = disp_to_float(dv, cxd);       // the DisparityImage payload from the same pass (convertTo)
         // missing value (d == min over the image): cv::reprojectImageTo3D sets Z = 10000, which isValidPoint rejects, so
         // the record is NaN xyz + colour whatever X and Y were; no arithmetic needed unless the xyz plane is wanted too
@@ -156,7 +175,8 @@ __global__ void __launch_bounds__(32 * RP_ROWS) reproject_pack_kernel(const int1
                 a[0] = ax;
                 a[1] = (double)__double2float_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(q11, (double)y)), q13));
                 a[2] = az;
-                w = __dadd_rn(__dadd_rn(0.0, __dmul_rn(q32, d)), q33);
+                w = __dadd_rn(0.0, __dmul_rn(q32, d));
+                if (STDQ == 1) w = __dadd_rn(w, q33);
             } else {
                 double h[4];
 #pragma unroll
@@ -186,11 +206,7 @@ __global__ void __launch_bounds__(32 * RP_ROWS) reproject_pack_kernel(const int1
             }
         }
         if (!pc2) continue;
-        uint32_t bgr = 0;
-        if (xin) {
-            if (ch == 3) bgr = (uint32_t)color[i * 3] | ((uint32_t)color[i * 3 + 1] << 8) | ((uint32_t)color[i * 3 + 2] << 16);
-            else { uint32_t g = color ? color[i] : 0; bgr = g | (g << 8) | (g << 16); }
-        }
+        const uint32_t bgr = bgrs[rr];
         if (full_row) {
             uint4* row = (uint4*)(pc2 + ((size_t)y * W + x0) * 32);
 #pragma unroll
@@ -264,13 +280,17 @@ int launch_reproject_pack(const int16_t* d16, int W, int H, double cxd, const do
     ReprojectExtras ex;
     if (extra) ex = *extra;
     if (qmask == QMASK_STEREO)
-        reproject_pack_kernel<true><<<g, 32 * RP_ROWS, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask, d_stride, color_stride,
-                                                         xyz_stride, frame_dst(pc2_stride, pc2_list), ex.dmin_const, ex.df,
-                                                         frame_dst(ex.df_stride, ex.df_list), ex.color_tab);
+        reproject_pack_kernel<1><<<g, 32 * RP_ROWS, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask, d_stride, color_stride,
+                                                      xyz_stride, frame_dst(pc2_stride, pc2_list), ex.dmin_const, ex.df,
+                                                      frame_dst(ex.df_stride, ex.df_list), ex.color_tab);
+    else if (qmask == QMASK_STEREO0)
+        reproject_pack_kernel<2><<<g, 32 * RP_ROWS, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask, d_stride, color_stride,
+                                                      xyz_stride, frame_dst(pc2_stride, pc2_list), ex.dmin_const, ex.df,
+                                                      frame_dst(ex.df_stride, ex.df_list), ex.color_tab);
     else
-        reproject_pack_kernel<false><<<g, 32 * RP_ROWS, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask, d_stride, color_stride,
-                                                          xyz_stride, frame_dst(pc2_stride, pc2_list), ex.dmin_const, ex.df,
-                                                          frame_dst(ex.df_stride, ex.df_list), ex.color_tab);
+        reproject_pack_kernel<0><<<g, 32 * RP_ROWS, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask, d_stride, color_stride,
+                                                      xyz_stride, frame_dst(pc2_stride, pc2_list), ex.dmin_const, ex.df,
+                                                      frame_dst(ex.df_stride, ex.df_list), ex.color_tab);
     return 1;
 }
 
