@@ -114,11 +114,14 @@ __device__ __forceinline__ void vh_e_words(const uint8_t* st, int loffs, int nco
     }
 }
 
-// HX (halo exchange): instead of recomputing the r window columns on either side of its 16 own columns (20 of 36 E words
-// at block 21), a VH thread computes its own 16 E words, publishes the first and the last r of them in shared memory and
-// reads its halos from the neighbouring column blocks after one named barrier of the VH warps (the two outermost column
-// blocks of the tile still compute their outer halo).  Used when the exchange buffer fits beside the S / key buffers
-// (nd <= 128); bit-identical by construction, the same words are just computed once.
+// HX (halo exchange) -- an experiment that is NOT in the default build (-DB200S_VH_HX_BUILD instantiates it,
+// B200S_VH_HX=1 selects it): instead of recomputing the r window columns on either side of its 16 own columns (20 of 36 E
+// words at block 21), a VH thread computes its own 16 E words, publishes the first and the last r of them in shared
+// memory and reads its halos from the neighbouring column blocks after one named barrier of the VH warps.  Bit-identical
+// (all parity tests pass with it) and 1.6 - 1.7 x SLOWER on C1 / C2 / C3 (profiles/r02_experiments.md section 6): the
+// barrier puts the VH warps in lock-step every row, which is exactly what the mbarrier hand-over had removed -- the
+// overlap of the VABSDIFF-heavy and the IMAD-heavy phases of different warps on the two integer pipes is worth more than
+// the 12 - 20 % of instructions the exchange saves.
 //
 // WIDE: preFilterCap 32..63.  The staged bytes reach 126, so a byte lane can hold ONE biased E word (128 + e in [2, 254])
 // but neither a pair sum nor a difference of two: every E word is widened on its own (the +128 of the entering and of
@@ -549,15 +552,20 @@ static int vh_regs2()
     }
     return regs;
 }
-// the halo exchange is instantiated where its buffer can fit: 64 and 128 disparities, narrow form
-static bool vh_hx_available(int nd, bool wide) { return !wide && (nd == 64 || nd == 128); }
+// the halo exchange experiment: instantiated only with -DB200S_VH_HX_BUILD, where its buffer can fit (64 / 128 disparities)
+#ifdef B200S_VH_HX_BUILD
+constexpr bool VH_HX_BUILT = true;
+#else
+constexpr bool VH_HX_BUILT = false;
+#endif
+static bool vh_hx_available(int nd, bool wide) { return VH_HX_BUILT && !wide && (nd == 64 || nd == 128); }
 template <int R>
 static int vh_regs1(int nd, bool wide)
 {
     if (wide) return vh_regs2<R, 0, true, false>();       // the wide form is instantiated for the generic disparity loop only
     if (nd == 256) return vh_regs2<R, 256, false, false>();
-    if (nd == 128) return vh_regs2<R, 128, false, true>();
-    if (nd == 64) return vh_regs2<R, 64, false, true>();
+    if (nd == 128) return vh_regs2<R, 128, false, VH_HX_BUILT>();
+    if (nd == 64) return vh_regs2<R, 64, false, VH_HX_BUILT>();
     return vh_regs2<R, 0, false, false>();
 }
 static int vh_regs(int r, int nd, bool wide)
@@ -605,8 +613,8 @@ static cudaError_t launch_vh(const VhParams& P, dim3 grid, int nt, size_t smem, 
 {
     if (P.cap > 31) return launch_vh2<R, 0, true, false>(P, grid, nt, smem, st);
     if (P.nd == 256) return launch_vh2<R, 256, false, false>(P, grid, nt, smem, st);
-    if (P.nd == 128) return P.oX >= 0 ? launch_vh2<R, 128, false, true>(P, grid, nt, smem, st) : launch_vh2<R, 128, false, false>(P, grid, nt, smem, st);
-    if (P.nd == 64) return P.oX >= 0 ? launch_vh2<R, 64, false, true>(P, grid, nt, smem, st) : launch_vh2<R, 64, false, false>(P, grid, nt, smem, st);
+    if (P.nd == 128) return P.oX >= 0 ? launch_vh2<R, 128, false, VH_HX_BUILT>(P, grid, nt, smem, st) : launch_vh2<R, 128, false, false>(P, grid, nt, smem, st);
+    if (P.nd == 64) return P.oX >= 0 ? launch_vh2<R, 64, false, VH_HX_BUILT>(P, grid, nt, smem, st) : launch_vh2<R, 64, false, false>(P, grid, nt, smem, st);
     return launch_vh2<R, 0, false, false>(P, grid, nt, smem, st);
 }
 
@@ -629,7 +637,7 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
     static const int ncb_env = getenv("B200S_VH_NCB") ? atoi(getenv("B200S_VH_NCB")) : 0;
     static const int bands_env = getenv("B200S_VH_BANDS") ? atoi(getenv("B200S_VH_BANDS")) : 0;
     static const int verbose = getenv("B200S_VH_VERBOSE") ? atoi(getenv("B200S_VH_VERBOSE")) : 0;
-    static const int use_hx = getenv("B200S_VH_HX") ? atoi(getenv("B200S_VH_HX")) : 1;
+    static const int use_hx = getenv("B200S_VH_HX") ? atoi(getenv("B200S_VH_HX")) : 0;
     const size_t smem_max = (size_t)gpu.smem_per_block - 1024;
     const int X0base = XA - ((XA - r - lofs) & 3);
     const int need = XB - X0base;

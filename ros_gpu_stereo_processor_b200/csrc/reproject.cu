@@ -71,6 +71,9 @@ __global__ void __launch_bounds__(256) disparity_to_float_kernel(const int16_t* 
 #endif
 constexpr int RP_ROWS = B200S_PACK_ROWS;      // block = 32 columns x RP_ROWS warps
 constexpr int RP_RPW = 4;                     // consecutive image rows per warp (column-only terms are computed once)
+#ifndef B200S_PACK_PREFETCH
+#define B200S_PACK_PREFETCH 1                 // 1: issue the loads of all rows of a warp before the arithmetic of the first
+#endif
 
 // bit (4 r + c) set = Q[r][c] != 0.  image_geometry's Q (StereoCameraModel::updateQ) has exactly these entries:
 //   X = Q00 x + Q03,  Y = Q11 y + Q13,  Z = Q23,  W = Q32 d + Q33      (Q33 = fy (cx - cx') is zero for equal principal points)
@@ -101,7 +104,12 @@ __device__ __forceinline__ float div_to_float(double a, double w, double rw)
 // it lies within a few FP64 ulps of a float rounding boundary (29 dropped bits = 0x10000000).  Those rare lanes, and
 // non-finite or tiny quotients, take the exact division: the result is bit-identical always.
 template <int STDQ>
-__global__ void __launch_bounds__(32 * RP_ROWS) reproject_pack_kernel(const int16_t* __restrict__ d16, int W, int H, double cxd,
+#if B200S_PACK_PREFETCH
+#define B200S_PACK_BOUNDS __launch_bounds__(32 * RP_ROWS, 1536 / (32 * RP_ROWS))    /* 40 registers: six blocks per SM */
+#else
+#define B200S_PACK_BOUNDS __launch_bounds__(32 * RP_ROWS)
+#endif
+__global__ void B200S_PACK_BOUNDS reproject_pack_kernel(const int16_t* __restrict__ d16, int W, int H, double cxd,
                                                              const double* __restrict__ Q, const int* __restrict__ min_d16,
                                                              const uint8_t* __restrict__ color, int ch,
                                                              float* __restrict__ xyz, uint8_t* __restrict__ pc2, unsigned qmask,
@@ -145,7 +153,7 @@ __global__ void __launch_bounds__(32 * RP_ROWS) reproject_pack_kernel(const int1
         const int y = yw + rr;
         dvs[rr] = 0;
         bgrs[rr] = 0;
-        if (xin && y < H) {
+        if (B200S_PACK_PREFETCH && xin && y < H) {
             const size_t i = (size_t)y * W + x;
             dvs[rr] = (int)d16[i];
             if (pc2) {
@@ -164,7 +172,7 @@ __global__ void __launch_bounds__(32 * RP_ROWS) reproject_pack_kernel(const int1
         // for posted PCIe writes when pc2 is pinned host memory.  Partial warps at the right edge store per thread.
         uint32_t ux = 0x7fc00000u, uy = 0x7fc00000u, uz = 0x7fc00000u;
         const size_t i = xin ? (size_t)y * W + x : 0;
-        const int dv = dvs[rr];
+        const int dv = B200S_PACK_PREFETCH ? dvs[rr] : (xin ? (int)d16[i] : 0);
         if (df && xin) df[i] = disp_to_float(dv, cxd);       // the DisparityImage payload from the same pass (convertTo)
         // missing value (d == min over the image): cv::reprojectImageTo3D sets Z = 10000, which isValidPoint rejects, so
         // the record is NaN xyz + colour whatever X and Y were; no arithmetic needed unless the xyz plane is wanted too
@@ -206,7 +214,11 @@ __global__ void __launch_bounds__(32 * RP_ROWS) reproject_pack_kernel(const int1
             }
         }
         if (!pc2) continue;
-        const uint32_t bgr = bgrs[rr];
+        uint32_t bgr = bgrs[rr];
+        if (!B200S_PACK_PREFETCH && xin) {
+            if (ch == 3) bgr = (uint32_t)color[i * 3] | ((uint32_t)color[i * 3 + 1] << 8) | ((uint32_t)color[i * 3 + 2] << 16);
+            else { const uint32_t g = color ? color[i] : 0; bgr = g | (g << 8) | (g << 16); }
+        }
         if (full_row) {
             uint4* row = (uint4*)(pc2 + ((size_t)y * W + x0) * 32);
 #pragma unroll
