@@ -410,7 +410,11 @@ int b200s_create(int device, b200s_handle** out)
     *out = nullptr;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return B200S_ECUDA;
-    if (cudaSetDevice(device) != cudaSuccess) return B200S_ECUDA;
+    DeviceGuard g(device);      // the caller's current device is restored when b200s_create returns
+    {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur != device) return B200S_ECUDA;
+    }
     b200s_handle* h = new (std::nothrow) b200s_handle();
     if (!h) return B200S_ENOMEM;
     h->device = device;
@@ -1056,13 +1060,13 @@ int b200s_last_bm_time(b200s_handle* h, int slot, float* ms, double* evals)
 int b200s_host_alloc(void** p, size_t bytes)
 {
     if (!p) return B200S_EINVAL;
-    return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? B200S_OK : B200S_ENOMEM;
+    return cudaHostAlloc(p, bytes, cudaHostAllocPortable) == cudaSuccess ? B200S_OK : B200S_ENOMEM;   // pinned for every GPU of the process
 }
 
 int b200s_host_alloc_mode(void** p, size_t bytes, int mode)
 {
     if (!p) return B200S_EINVAL;
-    return cudaHostAlloc(p, bytes, mode == 1 ? cudaHostAllocWriteCombined : cudaHostAllocDefault) == cudaSuccess ? B200S_OK : B200S_ENOMEM;
+    return cudaHostAlloc(p, bytes, cudaHostAllocPortable | (mode == 1 ? cudaHostAllocWriteCombined : 0)) == cudaSuccess ? B200S_OK : B200S_ENOMEM;
 }
 
 int b200s_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? B200S_OK : B200S_ECUDA; }
