@@ -168,34 +168,16 @@ __global__ void __launch_bounds__(FT_THREADS) rectify_xsobel_kernel(RectSide sl,
     const int x0 = blockIdx.x * FTX, y0 = blockIdx.y * FTY;
     int2 m[FT_PER];
     bool ok[FT_PER];
-    // tile pixel i = threadIdx.x + FT_THREADS * k, row-major over the (FTX + 2)-wide tile: (ty, tx) advance by a constant step
-    constexpr int TWD = FTX + 2, STEP_Y = FT_THREADS / TWD, STEP_X = FT_THREADS - STEP_Y * TWD;
-    const int ty0 = threadIdx.x / TWD, tx0 = threadIdx.x - ty0 * TWD;
-    // tiles whose halo lies inside the image (all but the outermost ring) need no mirroring and no bounds tests
-    const bool interior = x0 >= 1 && x0 + FTX + 1 <= W && y0 >= 1 && y0 + FTY + 1 <= H;
-    if (interior) {
-        int ty = ty0, tx = tx0;
 #pragma unroll
-        for (int k = 0; k < FT_PER; ++k) {
-            ok[k] = threadIdx.x + FT_THREADS * k < FT_N;
-            m[k] = make_int2(0, 0);
-            if (ok[k]) m[k] = map_at<MODE>(S.map, S.cm, x0 + tx - 1, y0 + ty - 1, W);
-            tx += STEP_X; ty += STEP_Y;
-            if (tx >= TWD) { tx -= TWD; ++ty; }
-        }
-    } else {
-        int ty = ty0, tx = tx0;
-#pragma unroll
-        for (int k = 0; k < FT_PER; ++k) {
-            const int x = x0 + tx - 1, y = y0 + ty - 1;
-            tx += STEP_X; ty += STEP_Y;
-            if (tx >= TWD) { tx -= TWD; ++ty; }
-            // rows are mirrored for the Sobel taps: the halo row above row 0 is row 1, below row H-1 is row H-2
-            const int ys = y < 0 ? 1 : (y >= H ? H - 2 : y);
-            ok[k] = threadIdx.x + FT_THREADS * k < FT_N && x >= 0 && x < W && ys >= 0 && ys < H;
-            m[k] = make_int2(0, 0);
-            if (ok[k]) m[k] = map_at<MODE>(S.map, S.cm, x, ys, W);
-        }
+    for (int k = 0; k < FT_PER; ++k) {
+        const int i = threadIdx.x + FT_THREADS * k;
+        const int ty = i / (FTX + 2), tx = i - ty * (FTX + 2);
+        const int x = x0 + tx - 1, y = y0 + ty - 1;
+        // rows are mirrored for the Sobel taps: the halo row above row 0 is row 1, below row H-1 is row H-2
+        const int ys = y < 0 ? 1 : (y >= H ? H - 2 : y);
+        ok[k] = i < FT_N && x >= 0 && x < W && ys >= 0 && ys < H;
+        m[k] = make_int2(0, 0);
+        if (ok[k]) m[k] = map_at<MODE>(S.map, S.cm, x, ys, W);
     }
     // Source window of the tile: the 2x2 footprints of all tile pixels lie in a small bounding box of the source image
     // (a smooth map moves a 66x18 tile to roughly 70x22 source pixels).  The block finds that box (min / max of the
@@ -275,13 +257,11 @@ __global__ void __launch_bounds__(FT_THREADS) rectify_xsobel_kernel(RectSide sl,
             }
         }
     }
-    int ty4 = ty0, tx4 = tx0;
 #pragma unroll
     for (int k = 0; k < FT_PER; ++k) {
-        const int ty = ty4, tx = tx4;
-        tx4 += STEP_X; ty4 += STEP_Y;
-        if (tx4 >= TWD) { tx4 -= TWD; ++ty4; }
-        if (threadIdx.x + FT_THREADS * k >= FT_N) continue;
+        const int i = threadIdx.x + FT_THREADS * k;
+        if (i >= FT_N) continue;
+        const int ty = i / (FTX + 2), tx = i - ty * (FTX + 2);
         const int a = m[k].x & 31, b = m[k].y & 31;
         // (32-a)(32-b) s00 + a(32-b) s01 + (32-a) b s10 + a b s11, factored (exact in integers)
         const int top = 32 * s00[k] + a * (s01[k] - s00[k]), bot = 32 * s10[k] + a * (s11[k] - s10[k]);
