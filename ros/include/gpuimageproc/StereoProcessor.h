@@ -68,9 +68,11 @@ class StereoProcessor
     boost::shared_ptr<message_filters::Synchronizer<ApproxImages> > approximate_sync_images_;
     boost::shared_ptr<message_filters::Synchronizer<ApproxImagesAndInfo> > approximate_sync_images_and_info_;
 
+    // the eleven output topics, one publisher per ConnectedTopics bit (table in StereoProcessor.cpp)
+    enum { N_TOPICS = 11 };
+    ros::Publisher publishers_[N_TOPICS];
+    ros::Publisher *pub(ConnectedTopics::Topic t) { return &publishers_[__builtin_ctz((unsigned)t)]; }
     boost::mutex connect_mutex_;
-    ros::Publisher pub_mono_left_, pub_mono_right_, pub_color_left_, pub_color_right_, pub_mono_rect_left_, pub_mono_rect_right_,
-        pub_color_rect_left_, pub_color_rect_right_, pub_disparity_, pub_disparity_vis_, pub_pointcloud_;
     ConnectedTopics connected_;
     std::string camera_info_file_left_, camera_info_file_right_;
     bool camera_info_from_files_;

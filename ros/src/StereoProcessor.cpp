@@ -24,6 +24,18 @@ const std::string StereoProcessor::CAMERA_TOPIC_INFO = "/camera_info";
 namespace
 {
 
+// The published surface of the reference (src/StereoProcessor.cpp:89-100), as data: bit i of ConnectedTopics <-> entry i.
+enum TopicKind { KIND_IMAGE, KIND_DISPARITY, KIND_CLOUD };
+struct TopicDesc
+{
+    const char *name;
+    TopicKind kind;
+};
+const TopicDesc kTopics[] = {
+    {"left/image_mono", KIND_IMAGE},  {"right/image_mono", KIND_IMAGE},  {"left/image_color", KIND_IMAGE}, {"right/image_color", KIND_IMAGE},
+    {"left/rect_mono", KIND_IMAGE},   {"right/rect_mono", KIND_IMAGE},   {"left/rect_color", KIND_IMAGE},  {"right/rect_color", KIND_IMAGE},
+    {"disparity", KIND_DISPARITY},    {"disparity_vis", KIND_IMAGE},     {"pointcloud", KIND_CLOUD}};
+
 CameraInfo toCameraInfo(const sensor_msgs::CameraInfo &m)
 {
     CameraInfo c;
@@ -85,39 +97,26 @@ StereoProcessor::StereoProcessor(ros::NodeHandle &nh_in, ros::NodeHandle &privat
     ReconfigureServer::CallbackType f = boost::bind(&StereoProcessor::configCb, this, _1, _2);
     reconfigure_server_->setCallback(f);
 
-    // Publishers; subscriptions to the cameras happen on demand in connectCb.  The lock keeps connectCb out until
-    // every publisher is assigned.
+    // Publishers; subscriptions to the cameras happen on demand in connectCb.  The lock keeps connectCb out until every
+    // publisher is assigned.
     ros::SubscriberStatusCallback connect_cb = boost::bind(&StereoProcessor::connectCb, this);
     boost::lock_guard<boost::mutex> lock(connect_mutex_);
-    int pq = 1;
-    private_nh.param("publisher_queue_size", pq, 1);
-    pub_mono_left_ = private_nh.advertise<sensor_msgs::Image>("left/image_mono", pq, connect_cb, connect_cb);
-    pub_mono_right_ = private_nh.advertise<sensor_msgs::Image>("right/image_mono", pq, connect_cb, connect_cb);
-    pub_color_left_ = private_nh.advertise<sensor_msgs::Image>("left/image_color", pq, connect_cb, connect_cb);
-    pub_color_right_ = private_nh.advertise<sensor_msgs::Image>("right/image_color", pq, connect_cb, connect_cb);
-    pub_mono_rect_left_ = private_nh.advertise<sensor_msgs::Image>("left/rect_mono", pq, connect_cb, connect_cb);
-    pub_color_rect_left_ = private_nh.advertise<sensor_msgs::Image>("left/rect_color", pq, connect_cb, connect_cb);
-    pub_mono_rect_right_ = private_nh.advertise<sensor_msgs::Image>("right/rect_mono", pq, connect_cb, connect_cb);
-    pub_color_rect_right_ = private_nh.advertise<sensor_msgs::Image>("right/rect_color", pq, connect_cb, connect_cb);
-    pub_disparity_ = private_nh.advertise<stereo_msgs::DisparityImage>("disparity", pq, connect_cb, connect_cb);
-    pub_disparity_vis_ = private_nh.advertise<sensor_msgs::Image>("disparity_vis", pq, connect_cb, connect_cb);
-    pub_pointcloud_ = private_nh.advertise<sensor_msgs::PointCloud2>("pointcloud", pq, connect_cb, connect_cb);
+    int depth = 1;
+    private_nh.param("publisher_queue_size", depth, 1);
+    for (int i = 0; i < N_TOPICS; ++i) {
+        switch (kTopics[i].kind) {
+        case KIND_DISPARITY: publishers_[i] = private_nh.advertise<stereo_msgs::DisparityImage>(kTopics[i].name, depth, connect_cb, connect_cb); break;
+        case KIND_CLOUD: publishers_[i] = private_nh.advertise<sensor_msgs::PointCloud2>(kTopics[i].name, depth, connect_cb, connect_cb); break;
+        default: publishers_[i] = private_nh.advertise<sensor_msgs::Image>(kTopics[i].name, depth, connect_cb, connect_cb); break;
+        }
+    }
 }
 
 void StereoProcessor::connectCb()
 {
     boost::lock_guard<boost::mutex> lock(connect_mutex_);
-    connected_.set(ConnectedTopics::MONO_LEFT, pub_mono_left_.getNumSubscribers() > 0);
-    connected_.set(ConnectedTopics::MONO_RIGHT, pub_mono_right_.getNumSubscribers() > 0);
-    connected_.set(ConnectedTopics::COLOR_LEFT, pub_color_left_.getNumSubscribers() > 0);
-    connected_.set(ConnectedTopics::COLOR_RIGHT, pub_color_right_.getNumSubscribers() > 0);
-    connected_.set(ConnectedTopics::RECT_MONO_LEFT, pub_mono_rect_left_.getNumSubscribers() > 0);
-    connected_.set(ConnectedTopics::RECT_MONO_RIGHT, pub_mono_rect_right_.getNumSubscribers() > 0);
-    connected_.set(ConnectedTopics::RECT_COLOR_LEFT, pub_color_rect_left_.getNumSubscribers() > 0);
-    connected_.set(ConnectedTopics::RECT_COLOR_RIGHT, pub_color_rect_right_.getNumSubscribers() > 0);
-    connected_.set(ConnectedTopics::DISPARITY, pub_disparity_.getNumSubscribers() > 0);
-    connected_.set(ConnectedTopics::DISPARITY_VIS, pub_disparity_vis_.getNumSubscribers() > 0);
-    connected_.set(ConnectedTopics::POINTCLOUD, pub_pointcloud_.getNumSubscribers() > 0);
+    for (int i = 0; i < N_TOPICS; ++i)
+        connected_.set(static_cast<ConnectedTopics::Topic>(1u << i), publishers_[i].getNumSubscribers() > 0);
     if (!connected_.any()) {
         ROS_INFO("Un-subscribing from images and camera infos");
         sub_l_raw_image_.unsubscribe();
@@ -246,23 +245,23 @@ void StereoProcessor::imageCb(const sensor_msgs::ImageConstPtr &l_raw_msg, const
         const double t_upload = msSince(t0);
 
         if (want.needsMonoLeft()) stereoProcessor_->convertRawToMono(GPU_MAT_SIDE_L);
-        if (want.has(ConnectedTopics::MONO_LEFT)) sendImage(GPU_MAT_SRC_L_MONO, l_raw_msg, sensor_msgs::image_encodings::MONO8, &pub_mono_left_);
+        if (want.has(ConnectedTopics::MONO_LEFT)) sendImage(GPU_MAT_SRC_L_MONO, l_raw_msg, sensor_msgs::image_encodings::MONO8, pub(ConnectedTopics::MONO_LEFT));
         if (want.needsMonoRight()) stereoProcessor_->convertRawToMono(GPU_MAT_SIDE_R);
-        if (want.has(ConnectedTopics::MONO_RIGHT)) sendImage(GPU_MAT_SRC_R_MONO, r_raw_msg, sensor_msgs::image_encodings::MONO8, &pub_mono_right_);
+        if (want.has(ConnectedTopics::MONO_RIGHT)) sendImage(GPU_MAT_SRC_R_MONO, r_raw_msg, sensor_msgs::image_encodings::MONO8, pub(ConnectedTopics::MONO_RIGHT));
         if (want.needsColorLeft()) stereoProcessor_->convertRawToColor(GPU_MAT_SIDE_L);
-        if (want.has(ConnectedTopics::COLOR_LEFT)) sendImage(GPU_MAT_SRC_L_COLOR, l_raw_msg, sensor_msgs::image_encodings::BGR8, &pub_color_left_);
+        if (want.has(ConnectedTopics::COLOR_LEFT)) sendImage(GPU_MAT_SRC_L_COLOR, l_raw_msg, sensor_msgs::image_encodings::BGR8, pub(ConnectedTopics::COLOR_LEFT));
         if (want.needsColorRight()) stereoProcessor_->convertRawToColor(GPU_MAT_SIDE_R);
-        if (want.has(ConnectedTopics::COLOR_RIGHT)) sendImage(GPU_MAT_SRC_R_COLOR, r_raw_msg, sensor_msgs::image_encodings::BGR8, &pub_color_right_);
+        if (want.has(ConnectedTopics::COLOR_RIGHT)) sendImage(GPU_MAT_SRC_R_COLOR, r_raw_msg, sensor_msgs::image_encodings::BGR8, pub(ConnectedTopics::COLOR_RIGHT));
         const double t_convert = msSince(t0);
 
         if (want.needsRectMonoLeft()) stereoProcessor_->rectifyImage(GPU_MAT_SRC_L_MONO, GPU_MAT_SRC_L_RECT_MONO, B200S_INTER_LINEAR);
         if (want.needsRectMonoRight()) stereoProcessor_->rectifyImage(GPU_MAT_SRC_R_MONO, GPU_MAT_SRC_R_RECT_MONO, B200S_INTER_LINEAR);
-        if (want.has(ConnectedTopics::RECT_MONO_LEFT)) sendImage(GPU_MAT_SRC_L_RECT_MONO, l_raw_msg, sensor_msgs::image_encodings::MONO8, &pub_mono_rect_left_);
-        if (want.has(ConnectedTopics::RECT_MONO_RIGHT)) sendImage(GPU_MAT_SRC_R_RECT_MONO, r_raw_msg, sensor_msgs::image_encodings::MONO8, &pub_mono_rect_right_);
+        if (want.has(ConnectedTopics::RECT_MONO_LEFT)) sendImage(GPU_MAT_SRC_L_RECT_MONO, l_raw_msg, sensor_msgs::image_encodings::MONO8, pub(ConnectedTopics::RECT_MONO_LEFT));
+        if (want.has(ConnectedTopics::RECT_MONO_RIGHT)) sendImage(GPU_MAT_SRC_R_RECT_MONO, r_raw_msg, sensor_msgs::image_encodings::MONO8, pub(ConnectedTopics::RECT_MONO_RIGHT));
         if (want.needsRectColorLeft()) stereoProcessor_->rectifyImage(GPU_MAT_SRC_L_COLOR, GPU_MAT_SRC_L_RECT_COLOR, B200S_INTER_LINEAR);
         if (want.needsRectColorRight()) stereoProcessor_->rectifyImage(GPU_MAT_SRC_R_COLOR, GPU_MAT_SRC_R_RECT_COLOR, B200S_INTER_LINEAR);
-        if (want.has(ConnectedTopics::RECT_COLOR_LEFT)) sendImage(GPU_MAT_SRC_L_RECT_COLOR, l_raw_msg, sensor_msgs::image_encodings::BGR8, &pub_color_rect_left_);
-        if (want.has(ConnectedTopics::RECT_COLOR_RIGHT)) sendImage(GPU_MAT_SRC_R_RECT_COLOR, r_raw_msg, sensor_msgs::image_encodings::BGR8, &pub_color_rect_right_);
+        if (want.has(ConnectedTopics::RECT_COLOR_LEFT)) sendImage(GPU_MAT_SRC_L_RECT_COLOR, l_raw_msg, sensor_msgs::image_encodings::BGR8, pub(ConnectedTopics::RECT_COLOR_LEFT));
+        if (want.has(ConnectedTopics::RECT_COLOR_RIGHT)) sendImage(GPU_MAT_SRC_R_RECT_COLOR, r_raw_msg, sensor_msgs::image_encodings::BGR8, pub(ConnectedTopics::RECT_COLOR_RIGHT));
         const double t_rectify = msSince(t0);
 
         if (want.needsDisparity()) {
@@ -271,18 +270,18 @@ void StereoProcessor::imageCb(const sensor_msgs::ImageConstPtr &l_raw_msg, const
             stereoProcessor_->computeDisparity(GPU_MAT_SRC_L_RECT_MONO, GPU_MAT_SRC_R_RECT_MONO, GPU_MAT_SRC_L_DISPARITY);
             stereoProcessor_->filterSpeckles(GPU_MAT_SRC_L_DISPARITY);
         }
-        if (want.has(ConnectedTopics::DISPARITY)) sendDisparity(GPU_MAT_SRC_L_DISPARITY, l_raw_msg, &pub_disparity_);
+        if (want.has(ConnectedTopics::DISPARITY)) sendDisparity(GPU_MAT_SRC_L_DISPARITY, l_raw_msg, pub(ConnectedTopics::DISPARITY));
         const double t_disparity = msSince(t0);
 
         if (want.has(ConnectedTopics::DISPARITY_VIS)) {
             stereoProcessor_->computeDisparityImage(GPU_MAT_SRC_L_DISPARITY, GPU_MAT_SRC_L_DISPARITY_IMG);
-            sendImage(GPU_MAT_SRC_L_DISPARITY_IMG, l_raw_msg, sensor_msgs::image_encodings::BGRA8, &pub_disparity_vis_);
+            sendImage(GPU_MAT_SRC_L_DISPARITY_IMG, l_raw_msg, sensor_msgs::image_encodings::BGRA8, pub(ConnectedTopics::DISPARITY_VIS));
         }
         const double t_vis = msSince(t0);
 
         if (want.has(ConnectedTopics::POINTCLOUD)) {
             stereoProcessor_->projectDisparityTo3DPoints(GPU_MAT_SRC_L_DISPARITY, GPU_MAT_SRC_L_POINTS2);
-            sendPoints(GPU_MAT_SRC_L_POINTS2, GPU_MAT_SRC_L_RECT_COLOR, l_raw_msg, &pub_pointcloud_);
+            sendPoints(GPU_MAT_SRC_L_POINTS2, GPU_MAT_SRC_L_RECT_COLOR, l_raw_msg, pub(ConnectedTopics::POINTCLOUD));
         }
         stereoProcessor_->waitForAllStreams();      // every sender has published from its stream callback by now
         stereoProcessor_->cleanSenders();
