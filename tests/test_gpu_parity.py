@@ -893,6 +893,26 @@ def test_disparity_vh_kernel_instantiations(proc, case):
     assert np.array_equal(got, want), _describe(got, want)
 
 
+# disp12MaxDiff >= 0: the matcher's edge tiles also produce the r columns either side of the clamp-free rectangle
+# (windows against the clamped image border); every window radius, minDisparity > 0 moves the right image's clamp
+EDGE_CASES = [(b, nd, 31, 0, 1) for b, nd in ((5, 64), (7, 128), (9, 256), (11, 16), (13, 48), (15, 128), (17, 64), (19, 96), (21, 64), (21, 256))] + [
+    (21, 64, 31, 7, 0), (21, 128, 31, 25, 2), (9, 64, 20, 3, 1), (15, 48, 63, 0, 1), (11, 256, 40, 5, 0), (5, 32, 63, 12, 3)]
+
+
+@pytest.mark.parametrize("case", EDGE_CASES)
+@pytest.mark.parametrize("width_extra", [420, 37])
+def test_disparity_lr_check_border_strips(proc, case, width_extra):
+    b, nd, cap, mind, d12 = case
+    p = O.BMParams(numDisparities=nd, blockSize=b, preFilterCap=cap, minDisparity=mind, disp12MaxDiff=d12, textureThreshold=3,
+                   uniquenessRatio=5)
+    W, H = nd + mind + width_extra, 90 + 2 * b      # width_extra 37: first and last tile are the same tile
+    L, R = synth.synth_pair(W, H, max(nd, 16), seed=b * 77 + nd + mind)
+    _set(proc, p)
+    got = proc.computeDisparityBare(L, R)
+    want = O.stereobm_compute(L, R, p)
+    assert np.array_equal(got, want), _describe(got, want)
+
+
 @pytest.mark.parametrize("cap", [31, 63])
 def test_disparity_tall_band_bias_limit(proc, cap):
     """bm_vh keeps 128 per accumulated row on the odd columns' sums (narrow form): a tall, narrow image forces long bands;
