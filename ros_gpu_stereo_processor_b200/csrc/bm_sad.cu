@@ -22,7 +22,7 @@ int launch_bm_ws(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
                  int XA, int XB, int YA, int YB, int16_t* disp, int16_t* cost, cudaStream_t st);
 int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg, int r, int lofs,
                  int XA, int XB, int YA, int YB, int16_t* disp, int16_t* cost, cudaStream_t st, int nf, size_t pre_stride,
-                 size_t disp_stride, bool edges);
+                 size_t disp_stride);
 int launch_bm_strips(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg, int r, int lofs,
                      int xa0, int xa1, int ya, int yb, int16_t* disp, int16_t* cost, cudaStream_t st, int nf, size_t pre_stride,
                      size_t disp_stride);
@@ -786,21 +786,15 @@ static int block_match_impl(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, 
     GenPlanes gp{Lp, Rp, pitch};
     static const int kernel_sel = getenv("B200S_KERNEL") ? atoi(getenv("B200S_KERNEL")) : 7;
     bool ws_done = false;
-    // the two r-wide border strips of the L/R-check path (columns whose windows run against the clamped image border)
-    const bool strips = need_bands && XA - outX0 == g.r && outX1 - XB == g.r && g.rofs == 0;
     if (fast_ok_base && kernel_sel >= 7) {
-        // ... which the warp-specialised matcher takes along in its edge tiles (B200S_VH_EDGES=0: separate strip kernel)
-        static const int vh_edges = getenv("B200S_VH_EDGES") ? atoi(getenv("B200S_VH_EDGES")) : 1;
-        const bool edges = strips && vh_edges;
-        int rc = launch_bm_vh(Lp, Rp, pitch, W, H, cfg, g.r, g.lofs, edges ? outX0 : XA, edges ? outX1 : XB, g.roiY0, g.roiY1, disp,
-                              cost, st, nf, pre_stride, disp_stride, edges);
+        int rc = launch_bm_vh(Lp, Rp, pitch, W, H, cfg, g.r, g.lofs, XA, XB, g.roiY0, g.roiY1, disp, cost, st, nf, pre_stride,
+                              disp_stride);
         if (rc < 0) return -1;
         ws_done = rc == 1;
-        if (ws_done && edges) return launches + 1;
     }
-    // otherwise one fused launch for both strips (bm_strip.cu) when it applies
+    // the two r-wide border strips of the L/R-check path: one fused launch (bm_strip.cu) when it applies
     bool strips_done = false;
-    if (ws_done && strips) {
+    if (ws_done && XA - outX0 == g.r && outX1 - XB == g.r && g.rofs == 0) {
         static const int use_strips = getenv("B200S_STRIPS") ? atoi(getenv("B200S_STRIPS")) : 1;
         if (use_strips) {
             int rc = launch_bm_strips(Lp, Rp, pitch, W, H, cfg, g.r, g.lofs, outX0 - g.lofs, XB - g.lofs, g.roiY0, g.roiY1, disp, cost, st,

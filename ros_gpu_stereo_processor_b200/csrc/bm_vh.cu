@@ -52,8 +52,6 @@ struct VhParams {
     int oMbar;                       // 8 mbarriers
     int oX;                          // halo exchange of the VH threads (HX): uint4 [2 buffers][2 sides][chunks][VH threads]
     size_t pre_stride, disp_stride;  // bytes between the frames of a batch (blockIdx.z = frame)
-    int edges;                       // [XA, XB) includes the r-wide border strips of the L/R-check path (see the VH role)
-    int rclo, rchi;                  // window columns (in X) the right image is clamped to in that case
 };
 
 namespace vh {
@@ -190,15 +188,6 @@ __global__ void __launch_bounds__(B200S_VH_MAXT, 1) bm_vh_kernel(const VhParams 
         uint32_t Se[NC], So[NC];
 #pragma unroll
         for (int i = 0; i < NC; ++i) Se[i] = So[i] = 0;
-        // Border strips (disp12MaxDiff >= 0: cv::StereoBM also matches the r columns either side of the clamp-free rectangle,
-        // SURVEY.md A.2.3).  There a window column X' takes its left byte from column clamp(X', 0, W - 1) -- the stager
-        // clamps its load addresses -- and its right bytes from the window column clamp(X', lofs, W - 1 + minD): the few
-        // threads whose window crosses one of the two limits build their E words through a slower, clamping form.
-        bool edge;
-        {
-            const int elo = P.rclo - (X0 - R) - 16 * cb, ehi = P.rchi - (X0 - R) - 16 * cb;  // limits as window-column indices
-            edge = !HX && P.edges && (elo > 0 || ehi < NE - 1);
-        }
 
         for (int j = 0; j < nIn; ++j) {
             const int sb = j & 1;
@@ -206,22 +195,6 @@ __global__ void __launch_bounds__(B200S_VH_MAXT, 1) bm_vh_kernel(const VhParams 
             uint32_t E[NE];
             {
                 const uint8_t* st = smem + P.oStage[sb];
-                if (edge) {
-                    // register-light form for the few edge threads: every right word straight from the unshifted copies
-                    // (copy 0: entering row, copy 4: leaving row) at the clamped window column
-                    const uint8_t* rc0 = st + 2 * P.ncolsP * 4 + 16 * cb + 4 * g4;
-                    const int el = P.rclo - (X0 - R) - 16 * cb, eh = P.rchi - (X0 - R) - 16 * cb;
-#pragma unroll
-                    for (int e = 0; e < NE; ++e) {
-                        const int of = min(max(e, el), eh);
-                        const uint32_t* pw = (const uint32_t*)(rc0 + (of & ~3));
-                        const uint32_t rn = __funnelshift_r(pw[0], pw[1], 8 * (of & 3));
-                        const uint32_t ro = __funnelshift_r(pw[P.CSB], pw[P.CSB + 1], 8 * (of & 3));
-                        const uint32_t ln = *(const uint32_t*)(st + loffs + 4 * e);
-                        const uint32_t lo = *(const uint32_t*)(st + 4 * P.ncolsP + loffs + 4 * e);
-                        E[e] = __vabsdiffu4(ln, rn) - __vabsdiffu4(lo, ro);
-                    }
-                } else {
                 uint32_t wn[4 * NRQ], wo[4 * NRQ];
 #pragma unroll
                 for (int q = 0; q < NRQ; ++q) {
@@ -236,7 +209,6 @@ __global__ void __launch_bounds__(B200S_VH_MAXT, 1) bm_vh_kernel(const VhParams 
                     vh_e_words<R, R + NC>(st, loffs, P.ncolsP, wn, wo, E);                 // the thread's own 16 columns
                     if (cb == 0) vh_e_words<0, R>(st, loffs, P.ncolsP, wn, wo, E);         // outer halos of the tile
                     if (cb == P.NCB - 1) vh_e_words<R + NC, NE>(st, loffs, P.ncolsP, wn, wo, E);
-                }
                 }
             }
             mbar_arrive(mb + 8 * (MB_EMPTY_STAGE + sb));   // the staged rows are in registers now
@@ -459,12 +431,10 @@ __global__ void __launch_bounds__(B200S_VH_MAXT, 1) bm_vh_kernel(const VhParams 
         const int Xr0 = X0 - r - P.lofs;     // multiple of 4 by construction
         if (s == 0) {
             int an[MAXL], ao[MAXL], trun[MAXL];      // trun: running texture column sums of the lane's columns
-            int lc[MAXL];                            // the lane's columns, clamped to the image (border strips, tile overhang)
 #pragma unroll
             for (int m = 0; m < MAXL; ++m) {
                 const int c = lane + 32 * m;
-                lc[m] = min(max(Xl0 + c, 0), P.W - 1) - Xl0;
-                an[m] = c < P.ncolsP ? (int)__ldg(gLp + (size_t)y_in0 * P.pitch + Xl0 + lc[m]) : 0;
+                an[m] = c < P.ncolsP ? (int)__ldg(gLp + (size_t)y_in0 * P.pitch + Xl0 + c) : 0;
                 ao[m] = 0;
                 trun[m] = 0;
             }
@@ -482,8 +452,8 @@ __global__ void __launch_bounds__(B200S_VH_MAXT, 1) bm_vh_kernel(const VhParams 
                     for (int m = 0; m < MAXL; ++m) {
                         const int c = lane + 32 * m;
                         if (c < P.ncolsP) {
-                            an[m] = (int)__ldg(ln + lc[m]);
-                            ao[m] = has_old ? (int)__ldg(lo + lc[m]) : 0;
+                            an[m] = (int)__ldg(ln + c);
+                            ao[m] = has_old ? (int)__ldg(lo + c) : 0;
                         }
                     }
                 }
@@ -651,7 +621,7 @@ static cudaError_t launch_vh(const VhParams& P, dim3 grid, int nt, size_t smem, 
 // returns 1 when launched, 0 when this configuration is not handled (caller falls back), < 0 on CUDA errors
 int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int H, const BMConfig& cfg, int r, int lofs,
                  int XA, int XB, int YA, int YB, int16_t* disp, int16_t* cost, cudaStream_t st, int nf, size_t pre_stride,
-                 size_t disp_stride, bool edges)
+                 size_t disp_stride)
 {
     using vh::NC;
     const int nd = cfg.nd;
@@ -739,7 +709,6 @@ int launch_bm_vh(const uint8_t* Lp, const uint8_t* Rp, size_t pitch, int W, int 
     P.texThr = cfg.textureThreshold; P.uniq = cfg.uniquenessRatio; P.lofs = lofs;
     P.X0base = X0base; P.XA = XA; P.XB = XB; P.YA = YA; P.YB = YB;
     P.pre_stride = pre_stride; P.disp_stride = disp_stride;
-    P.edges = edges ? 1 : 0; P.rclo = lofs; P.rchi = W - 1 + cfg.minD;
     const int tilesX = (need + P.TW - 1) / P.TW;
     P.BH = (rows + best_bands - 1) / best_bands;
     dim3 grid(tilesX, (rows + P.BH - 1) / P.BH, nf);
