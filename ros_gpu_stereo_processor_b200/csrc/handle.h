@@ -70,7 +70,7 @@ struct Work {
     cudaStream_t st = nullptr;
     bool own_stream = false;
     int depth = 1;
-    DevBuf rawL, rawR, rawC, rectL, rectR, rectC, preL, preR, disp, cost, df, xyz, pc2, vol, ccl, normtmp, misc;
+    DevBuf rawL, rawR, rawC, rectL, rectR, rectC, preL, preR, disp, cost, df, xyz, pc2, vol, ccl, normtmp, misc, lut;
     cudaEvent_t ev_bm0 = nullptr, ev_bm1 = nullptr, ev_done = nullptr;
     cudaEvent_t ev_stage[ST_COUNT + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double last_evals = 0;
@@ -82,6 +82,8 @@ struct Work {
     uint64_t use_counter = 0;
     std::string tab_cache;        // last input-address table written to the device (slots.cu)
     std::string border_key;       // geometry + FILTERED value the border of the slot's disparity planes was last filled for
+    std::string lut_key;          // Q, cx difference and disparity range the pack kernel's per-disparity table was built for
+    int lut_n = 0;                // entries of that table (0: none, the pack kernel computes per pixel)
     const void* in_tab[3 * MAX_BATCH] = {nullptr};   // host copy of that table: L[32], R[32], colour[32]
     void drop_graphs()
     {
@@ -93,7 +95,9 @@ struct Work {
     void release()
     {
         drop_graphs();
-        DevBuf* all[] = {&rawL, &rawR, &rawC, &rectL, &rectR, &rectC, &preL, &preR, &disp, &cost, &df, &xyz, &pc2, &vol, &ccl, &normtmp, &misc};
+        DevBuf* all[] = {&rawL, &rawR, &rawC, &rectL, &rectR, &rectC, &preL, &preR, &disp, &cost, &df, &xyz, &pc2, &vol, &ccl, &normtmp, &misc, &lut};
+        lut_key.clear();
+        lut_n = 0;
         for (DevBuf* b : all) b->release();
         if (ev_bm0) cudaEventDestroy(ev_bm0);
         if (ev_bm1) cudaEventDestroy(ev_bm1);

@@ -125,7 +125,15 @@ struct ReprojectExtras {
     size_t df_stride = 0;
     const PtrList* df_list = nullptr;
     const uint8_t* const* color_tab = nullptr;      // per-frame colour planes (see `tab*` above)
+    // table over the disparity values the chain can produce (launch_reproject_lut): entry dv - dmin_const
+    const void* lut = nullptr;
+    int lut_n = 0;
 };
+// Everything of a PointCloud2 record that depends on the disparity alone -- the reciprocal of W, float(Z / W) with the
+// missing-value and isValidPoint rules applied, the float disparity -- for dv = dmin .. dmin + n - 1 (16 bytes each).
+// returns 1 when built (image_geometry's Q sparsity), 0 when this Q has no table (the kernel computes per pixel)
+int launch_reproject_lut(void* lut, int n, int dmin, double cxd, const double* Q, unsigned qmask, cudaStream_t st);
+constexpr int REPROJECT_LUT_MAX = 1 << 16;          // entries a slot keeps room for (numDisparities up to 4094)
 int launch_reproject_pack(const int16_t* d16, int W, int H, double cxd, const double* Q, unsigned qmask, const int* min_d16,
                           const uint8_t* color, int ch, float* xyz, uint8_t* pc2, cudaStream_t st, int nf = 1,
                           size_t d_stride = 0, size_t color_stride = 0, size_t xyz_stride = 0, size_t pc2_stride = 0,

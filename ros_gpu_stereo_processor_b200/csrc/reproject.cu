@@ -91,6 +91,36 @@ __device__ __forceinline__ float div_to_float(double a, double w, double rw)
     return __double2float_rn(safe ? q : __ddiv_rn(a, w));
 }
 
+constexpr uint32_t LUT_INVALID_Z = 0x7f800001u;     // a signalling NaN: no float conversion produces it
+
+// w of the standard Q and the record terms that depend on the disparity only, exactly as the per-pixel path forms them
+template <int STDQ>
+__device__ __forceinline__ double stdq_w(double q32, double q33, double d)
+{
+    double w = __dadd_rn(0.0, __dmul_rn(q32, d));
+    if (STDQ == 1) w = __dadd_rn(w, q33);
+    return w;
+}
+
+template <int STDQ>
+__global__ void __launch_bounds__(256) reproject_lut_kernel(uint4* __restrict__ lut, int n, int dmin, double cxd,
+                                                            const double* __restrict__ Q)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int dv = dmin + i;
+    const float dfv = disp_to_float(dv, cxd);
+    const double d = (double)dfv, minDisp = (double)disp_to_float(dmin, cxd);
+    const double az = (double)__double2float_rn(__dadd_rn(0.0, __ldg(Q + 11)));
+    const double w = stdq_w<STDQ>(__ldg(Q + 14), __ldg(Q + 15), d);
+    const double rw = __drcp_rn(w);
+    float z = div_to_float(az, w, rw);
+    if (fabs(__dadd_rn(d, -minDisp)) <= (double)1.1920928955078125e-07f) z = 10000.0f;
+    const bool valid = (z != 10000.0f) && !isinf(z);
+    lut[i] = make_uint4((uint32_t)__double2loint(rw), (uint32_t)__double2hiint(rw), valid ? __float_as_uint(z) : LUT_INVALID_Z,
+                        __float_as_uint(dfv));
+}
+
 // cv::reprojectImageTo3D(handleMissingValues = true) + PointCloud2 records (+ the float disparity plane) in one pass.
 // STDQ (1: with Q33, 2: Q33 == 0, 0: any Q): Q has the sparsity of image_geometry's stereo model (the only Q the reference
 // can produce); the terms that depend on the column only are then computed once per thread and reused for the RP_RPW rows
@@ -102,7 +132,9 @@ __device__ __forceinline__ float div_to_float(double a, double w, double rw)
 // quotient within 2 ulp (FP64) of a / w; rounding THAT to float gives the same float as rounding the exact quotient unless
 // it lies within a few FP64 ulps of a float rounding boundary (29 dropped bits = 0x10000000).  Those rare lanes, and
 // non-finite or tiny quotients, take the exact division: the result is bit-identical always.
-template <int STDQ>
+// LUT (STDQ only, records without the xyz plane): the per-disparity terms come from the table of reproject_lut_kernel --
+// the same operations, done once per value instead of once per pixel; disparities outside the table take the arithmetic.
+template <int STDQ, bool LUT>
 #if B200S_PACK_PREFETCH
 #define B200S_PACK_BOUNDS __launch_bounds__(32 * RP_ROWS, 1536 / (32 * RP_ROWS))    /* 40 registers: six blocks per SM */
 #else
@@ -114,7 +146,8 @@ __global__ void B200S_PACK_BOUNDS reproject_pack_kernel(const int16_t* __restric
                                                              float* __restrict__ xyz, uint8_t* __restrict__ pc2, unsigned qmask,
                                                              size_t d_stride, size_t color_stride, size_t xyz_stride, const FrameDst fd,
                                                              int dmin_const, float* __restrict__ df, const FrameDst fdf,
-                                                             const uint8_t* const* __restrict__ color_tab)
+                                                             const uint8_t* const* __restrict__ color_tab,
+                                                             const uint4* __restrict__ lut, int lut_n)
 {
     const int lane = threadIdx.x & 31;
     const int x0 = blockIdx.x * 32, x = x0 + lane;
@@ -172,6 +205,32 @@ __global__ void B200S_PACK_BOUNDS reproject_pack_kernel(const int16_t* __restric
         uint32_t ux = 0x7fc00000u, uy = 0x7fc00000u, uz = 0x7fc00000u;
         const size_t i = xin ? (size_t)y * W + x : 0;
         const int dv = B200S_PACK_PREFETCH ? dvs[rr] : (xin ? (int)d16[i] : 0);
+        const unsigned li = (unsigned)(dv - dmin);
+        if (LUT && li < (unsigned)lut_n) {
+            const uint4 e = xin ? __ldg(lut + li) : make_uint4(0u, 0u, LUT_INVALID_Z, 0u);
+            if (df && xin) df[i] = __uint_as_float(e.w);
+            if (xin && e.z != LUT_INVALID_Z) {
+                const double rw = __hiloint2double((int)e.y, (int)e.x);
+                const double ay = (double)__double2float_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(q11, (double)y)), q13));
+                double w = 0.0;
+                float p0, p1;
+                {
+                    const double q = __dmul_rn(ax, rw);
+                    const unsigned lo = (unsigned)__double2loint(q) & 0x1FFFFFFFu, hi = (unsigned)__double2hiint(q) & 0x7FFFFFFFu;
+                    const bool safe = hi > 0x39B00000u && hi < 0x46300000u && (lo - 0x0FFFFFF0u) > 0x20u;
+                    if (!safe) w = stdq_w<STDQ>(q32, q33, (double)__uint_as_float(e.w));
+                    p0 = __double2float_rn(safe ? q : __ddiv_rn(ax, w));
+                }
+                {
+                    const double q = __dmul_rn(ay, rw);
+                    const unsigned lo = (unsigned)__double2loint(q) & 0x1FFFFFFFu, hi = (unsigned)__double2hiint(q) & 0x7FFFFFFFu;
+                    const bool safe = hi > 0x39B00000u && hi < 0x46300000u && (lo - 0x0FFFFFF0u) > 0x20u;
+                    if (!safe) w = stdq_w<STDQ>(q32, q33, (double)__uint_as_float(e.w));
+                    p1 = __double2float_rn(safe ? q : __ddiv_rn(ay, w));
+                }
+                ux = __float_as_uint(p0); uy = __float_as_uint(p1); uz = e.z;
+            }
+        } else {
         if (df && xin) df[i] = disp_to_float(dv, cxd);       // the DisparityImage payload from the same pass (convertTo)
         // missing value (d == min over the image): cv::reprojectImageTo3D sets Z = 10000, which isValidPoint rejects, so
         // the record is NaN xyz + colour whatever X and Y were; no arithmetic needed unless the xyz plane is wanted too
@@ -182,8 +241,7 @@ __global__ void B200S_PACK_BOUNDS reproject_pack_kernel(const int16_t* __restric
                 a[0] = ax;
                 a[1] = (double)__double2float_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(q11, (double)y)), q13));
                 a[2] = az;
-                w = __dadd_rn(0.0, __dmul_rn(q32, d));
-                if (STDQ == 1) w = __dadd_rn(w, q33);
+                w = stdq_w<STDQ>(q32, q33, d);
             } else {
                 double h[4];
 #pragma unroll
@@ -211,6 +269,7 @@ __global__ void B200S_PACK_BOUNDS reproject_pack_kernel(const int16_t* __restric
             if ((p[2] != 10000.0f) && !isinf(p[2])) {
                 ux = __float_as_uint(p[0]); uy = __float_as_uint(p[1]); uz = __float_as_uint(p[2]);
             }
+        }
         }
         if (!pc2) continue;
         uint32_t bgr = bgrs[rr];
@@ -290,18 +349,27 @@ int launch_reproject_pack(const int16_t* d16, int W, int H, double cxd, const do
     if (pc2_list && !pc2) pc2 = (uint8_t*)pc2_list->p[0];     // the kernel tests pc2 for "records wanted"
     ReprojectExtras ex;
     if (extra) ex = *extra;
-    if (qmask == QMASK_STEREO)
-        reproject_pack_kernel<1><<<g, 32 * RP_ROWS, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask, d_stride, color_stride,
-                                                      xyz_stride, frame_dst(pc2_stride, pc2_list), ex.dmin_const, ex.df,
-                                                      frame_dst(ex.df_stride, ex.df_list), ex.color_tab);
-    else if (qmask == QMASK_STEREO0)
-        reproject_pack_kernel<2><<<g, 32 * RP_ROWS, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask, d_stride, color_stride,
-                                                      xyz_stride, frame_dst(pc2_stride, pc2_list), ex.dmin_const, ex.df,
-                                                      frame_dst(ex.df_stride, ex.df_list), ex.color_tab);
-    else
-        reproject_pack_kernel<0><<<g, 32 * RP_ROWS, 0, st>>>(d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask, d_stride, color_stride,
-                                                      xyz_stride, frame_dst(pc2_stride, pc2_list), ex.dmin_const, ex.df,
-                                                      frame_dst(ex.df_stride, ex.df_list), ex.color_tab);
+    const uint4* lut = (const uint4*)ex.lut;
+    const int stdq = qmask == QMASK_STEREO ? 1 : (qmask == QMASK_STEREO0 ? 2 : 0);
+    const bool use_lut = stdq && lut && ex.lut_n > 0 && !xyz && !min_d16;
+#define B200S_PACK_ARGS d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask, d_stride, color_stride, xyz_stride, \
+                        frame_dst(pc2_stride, pc2_list), ex.dmin_const, ex.df, frame_dst(ex.df_stride, ex.df_list), ex.color_tab, \
+                        use_lut ? lut : nullptr, use_lut ? ex.lut_n : 0
+    if (stdq == 1 && use_lut) reproject_pack_kernel<1, true><<<g, 32 * RP_ROWS, 0, st>>>(B200S_PACK_ARGS);
+    else if (stdq == 2 && use_lut) reproject_pack_kernel<2, true><<<g, 32 * RP_ROWS, 0, st>>>(B200S_PACK_ARGS);
+    else if (stdq == 1) reproject_pack_kernel<1, false><<<g, 32 * RP_ROWS, 0, st>>>(B200S_PACK_ARGS);
+    else if (stdq == 2) reproject_pack_kernel<2, false><<<g, 32 * RP_ROWS, 0, st>>>(B200S_PACK_ARGS);
+    else reproject_pack_kernel<0, false><<<g, 32 * RP_ROWS, 0, st>>>(B200S_PACK_ARGS);
+#undef B200S_PACK_ARGS
+    return 1;
+}
+
+int launch_reproject_lut(void* lut, int n, int dmin, double cxd, const double* Q, unsigned qmask, cudaStream_t st)
+{
+    if (n <= 0 || !lut) return 0;
+    if (qmask == QMASK_STEREO) reproject_lut_kernel<1><<<(n + 255) / 256, 256, 0, st>>>((uint4*)lut, n, dmin, cxd, Q);
+    else if (qmask == QMASK_STEREO0) reproject_lut_kernel<2><<<(n + 255) / 256, 256, 0, st>>>((uint4*)lut, n, dmin, cxd, Q);
+    else return 0;
     return 1;
 }
 

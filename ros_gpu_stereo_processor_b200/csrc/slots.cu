@@ -132,6 +132,10 @@ int run_frame_chain(b200s_handle* h, Work& w, int nf, const b200s_frame_io* ios,
         if (want_xyz && w.xyz.ensure(lay.xyz * w.depth)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (points)");
         ReprojectExtras ex;
         ex.dmin_const = filtered;
+        if (w.lut_n > 0 && !want_xyz) {
+            ex.lut = w.lut.p;
+            ex.lut_n = w.lut_n;
+        }
         if (want_df) {
             ex.df = df_direct ? nullptr : (float*)w.df.p;
             ex.df_stride = lay.df;
@@ -164,6 +168,31 @@ int run_frame_chain(b200s_handle* h, Work& w, int nf, const b200s_frame_io* ios,
         if (want_pc && !pc_direct && (rc = copy_out(h, o.pointcloud2, (uint8_t*)w.pc2.p + f * lay.pc2, n * 32, od, st))) return rc;
         if (want_xyz && (rc = copy_out(h, o.points_xyz, (uint8_t*)w.xyz.p + f * lay.xyz, n * 12, od, st))) return rc;
     }
+    return B200S_OK;
+}
+
+// The pack kernel's per-disparity table (kernels.h launch_reproject_lut) of this slot: rebuilt on the slot's stream, outside
+// any graph, when the calibration or the disparity range changed.  The buffer keeps its address (graphs hold it).
+static int ensure_reproject_lut(b200s_handle* h, Work& w, cudaStream_t st)
+{
+    static const int use_lut = getenv("B200S_PACK_LUT") ? atoi(getenv("B200S_PACK_LUT")) : 1;
+    const int dmin = (h->prm.min_disparity - 1) * 16;
+    const int n = (h->prm.num_disparities + 1) * 16 + 1;       // FILTERED .. the largest value the sub-pixel fit can round to
+    if (!use_lut || !h->model_ok || n > REPROJECT_LUT_MAX) {
+        w.lut_n = 0;
+        w.lut_key.clear();
+        return B200S_OK;
+    }
+    std::string key((const char*)h->Q, sizeof h->Q);
+    key.append((const char*)&h->cxd, sizeof h->cxd);
+    key.append((const char*)&dmin, sizeof dmin);
+    key.append((const char*)&n, sizeof n);
+    if (key == w.lut_key) return B200S_OK;
+    if (w.lut.ensure((size_t)REPROJECT_LUT_MAX * 16)) return fail(h, B200S_ENOMEM, "cudaMalloc failed (reprojection table)");
+    const int built = launch_reproject_lut(w.lut.p, n, dmin, h->cxd, (const double*)h->Qdev.p, h->qmask, st);
+    h->launches += built;
+    w.lut_n = built ? n : 0;
+    w.lut_key = key;
     return B200S_OK;
 }
 
@@ -314,7 +343,8 @@ int b200s_process_batch_async(b200s_handle* h, int slot, int n_frames, const voi
         w.tab_cache.assign((const char*)tab, sizeof tab);
     }
     memcpy(w.in_tab, tab, sizeof tab);
-    int rc = B200S_OK;
+    int rc = ensure_reproject_lut(h, w, st);
+    if (rc) return rc;
     if (!graphs) {
         rc = run_frame_chain(h, w, nf, ios, with_color, st);
     } else {
