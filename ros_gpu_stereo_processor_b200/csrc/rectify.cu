@@ -6,6 +6,7 @@
 #include "kernels.h"
 
 #include <climits>
+#include <cstdlib>
 #include <cstdint>
 
 namespace b200s {
@@ -314,6 +315,204 @@ __global__ void __launch_bounds__(FT_THREADS) rectify_xsobel_kernel(RectSide sl,
     }
 }
 
+// ---- the same, four adjacent pixels per thread ("quad" form, the one launched for rectifying maps) --------------------
+// The tile-with-halo is 18 rows of 17 quads (columns x0 - 2 .. x0 + 65), one quad per thread: the row terms (mirroring,
+// validity, addresses) are formed once per four pixels, the four map entries arrive with one or two vector loads, and the
+// four rectified bytes leave with one 32-bit shared-memory store.  Source window, blend and Sobel as above; same bytes.
+constexpr int QT_QPR = (FTX + 4) / 4;                    // quads per tile row
+constexpr int QT_ROWS = FTY + 2;
+constexpr int QT_NQ = QT_QPR * QT_ROWS;
+constexpr int QT_THREADS = ((QT_NQ > 16 * FTY ? QT_NQ : 16 * FTY) + 31) / 32 * 32;
+constexpr int QT_PITCH = 4 * QT_QPR + 4;                 // tile row stride in bytes (the Sobel phase reads two whole words past a quad)
+
+template <int MODE>
+__global__ void __launch_bounds__(QT_THREADS) rectify_xsobel_quad_kernel(RectSide sl, RectSide sr, BatchStrides bs, int sW, int sH,
+                                                                         size_t ppitch, int W, int H, int cap)
+{
+    static_assert(MODE != MAP_NONE, "the identity map keeps the per-pixel kernel");
+    __shared__ __align__(16) uint8_t tile[QT_ROWS][QT_PITCH];
+    __shared__ __align__(16) uint8_t win[RECT_WIN_BYTES];
+    __shared__ int bbox[4];
+    const RectSide& S = (blockIdx.z & 1) ? sr : sl;
+    const int frame = blockIdx.z >> 1;
+    const uint8_t* __restrict__ src = frame_src(S, bs, blockIdx.z & 1, frame);
+    const int x0 = blockIdx.x * FTX, y0 = blockIdx.y * FTY;
+    const int q = threadIdx.x;
+    const bool qact = q < QT_NQ;
+    const int ty = q / QT_QPR, tq = q - ty * QT_QPR;
+    const int xq = x0 - 2 + 4 * tq, y = y0 + ty - 1;
+    // rows are mirrored for the Sobel taps: the halo row above row 0 is row 1, below row H-1 is row H-2
+    const int ys = y < 0 ? 1 : (y >= H ? H - 2 : y);
+    const bool rowok = qact && ys >= 0 && ys < H;
+    int mx[4], my[4];
+    unsigned okm = 0;                                     // bit k: pixel xq + k is inside the image
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        mx[k] = my[k] = 0;
+        if (rowok && xq + k >= 0 && xq + k < W) okm |= 1u << k;
+    }
+    if (okm == 0xFu && MODE == MAP_DELTA16 && !(W & 1)) {
+        // xq is even and so is ys * W: the four 4-byte entries are two aligned 8-byte loads
+        const uint2* mp = (const uint2*)((const uint32_t*)S.map + (size_t)ys * W + xq);
+        const uint2 e0 = __ldg(mp), e1 = __ldg(mp + 1);
+        const uint32_t v[4] = {e0.x, e0.y, e1.x, e1.y};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            mx[k] = 32 * (xq + k) + (int)(int16_t)(v[k] & 0xffffu);
+            my[k] = 32 * ys + ((int)v[k] >> 16);
+        }
+    } else if (okm == 0xFu && MODE == MAP_ABS32 && !(W & 1)) {
+        const int4* mp = (const int4*)((const int2*)S.map + (size_t)ys * W + xq);
+        const int4 e0 = __ldg(mp), e1 = __ldg(mp + 1);
+        mx[0] = e0.x; my[0] = e0.y; mx[1] = e0.z; my[1] = e0.w;
+        mx[2] = e1.x; my[2] = e1.y; mx[3] = e1.z; my[3] = e1.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((okm >> k) & 1u) {
+                const int2 m = map_at<MODE>(S.map, S.cm, xq + k, ys, W);
+                mx[k] = m.x; my[k] = m.y;
+            }
+    }
+    // source window of the tile (see rectify_xsobel_kernel); integer source coordinates, saturated like cv::remap's maps
+    int X0[4], Y0[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { X0[k] = sat16(mx[k] >> 5); Y0[k] = sat16(my[k] >> 5); }
+    int xmn = INT_MAX, xmx = INT_MIN, ymn = INT_MAX, ymx = INT_MIN;
+    if (okm == 0xFu) {
+        xmn = min(min(X0[0], X0[1]), min(X0[2], X0[3])); xmx = max(max(X0[0], X0[1]), max(X0[2], X0[3]));
+        ymn = min(min(Y0[0], Y0[1]), min(Y0[2], Y0[3])); ymx = max(max(Y0[0], Y0[1]), max(Y0[2], Y0[3]));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((okm >> k) & 1u) { xmn = min(xmn, X0[k]); xmx = max(xmx, X0[k]); ymn = min(ymn, Y0[k]); ymx = max(ymx, Y0[k]); }
+    }
+    xmn = __reduce_min_sync(0xffffffffu, xmn); xmx = __reduce_max_sync(0xffffffffu, xmx);
+    ymn = __reduce_min_sync(0xffffffffu, ymn); ymx = __reduce_max_sync(0xffffffffu, ymx);
+    if (threadIdx.x == 0) { bbox[0] = INT_MAX; bbox[1] = INT_MIN; bbox[2] = INT_MAX; bbox[3] = INT_MIN; }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&bbox[0], xmn); atomicMax(&bbox[1], xmx); atomicMin(&bbox[2], ymn); atomicMax(&bbox[3], ymx);
+    }
+    __syncthreads();
+    xmn = bbox[0]; xmx = bbox[1]; ymn = bbox[2]; ymx = bbox[3];
+    bool staged = false;
+    int wx0 = 0, wy0 = 0, wpitch = 0;
+    if (xmn <= xmx) {
+        wx0 = xmn & ~15;                                   // floor to a multiple of 16 (also for negative x)
+        wy0 = ymn;
+        wpitch = (xmx + 2 - wx0 + 15) & ~15;
+        const int wh = ymx + 2 - ymn;
+        staged = (long long)wpitch * wh <= RECT_WIN_BYTES;
+        if (staged) {
+            // 8 threads walk the 16-byte units of a window row, QT_THREADS / 8 rows at a time
+            const int upr = wpitch >> 4;
+            const bool vec = ((sW & 15) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+            for (int row = threadIdx.x >> 3; row < wh; row += QT_THREADS / 8) {
+                const int yy = wy0 + row;
+                for (int cx = threadIdx.x & 7; cx < upr; cx += 8) {
+                    const int x = wx0 + 16 * cx;
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if ((unsigned)yy < (unsigned)sH) {
+                        const uint8_t* p = src + (size_t)yy * sW + x;
+                        if (vec && x >= 0 && x + 16 <= sW) {
+                            v = __ldg((const uint4*)p);
+                        } else {
+                            uint32_t w4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if ((unsigned)(x + j) < (unsigned)sW) w4[j >> 2] |= (uint32_t)__ldg(p + j) << (8 * (j & 3));
+                            v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                        }
+                    }
+                    *(uint4*)(win + (size_t)row * wpitch + 16 * cx) = v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (qact) {
+        uint32_t out4 = 0;
+        // (32-a)(32-b) s00 + a(32-b) s01 + (32-a) b s10 + a b s11, factored (exact in integers)
+        auto blend = [](int mxk, int myk, int s00, int s01, int s10, int s11) {
+            const int a = mxk & 31, b = myk & 31;
+            const int top = 32 * s00 + a * (s01 - s00), bot = 32 * s10 + a * (s11 - s10);
+            const int acc = 32 * top + b * (bot - top);
+            return (uint32_t)((acc + 512) >> 10);
+        };
+        if (staged && okm == 0xFu) {
+            const uint8_t* wbase = win - wy0 * wpitch - wx0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint8_t* p = wbase + Y0[k] * wpitch + X0[k];
+                out4 |= blend(mx[k], my[k], p[0], p[1], p[wpitch], p[wpitch + 1]) << (8 * k);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!((okm >> k) & 1u)) continue;
+                int s00, s01, s10, s11;
+                if (staged) {
+                    const uint8_t* p = win + (Y0[k] - wy0) * wpitch + (X0[k] - wx0);
+                    s00 = p[0]; s01 = p[1]; s10 = p[wpitch]; s11 = p[wpitch + 1];
+                } else if ((unsigned)X0[k] < (unsigned)(sW - 1) && (unsigned)Y0[k] < (unsigned)(sH - 1)) {
+                    const uint8_t* p = src + (size_t)Y0[k] * sW + X0[k];
+                    s00 = __ldg(p); s01 = __ldg(p + 1); s10 = __ldg(p + sW); s11 = __ldg(p + sW + 1);
+                } else {
+                    s00 = fetch1(src, sW, sH, X0[k], Y0[k], 1, 0);
+                    s01 = fetch1(src, sW, sH, X0[k] + 1, Y0[k], 1, 0);
+                    s10 = fetch1(src, sW, sH, X0[k], Y0[k] + 1, 1, 0);
+                    s11 = fetch1(src, sW, sH, X0[k] + 1, Y0[k] + 1, 1, 0);
+                }
+                out4 |= blend(mx[k], my[k], s00, s01, s10, s11) << (8 * k);
+            }
+        }
+        *(uint32_t*)&tile[ty][4 * tq] = out4;
+    }
+    __syncthreads();
+    // Sobel: thread = 4 adjacent pixels x .. x + 3, tile columns 4 t + 2 .. 4 t + 5 (column 0 is x0 - 2)
+    if (threadIdx.x < 16 * FTY) {
+        const int sy = threadIdx.x >> 4, tx = (threadIdx.x & 15) * 4;
+        const int x = x0 + tx, yy = y0 + sy;
+        if (x < W && yy < H) {
+            const bool last_odd = (H & 1) && (yy == H - 1);
+            uint32_t de = 0, dO = 0, rect4 = 0;     // Sobel sums of pixels (0, 2) and (1, 3) as s16x2
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) {
+                const uint32_t w0 = *(const uint32_t*)&tile[sy + rr][tx], w1 = *(const uint32_t*)&tile[sy + rr][tx + 4];
+                const uint32_t lw = __funnelshift_r(w0, w1, 8);                       // bytes x-1 .. x+2
+                const uint32_t hi = __funnelshift_r(w0, w1, 24);                      // bytes x+1 .. x+4
+                const uint32_t le = lw & 0x00ff00ffu, lo = (lw >> 8) & 0x00ff00ffu;    // x-1, x+1 | x, x+2
+                const uint32_t he = hi & 0x00ff00ffu, ho = (hi >> 8) & 0x00ff00ffu;    // x+1, x+3 | x+2, x+4
+                uint32_t d_e = __vsub2(he, le), d_o = __vsub2(ho, lo);                 // pixels 0, 2 | pixels 1, 3
+                if (rr == 1) {
+                    d_e = __vadd2(d_e, d_e);
+                    d_o = __vadd2(d_o, d_o);
+                    rect4 = __funnelshift_r(w0, w1, 16);                               // bytes x .. x+3 of the centre row
+                }
+                de = __vadd2(de, d_e);
+                dO = __vadd2(dO, d_o);
+            }
+            const uint32_t capw = (uint32_t)cap * 0x00010001u, ncapw = (uint32_t)(-cap & 0xffff) * 0x00010001u;
+            de = __vadd2(__vmins2(__vmaxs2(de, ncapw), capw), capw);
+            dO = __vadd2(__vmins2(__vmaxs2(dO, ncapw), capw), capw);
+            uint32_t pre4 = __byte_perm(de, dO, 0x6240);                               // p0 p1 p2 p3
+            if (last_odd || H <= 1) pre4 = (uint32_t)cap * 0x01010101u;
+            else if (x == 0 || x + 3 >= W - 1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (x + i == 0 || x + i >= W - 1) pre4 = (pre4 & ~(0xffu << (8 * i))) | ((uint32_t)cap << (8 * i));
+            }
+            uint8_t* pp = S.pre + frame * bs.pre + (size_t)yy * ppitch + x;
+            if (x + 3 < W) *(uint32_t*)pp = pre4;                    // ppitch % 16 == 0 and x % 4 == 0
+            else for (int i = 0; i < 4 && x + i < W; ++i) pp[i] = (uint8_t)(pre4 >> (8 * i));
+            uint8_t* rp = S.rect + frame * bs.rect + (size_t)yy * W + x;
+            if (x + 3 < W && (W & 3) == 0 && (bs.rect & 3) == 0) *(uint32_t*)rp = rect4;
+            else for (int i = 0; i < 4 && x + i < W; ++i) rp[i] = (uint8_t)(rect4 >> (8 * i));
+        }
+    }
+}
+
 // ---- fused (rectify +) normalised-response prefilter -------------------------------------------------------
 // cv::StereoBM's NORMALIZED_RESPONSE prefilter: out = clip((c * scale_g - boxsum * scale_s) >> 10) + cap
 // with c = 4 I(x,y) + its 4 neighbours and boxsum over preFilterSize^2, replicate borders.  One block rectifies (or just
@@ -480,6 +679,15 @@ int launch_rectify_xsobel_pair(const uint8_t* srcL, const uint8_t* srcR, int sW,
     dim3 g((W + FTX - 1) / FTX, (H + FTY - 1) / FTY, 2 * nf);
     RectSide l{srcL, mapL, rectL, preL, cmL}, r{srcR, mapR, rectR, preR, cmR};
     BatchStrides bs{src_stride, rect_stride, pre_stride, tabL, tabR};
+    static const int use_quad = getenv("B200S_RECT_QUAD") ? atoi(getenv("B200S_RECT_QUAD")) : 1;
+    if (use_quad && mode != MAP_NONE) {
+        switch (mode) {
+        case MAP_ABS32: rectify_xsobel_quad_kernel<MAP_ABS32><<<g, QT_THREADS, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
+        case MAP_DELTA16: rectify_xsobel_quad_kernel<MAP_DELTA16><<<g, QT_THREADS, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
+        default: rectify_xsobel_quad_kernel<MAP_FLY><<<g, QT_THREADS, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
+        }
+        return 1;
+    }
     switch (mode) {
     case MAP_NONE: rectify_xsobel_kernel<MAP_NONE><<<g, FT_THREADS, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
     case MAP_ABS32: rectify_xsobel_kernel<MAP_ABS32><<<g, FT_THREADS, 0, st>>>(l, r, bs, sW, sH, pre_pitch, W, H, cap); break;
