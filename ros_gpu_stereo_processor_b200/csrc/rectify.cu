@@ -37,14 +37,17 @@ __device__ __forceinline__ void map_uv(const CamModel& c, int j, int i, float& u
     vf = __double2float_rn(v);
 }
 
+__device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }
+
+// The integer part saturates to int16 like cv::convertMaps' CV_16SC2 coordinates; it is applied here once, so that every
+// map entry (table or on the fly) already holds sat16(sx >> 5) * 32 + (sx & 31) and consumers may use entry >> 5 as it is.
 __device__ __forceinline__ int2 map_point(const CamModel& c, int j, int i)
 {
     float uf, vf;
     map_uv(c, j, i, uf, vf);
-    return make_int2(__float2int_rn(__fmul_rn(uf, 32.0f)), __float2int_rn(__fmul_rn(vf, 32.0f)));
+    const int sx = __float2int_rn(__fmul_rn(uf, 32.0f)), sy = __float2int_rn(__fmul_rn(vf, 32.0f));
+    return make_int2(sat16(sx >> 5) * 32 + (sx & 31), sat16(sy >> 5) * 32 + (sy & 31));
 }
-
-__device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }
 
 __device__ __forceinline__ int fetch1(const uint8_t* __restrict__ s, int sW, int sH, int x, int y, int ch, int c)
 {
@@ -326,7 +329,7 @@ constexpr int QT_THREADS = ((QT_NQ > 16 * FTY ? QT_NQ : 16 * FTY) + 31) / 32 * 3
 constexpr int QT_PITCH = 4 * QT_QPR + 4;                 // tile row stride in bytes (the Sobel phase reads two whole words past a quad)
 
 template <int MODE>
-__global__ void __launch_bounds__(QT_THREADS) rectify_xsobel_quad_kernel(RectSide sl, RectSide sr, BatchStrides bs, int sW, int sH,
+__global__ void __launch_bounds__(QT_THREADS, 6) rectify_xsobel_quad_kernel(RectSide sl, RectSide sr, BatchStrides bs, int sW, int sH,
                                                                          size_t ppitch, int W, int H, int cap)
 {
     static_assert(MODE != MAP_NONE, "the identity map keeps the per-pixel kernel");
@@ -345,12 +348,11 @@ __global__ void __launch_bounds__(QT_THREADS) rectify_xsobel_quad_kernel(RectSid
     const int ys = y < 0 ? 1 : (y >= H ? H - 2 : y);
     const bool rowok = qact && ys >= 0 && ys < H;
     int mx[4], my[4];
-    unsigned okm = 0;                                     // bit k: pixel xq + k is inside the image
+    // bit k: pixel xq + k is inside the image
+    const int klo = max(-xq, 0), khi = min(W - xq, 4);
+    const unsigned okm = rowok && khi > klo ? ((1u << khi) - 1u) & ~((1u << klo) - 1u) : 0u;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        mx[k] = my[k] = 0;
-        if (rowok && xq + k >= 0 && xq + k < W) okm |= 1u << k;
-    }
+    for (int k = 0; k < 4; ++k) mx[k] = my[k] = 0;
     if (okm == 0xFu && MODE == MAP_DELTA16 && !(W & 1)) {
         // xq is even and so is ys * W: the four 4-byte entries are two aligned 8-byte loads
         const uint2* mp = (const uint2*)((const uint32_t*)S.map + (size_t)ys * W + xq);
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(QT_THREADS) rectify_xsobel_quad_kernel(RectSid
     // source window of the tile (see rectify_xsobel_kernel); integer source coordinates, saturated like cv::remap's maps
     int X0[4], Y0[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { X0[k] = sat16(mx[k] >> 5); Y0[k] = sat16(my[k] >> 5); }
+    for (int k = 0; k < 4; ++k) { X0[k] = mx[k] >> 5; Y0[k] = my[k] >> 5; }      // map entries are saturated when they are made
     int xmn = INT_MAX, xmx = INT_MIN, ymn = INT_MAX, ymx = INT_MIN;
     if (okm == 0xFu) {
         xmn = min(min(X0[0], X0[1]), min(X0[2], X0[3])); xmx = max(max(X0[0], X0[1]), max(X0[2], X0[3]));
@@ -470,45 +472,53 @@ __global__ void __launch_bounds__(QT_THREADS) rectify_xsobel_quad_kernel(RectSid
         *(uint32_t*)&tile[ty][4 * tq] = out4;
     }
     __syncthreads();
-    // Sobel: thread = 4 adjacent pixels x .. x + 3, tile columns 4 t + 2 .. 4 t + 5 (column 0 is x0 - 2)
-    if (threadIdx.x < 16 * FTY) {
-        const int sy = threadIdx.x >> 4, tx = (threadIdx.x & 15) * 4;
+    // Sobel: thread = 4 adjacent pixels x .. x + 3 (tile columns 4 t + 2 .. 4 t + 5, column 0 is x0 - 2) of two rows: four
+    // tile rows give both, every row's horizontal differences are formed once
+    if (threadIdx.x < 8 * FTY) {
+        const int sy = (threadIdx.x >> 4) * 2, tx = (threadIdx.x & 15) * 4;
         const int x = x0 + tx, yy = y0 + sy;
         if (x < W && yy < H) {
-            const bool last_odd = (H & 1) && (yy == H - 1);
-            uint32_t de = 0, dO = 0, rect4 = 0;     // Sobel sums of pixels (0, 2) and (1, 3) as s16x2
+            uint32_t dE[4], dOd[4], rc[4];           // per tile row: differences of pixels (0, 2) and (1, 3) as s16x2, bytes x .. x+3
 #pragma unroll
-            for (int rr = 0; rr < 3; ++rr) {
+            for (int rr = 0; rr < 4; ++rr) {
                 const uint32_t w0 = *(const uint32_t*)&tile[sy + rr][tx], w1 = *(const uint32_t*)&tile[sy + rr][tx + 4];
                 const uint32_t lw = __funnelshift_r(w0, w1, 8);                       // bytes x-1 .. x+2
                 const uint32_t hi = __funnelshift_r(w0, w1, 24);                      // bytes x+1 .. x+4
                 const uint32_t le = lw & 0x00ff00ffu, lo = (lw >> 8) & 0x00ff00ffu;    // x-1, x+1 | x, x+2
                 const uint32_t he = hi & 0x00ff00ffu, ho = (hi >> 8) & 0x00ff00ffu;    // x+1, x+3 | x+2, x+4
-                uint32_t d_e = __vsub2(he, le), d_o = __vsub2(ho, lo);                 // pixels 0, 2 | pixels 1, 3
-                if (rr == 1) {
-                    d_e = __vadd2(d_e, d_e);
-                    d_o = __vadd2(d_o, d_o);
-                    rect4 = __funnelshift_r(w0, w1, 16);                               // bytes x .. x+3 of the centre row
-                }
-                de = __vadd2(de, d_e);
-                dO = __vadd2(dO, d_o);
+                dE[rr] = __vsub2(he, le);
+                dOd[rr] = __vsub2(ho, lo);
+                rc[rr] = __funnelshift_r(w0, w1, 16);
             }
             const uint32_t capw = (uint32_t)cap * 0x00010001u, ncapw = (uint32_t)(-cap & 0xffff) * 0x00010001u;
-            de = __vadd2(__vmins2(__vmaxs2(de, ncapw), capw), capw);
-            dO = __vadd2(__vmins2(__vmaxs2(dO, ncapw), capw), capw);
-            uint32_t pre4 = __byte_perm(de, dO, 0x6240);                               // p0 p1 p2 p3
-            if (last_odd || H <= 1) pre4 = (uint32_t)cap * 0x01010101u;
-            else if (x == 0 || x + 3 >= W - 1) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (x + i == 0 || x + i >= W - 1) pre4 = (pre4 & ~(0xffu << (8 * i))) | ((uint32_t)cap << (8 * i));
-            }
+            const bool edge_cols = x == 0 || x + 3 >= W - 1;
+            const bool vec_pre = x + 3 < W;                          // ppitch % 16 == 0 and x % 4 == 0
+            const bool vec_rect = x + 3 < W && (W & 3) == 0 && (bs.rect & 3) == 0;
             uint8_t* pp = S.pre + frame * bs.pre + (size_t)yy * ppitch + x;
-            if (x + 3 < W) *(uint32_t*)pp = pre4;                    // ppitch % 16 == 0 and x % 4 == 0
-            else for (int i = 0; i < 4 && x + i < W; ++i) pp[i] = (uint8_t)(pre4 >> (8 * i));
             uint8_t* rp = S.rect + frame * bs.rect + (size_t)yy * W + x;
-            if (x + 3 < W && (W & 3) == 0 && (bs.rect & 3) == 0) *(uint32_t*)rp = rect4;
-            else for (int i = 0; i < 4 && x + i < W; ++i) rp[i] = (uint8_t)(rect4 >> (8 * i));
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+                if (yy + o >= H) break;
+                uint32_t de = __vadd2(__vadd2(dE[o], dE[o + 2]), __vadd2(dE[o + 1], dE[o + 1]));
+                uint32_t dO = __vadd2(__vadd2(dOd[o], dOd[o + 2]), __vadd2(dOd[o + 1], dOd[o + 1]));
+                de = __vadd2(__vmins2(__vmaxs2(de, ncapw), capw), capw);
+                dO = __vadd2(__vmins2(__vmaxs2(dO, ncapw), capw), capw);
+                uint32_t pre4 = __byte_perm(de, dO, 0x6240);                           // p0 p1 p2 p3
+                const bool last_odd = (H & 1) && (yy + o == H - 1);
+                if (last_odd || H <= 1) pre4 = (uint32_t)cap * 0x01010101u;
+                else if (edge_cols) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (x + i == 0 || x + i >= W - 1) pre4 = (pre4 & ~(0xffu << (8 * i))) | ((uint32_t)cap << (8 * i));
+                }
+                const uint32_t rect4 = rc[o + 1];
+                if (vec_pre) *(uint32_t*)pp = pre4;
+                else for (int i = 0; i < 4 && x + i < W; ++i) pp[i] = (uint8_t)(pre4 >> (8 * i));
+                if (vec_rect) *(uint32_t*)rp = rect4;
+                else for (int i = 0; i < 4 && x + i < W; ++i) rp[i] = (uint8_t)(rect4 >> (8 * i));
+                pp += ppitch;
+                rp += W;
+            }
         }
     }
 }
