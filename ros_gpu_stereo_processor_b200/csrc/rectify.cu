@@ -329,7 +329,7 @@ constexpr int QT_THREADS = ((QT_NQ > 16 * FTY ? QT_NQ : 16 * FTY) + 31) / 32 * 3
 constexpr int QT_PITCH = 4 * QT_QPR + 4;                 // tile row stride in bytes (the Sobel phase reads two whole words past a quad)
 
 template <int MODE>
-__global__ void __launch_bounds__(QT_THREADS, 6) rectify_xsobel_quad_kernel(RectSide sl, RectSide sr, BatchStrides bs, int sW, int sH,
+__global__ void __launch_bounds__(QT_THREADS, MODE == MAP_FLY ? 4 : 6) rectify_xsobel_quad_kernel(RectSide sl, RectSide sr, BatchStrides bs, int sW, int sH,
                                                                          size_t ppitch, int W, int H, int cap)
 {
     static_assert(MODE != MAP_NONE, "the identity map keeps the per-pixel kernel");

@@ -6,6 +6,8 @@
 // bit-identical to cv2's (the 1e-5 bar of the north star needs FP64: pure f32 reaches 2e-5).
 #include "kernels.h"
 
+#include <cstdlib>
+
 #include <climits>
 
 namespace b200s {
@@ -294,6 +296,124 @@ __global__ void B200S_PACK_BOUNDS reproject_pack_kernel(const int16_t* __restric
     }
 }
 
+// The table path of the frame chain as a kernel of its own: PointCloud2 records (+ the float disparity plane) from the
+// per-disparity table, eight rows per warp, with the loads software-pipelined -- the disparity and the colour byte of row
+// r + 2 and the table entry of row r + 1 are in flight while row r is computed and stored (the generic kernel waited for two
+// dependent loads in every row: 49 % of its issue slots were busy).  Same operations per value as reproject_pack_kernel.
+constexpr int PL_RPW = 8;                        // consecutive image rows per warp
+constexpr uint32_t LUT_MISS_Z = 0x7f800002u;     // pipeline marker: disparity outside the table, take the arithmetic
+
+template <int STDQ>
+__device__ __forceinline__ float stdq_coord(double a, double rw, double q32, double q33, float dfv)
+{
+    const double q = __dmul_rn(a, rw);
+    const unsigned lo = (unsigned)__double2loint(q) & 0x1FFFFFFFu, hi = (unsigned)__double2hiint(q) & 0x7FFFFFFFu;
+    const bool safe = hi > 0x39B00000u && hi < 0x46300000u && (lo - 0x0FFFFFF0u) > 0x20u;
+    return __double2float_rn(safe ? q : __ddiv_rn(a, stdq_w<STDQ>(q32, q33, (double)dfv)));
+}
+
+template <int STDQ, int CH>
+__global__ void __launch_bounds__(256, 5) pack_lut_kernel(const int16_t* __restrict__ d16, int W, int H, double cxd,
+                                                       const double* __restrict__ Q, const uint8_t* __restrict__ color,
+                                                       uint8_t* __restrict__ pc2, size_t d_stride, size_t color_stride, const FrameDst fd,
+                                                       int dmin, float* __restrict__ df, const FrameDst fdf,
+                                                       const uint8_t* const* __restrict__ color_tab,
+                                                       const uint4* __restrict__ lut, int lut_n)
+{
+    const int lane = threadIdx.x & 31;
+    const int x0 = blockIdx.x * 32, x = x0 + lane;
+    const int yw = (blockIdx.y * 8 + (threadIdx.x >> 5)) * PL_RPW;      // first row of this warp
+    {
+        const int f = blockIdx.z;          // frame of the batch
+        d16 = (const int16_t*)((const uint8_t*)d16 + f * d_stride);
+        if (color_tab) color = color_tab[f];
+        else if (color) color += f * color_stride;
+        if (fd.use_list) pc2 = (uint8_t*)fd.list.p[f];
+        else pc2 += f * fd.stride;
+        if (fdf.use_list) df = (float*)fdf.list.p[f];
+        else if (df) df = (float*)((uint8_t*)df + f * fdf.stride);
+    }
+    if (yw >= H) return;
+    const double ax = (double)__double2float_rn(__dadd_rn(__dmul_rn(__ldg(Q + 0), (double)x), __ldg(Q + 3)));
+    const double q11 = __ldg(Q + 5), q13 = __ldg(Q + 7), q32 = __ldg(Q + 14), q33 = __ldg(Q + 15);
+    const bool xin = x < W;
+    const bool full_row = x0 + 32 <= W;
+    const int nrows = min(PL_RPW, H - yw);
+    auto load_dv = [&](int y) { return xin ? (int)__ldg(d16 + (size_t)y * W + x) : dmin; };
+    auto load_bgr = [&](int y) -> uint32_t {
+        if (!xin || !color) return 0u;
+        const size_t i = (size_t)y * W + x;
+        if (CH == 3) return (uint32_t)__ldg(color + i * 3) | ((uint32_t)__ldg(color + i * 3 + 1) << 8) | ((uint32_t)__ldg(color + i * 3 + 2) << 16);
+        const uint32_t g = __ldg(color + i);
+        return g | (g << 8) | (g << 16);
+    };
+    auto load_entry = [&](int dv) {
+        const unsigned li = (unsigned)(dv - dmin);
+        return li < (unsigned)lut_n ? __ldg(lut + li) : make_uint4(0u, 0u, LUT_MISS_Z, 0u);
+    };
+    // pipeline: A = loaded two rows ahead (disparity, colour), B = one row ahead (+ table entry)
+    int dvB = load_dv(yw);
+    uint32_t bgrB = load_bgr(yw);
+    int dvA = nrows > 1 ? load_dv(yw + 1) : dmin;
+    uint32_t bgrA = nrows > 1 ? load_bgr(yw + 1) : 0u;
+    uint4 eB = load_entry(dvB);
+#pragma unroll 2
+    for (int rr = 0; rr < nrows; ++rr) {
+        const int y = yw + rr;
+        const uint4 e = eB;
+        const int dv = dvB;
+        const uint32_t bgr = bgrB;
+        if (rr + 1 < nrows) {
+            dvB = dvA; bgrB = bgrA;
+            eB = load_entry(dvB);
+            if (rr + 2 < nrows) { dvA = load_dv(y + 2); bgrA = load_bgr(y + 2); }
+        }
+        uint32_t ux = 0x7fc00000u, uy = 0x7fc00000u, uz = 0x7fc00000u;
+        const size_t i = xin ? (size_t)y * W + x : 0;
+        if (e.z == LUT_MISS_Z) {
+            // outside the table (cannot happen for planes this library's matcher wrote): the arithmetic of reproject_pack_kernel
+            const float dfv = disp_to_float(dv, cxd);
+            if (df && xin) df[i] = dfv;
+            if (xin && dv != dmin) {
+                const double d = (double)dfv, minDisp = (double)disp_to_float(dmin, cxd);
+                const double az = (double)__double2float_rn(__dadd_rn(0.0, __ldg(Q + 11)));
+                const double ay = (double)__double2float_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(q11, (double)y)), q13));
+                const double w = stdq_w<STDQ>(q32, q33, d);
+                const double rw = __drcp_rn(w);
+                const float p0 = div_to_float(ax, w, rw), p1 = div_to_float(ay, w, rw);
+                float p2 = div_to_float(az, w, rw);
+                if (fabs(__dadd_rn(d, -minDisp)) <= (double)1.1920928955078125e-07f) p2 = 10000.0f;
+                if ((p2 != 10000.0f) && !isinf(p2)) { ux = __float_as_uint(p0); uy = __float_as_uint(p1); uz = __float_as_uint(p2); }
+            }
+        } else {
+            if (df && xin) df[i] = __uint_as_float(e.w);
+            if (xin && e.z != LUT_INVALID_Z) {
+                const double rw = __hiloint2double((int)e.y, (int)e.x);
+                const double ay = (double)__double2float_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(q11, (double)y)), q13));
+                const float dfv = __uint_as_float(e.w);
+                ux = __float_as_uint(stdq_coord<STDQ>(ax, rw, q32, q33, dfv));
+                uy = __float_as_uint(stdq_coord<STDQ>(ay, rw, q32, q33, dfv));
+                uz = e.z;
+            }
+        }
+        // records: see reproject_pack_kernel (two 512-byte store instructions per warp row)
+        if (full_row) {
+            uint4* row = (uint4*)(pc2 + ((size_t)y * W + x0) * 32);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int src = (lane >> 1) + 16 * k;
+                const uint32_t sx = __shfl_sync(0xffffffffu, ux, src), sy = __shfl_sync(0xffffffffu, uy, src);
+                const uint32_t sz = __shfl_sync(0xffffffffu, uz, src), sc = __shfl_sync(0xffffffffu, bgr, src);
+                row[32 * k + lane] = (lane & 1) ? make_uint4(sc, 0u, 0u, 0u) : make_uint4(sx, sy, sz, 0u);
+            }
+        } else if (xin) {
+            uint4* o = (uint4*)(pc2 + i * 32);
+            o[0] = make_uint4(ux, uy, uz, 0u);
+            o[1] = make_uint4(bgr, 0u, 0u, 0u);
+        }
+    }
+}
+
 // cv::cuda::drawColorDisp (opencv_contrib cudastereo, util.cu cvtPixel) on the integer disparity d = clamp(d16 >> 4, 0, 255),
 // the u8 value the reference's matcher plane holds (invalid = 0 -> hue 240 = blue).  Reference call site:
 // computeDisparityImage, src/GPUStereoProcessor.cpp:323-330.  "next" row 1 of the scope table; the upstream kernel is
@@ -355,6 +475,18 @@ int launch_reproject_pack(const int16_t* d16, int W, int H, double cxd, const do
 #define B200S_PACK_ARGS d16, W, H, cxd, Q, min_d16, color, ch, xyz, pc2, qmask, d_stride, color_stride, xyz_stride, \
                         frame_dst(pc2_stride, pc2_list), ex.dmin_const, ex.df, frame_dst(ex.df_stride, ex.df_list), ex.color_tab, \
                         use_lut ? lut : nullptr, use_lut ? ex.lut_n : 0
+    static const int lean = getenv("B200S_PACK_LEAN") ? atoi(getenv("B200S_PACK_LEAN")) : 1;
+    if (use_lut && lean && pc2 && (ch == 1 || ch == 3)) {
+        dim3 g2((W + 31) / 32, (H + 8 * PL_RPW - 1) / (8 * PL_RPW), nf);
+#define B200S_LEAN_ARGS d16, W, H, cxd, Q, color, pc2, d_stride, color_stride, frame_dst(pc2_stride, pc2_list), ex.dmin_const, ex.df, \
+                        frame_dst(ex.df_stride, ex.df_list), ex.color_tab, lut, ex.lut_n
+        if (stdq == 1 && ch == 3) pack_lut_kernel<1, 3><<<g2, 256, 0, st>>>(B200S_LEAN_ARGS);
+        else if (stdq == 1) pack_lut_kernel<1, 1><<<g2, 256, 0, st>>>(B200S_LEAN_ARGS);
+        else if (ch == 3) pack_lut_kernel<2, 3><<<g2, 256, 0, st>>>(B200S_LEAN_ARGS);
+        else pack_lut_kernel<2, 1><<<g2, 256, 0, st>>>(B200S_LEAN_ARGS);
+#undef B200S_LEAN_ARGS
+        return 1;
+    }
     if (stdq == 1 && use_lut) reproject_pack_kernel<1, true><<<g, 32 * RP_ROWS, 0, st>>>(B200S_PACK_ARGS);
     else if (stdq == 2 && use_lut) reproject_pack_kernel<2, true><<<g, 32 * RP_ROWS, 0, st>>>(B200S_PACK_ARGS);
     else if (stdq == 1) reproject_pack_kernel<1, false><<<g, 32 * RP_ROWS, 0, st>>>(B200S_PACK_ARGS);
