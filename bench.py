@@ -566,10 +566,10 @@ def run_ours(args, rank, world, local_rank):
         rect_bytes = (2 * n + 2 * 4 * n + 4 * n) if c["rectify"] else (2 * n + 2 * n)    # raw pair + 4 B/px map pair -> rect + prefiltered pair
         pack_bytes = 2 * n + n + 32 * n                                                  # s16 disparity + grey -> 32 B records
         roof_other = {
-            "rectify_prefilter": dict(kernel="rectify_xsobel_kernel (both sides, one launch)", bound="hbm", algorithmic_bytes=rect_bytes,
+            "rectify_prefilter": dict(kernel="rectify_xsobel_quad_kernel (both sides, one launch)", bound="hbm", algorithmic_bytes=rect_bytes,
                                       kernel_ms=stages["rectify_prefilter"] * 1e3, achieved=rect_bytes / stages["rectify_prefilter"] / 1e9,
                                       peak=hbm_peak, unit="GB/s", frac=rect_bytes / stages["rectify_prefilter"] / 1e9 / hbm_peak),
-            "reproject_pack": dict(kernel="reproject_pack_kernel", bound="hbm", algorithmic_bytes=pack_bytes,
+            "reproject_pack": dict(kernel="pack_lut_kernel (reproject + PointCloud2 records + float disparity; table path of reproject_pack_kernel)", bound="hbm", algorithmic_bytes=pack_bytes,
                                    kernel_ms=stages["reproject_pack"] * 1e3, achieved=pack_bytes / stages["reproject_pack"] / 1e9,
                                    peak=hbm_peak, unit="GB/s", frac=pack_bytes / stages["reproject_pack"] / 1e9 / hbm_peak),
             "to_float": dict(kernel="disparity_to_float_kernel", kernel_ms=stages["to_float"] * 1e3),
