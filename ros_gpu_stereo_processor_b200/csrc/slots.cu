@@ -177,7 +177,10 @@ static int ensure_reproject_lut(b200s_handle* h, Work& w, cudaStream_t st)
 {
     static const int use_lut = getenv("B200S_PACK_LUT") ? atoi(getenv("B200S_PACK_LUT")) : 1;
     const int dmin = (h->prm.min_disparity - 1) * 16;
-    const int n = (h->prm.num_disparities + 1) * 16 + 1;       // FILTERED .. the largest value the sub-pixel fit can round to
+    int n = (h->prm.num_disparities + 1) * 16 + 1;             // FILTERED .. the largest value the sub-pixel fit can round to
+    // test hook: a table that is too short, so that most disparities take the kernel's arithmetic for values outside it
+    static const int max_entries = getenv("B200S_PACK_LUT_ENTRIES") ? atoi(getenv("B200S_PACK_LUT_ENTRIES")) : 0;
+    if (max_entries > 0 && n > max_entries) n = max_entries;
     if (!use_lut || !h->model_ok || n > REPROJECT_LUT_MAX) {
         w.lut_n = 0;
         w.lut_key.clear();

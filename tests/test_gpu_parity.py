@@ -285,6 +285,45 @@ def test_fused_chain_matches_oracle_chain(cfg):
     proc.close()
 
 
+def test_pack_table_misses_take_the_same_arithmetic():
+    """The pack kernels take the disparity-only terms of a record from a table over the values the matcher can produce and
+    fall back to the per-pixel arithmetic for values outside it.  B200S_PACK_LUT_ENTRIES (a test hook) cuts the table to
+    100 entries so that most disparities miss it: same bytes, in the pipelined kernel and in the generic one."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys
+import numpy as np
+sys.path.insert(0, %r)
+import ros_gpu_stereo_processor_b200 as m
+from oracle import oracle as O, synth
+W, H, nd = 500, 260, 64
+Lraw, Rraw, cal = synth.synth_raw_pair(W, H, nd, seed=31)
+info = lambda c: dict(width=W, height=H, K=c["K"], D=c["D"], R=c["R"], P=c["P"])
+proc = m.GpuStereoProcessor(0)
+proc.initStereoModel(info(cal["left"]), info(cal["right"]))
+p = O.BMParams(numDisparities=nd, blockSize=9)
+proc.setParams(**p.as_dict())
+rl, rr = O.rectify(Lraw, **cal["left"]), O.rectify(Rraw, **cal["right"])
+d = O.stereobm_compute(rl, rr, p)
+df = O.disparity_to_float(d, cal["left"]["P"][2] - cal["right"]["P"][2])
+xyz = O.reproject(df, O.stereo_Q(cal["left"]["P"], cal["right"]["P"]))
+assert ((d.astype(int) - int(d.min())) >= 100).mean() > 0.1       # many valid disparities lie outside a 100-entry table
+for k in range(3):                                                  # eager run, graph capture, graph replay
+    out = proc.processPair(Lraw, Rraw, rectify=True, want=("disparity16", "disparity32f", "pointcloud2"))
+    assert np.array_equal(out["disparity16"], d)
+    assert np.array_equal(out["disparity32f"], df)
+    assert np.array_equal(out["pointcloud2"], O.pack_pointcloud2(xyz, rl))
+print("ok")
+""" % root
+    for lean in ("1", "0"):
+        env = dict(os.environ, B200S_PACK_LUT_ENTRIES="100", B200S_PACK_LEAN=lean)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600, cwd=root)
+        assert r.returncode == 0 and "ok" in r.stdout, (lean, r.stdout[-500:], r.stderr[-2000:])
+
+
 def test_graph_replay_gives_identical_frames():
     """The slot chain is captured into a CUDA graph on its second run and replayed afterwards; every replayed frame must
     equal the oracle chain, also after a parameter change (re-capture) and with graphs switched off."""
