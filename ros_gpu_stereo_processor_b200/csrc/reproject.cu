@@ -297,9 +297,9 @@ __global__ void B200S_PACK_BOUNDS reproject_pack_kernel(const int16_t* __restric
 }
 
 // The table path of the frame chain as a kernel of its own: PointCloud2 records (+ the float disparity plane) from the
-// per-disparity table, eight rows per warp, with the loads software-pipelined -- the disparity and the colour byte of row
-// r + 2 and the table entry of row r + 1 are in flight while row r is computed and stored (the generic kernel waited for two
-// dependent loads in every row: 49 % of its issue slots were busy).  Same operations per value as reproject_pack_kernel.
+// per-disparity table, eight rows per warp, with the loads hoisted -- the disparities and colour bytes of all eight rows are
+// requested up front and the table entry of row r + 1 is in flight while row r is computed and stored (the generic kernel
+// waited for two dependent loads in every row: 49 % of its issue slots were busy).  Same operations per value as reproject_pack_kernel.
 constexpr int PL_RPW = 8;                        // consecutive image rows per warp
 constexpr uint32_t LUT_MISS_Z = 0x7f800002u;     // pipeline marker: disparity outside the table, take the arithmetic
 
@@ -313,7 +313,7 @@ __device__ __forceinline__ float stdq_coord(double a, double rw, double q32, dou
 }
 
 template <int STDQ, int CH>
-__global__ void __launch_bounds__(256, 5) pack_lut_kernel(const int16_t* __restrict__ d16, int W, int H, double cxd,
+__global__ void __launch_bounds__(256, 4) pack_lut_kernel(const int16_t* __restrict__ d16, int W, int H, double cxd,
                                                        const double* __restrict__ Q, const uint8_t* __restrict__ color,
                                                        uint8_t* __restrict__ pc2, size_t d_stride, size_t color_stride, const FrameDst fd,
                                                        int dmin, float* __restrict__ df, const FrameDst fdf,
@@ -351,23 +351,24 @@ __global__ void __launch_bounds__(256, 5) pack_lut_kernel(const int16_t* __restr
         const unsigned li = (unsigned)(dv - dmin);
         return li < (unsigned)lut_n ? __ldg(lut + li) : make_uint4(0u, 0u, LUT_MISS_Z, 0u);
     };
-    // pipeline: A = loaded two rows ahead (disparity, colour), B = one row ahead (+ table entry)
-    int dvB = load_dv(yw);
-    uint32_t bgrB = load_bgr(yw);
-    int dvA = nrows > 1 ? load_dv(yw + 1) : dmin;
-    uint32_t bgrA = nrows > 1 ? load_bgr(yw + 1) : 0u;
-    uint4 eB = load_entry(dvB);
-#pragma unroll 2
-    for (int rr = 0; rr < nrows; ++rr) {
+    // all disparities and colour bytes of the warp's rows are requested first; the table entry of row r + 1 is requested
+    // before row r is computed and stored
+    int dvs[PL_RPW];
+    uint32_t bgrs[PL_RPW];
+#pragma unroll
+    for (int rr = 0; rr < PL_RPW; ++rr) {
+        dvs[rr] = rr < nrows ? load_dv(yw + rr) : dmin;
+        bgrs[rr] = rr < nrows ? load_bgr(yw + rr) : 0u;
+    }
+    uint4 eB = load_entry(dvs[0]);
+#pragma unroll
+    for (int rr = 0; rr < PL_RPW; ++rr) {
+        if (rr >= nrows) break;                              // warp-uniform
         const int y = yw + rr;
         const uint4 e = eB;
-        const int dv = dvB;
-        const uint32_t bgr = bgrB;
-        if (rr + 1 < nrows) {
-            dvB = dvA; bgrB = bgrA;
-            eB = load_entry(dvB);
-            if (rr + 2 < nrows) { dvA = load_dv(y + 2); bgrA = load_bgr(y + 2); }
-        }
+        const int dv = dvs[rr];
+        const uint32_t bgr = bgrs[rr];
+        if (rr + 1 < PL_RPW && rr + 1 < nrows) eB = load_entry(dvs[rr + 1]);
         uint32_t ux = 0x7fc00000u, uy = 0x7fc00000u, uz = 0x7fc00000u;
         const size_t i = xin ? (size_t)y * W + x : 0;
         if (e.z == LUT_MISS_Z) {
