@@ -559,6 +559,8 @@ def run_ours(args, rank, world, local_rank):
                          "single-pipe IADD3 rate exceeds 1; ncu_pipes is the hardware view of the same kernel (profiles/, committed capture)",
                     ncu_pipes=ncu_pipes,
                     kernel_ms=t_bm * 1e3, evals_effective_per_launch=eff * run.B, frames_per_launch=run.B, gevals_per_s=eff / t_bm / 1e9, traffic=traffic,
+                    per="kernel_ms, traffic and hbm.algorithmic_bytes are per frame: the launch time divided by frames_per_launch (CUDA events "
+                        "on the matcher's stream), the DRAM bytes of a one-frame launch under ncu",
                     hbm=dict(achieved=alg_bytes / t_bm / 1e9, peak=hbm_peak, unit="GB/s", frac=alg_bytes / t_bm / 1e9 / hbm_peak,
                              algorithmic_bytes=alg_bytes, peak_source=hbm_src),
                     int_peaks_tops=int_peaks, share_of_step=t_bm * FRAMES_PER_STEP / (main["_ms_dev"] * 1e-3 / args.steps))
